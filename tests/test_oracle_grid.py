@@ -1,0 +1,80 @@
+"""Grid sampler / aggregator restatement (oracle/grid.py): torchio's worked example, the patch-count table of
+SURVEY.md section 8 and the structural properties of the algorithm.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import grid
+
+
+def test_torchio_source_comment_example():
+    # torchio/data/sampler/grid.py: image 10, patch 5, overlap 2 -> [[0,5],[3,8],[5,10]]
+    assert grid.axis_starts(10, 5, 2) == [0, 3, 5]
+
+
+@pytest.mark.parametrize("size,patch,overlap,n", [
+    ((96, 96, 96), 64, 16, 8),            # config 1
+    ((304, 304, 240), 96, 48, 144),       # config 2, edge padded
+    ((256, 256, 192), 96, 48, 75),        # config 2, unpadded
+    ((272, 272, 272), 96, 48, 125),       # config 3, padded
+    ((224, 224, 224), 96, 48, 64),
+])
+def test_patch_counts(size, patch, overlap, n):
+    loc = grid.grid_locations(size, patch, overlap)
+    assert loc.shape == (n, 6) and loc.dtype == np.int64
+    assert (loc[:, 3:] - loc[:, :3] == patch).all()
+    assert loc.tolist() == sorted(loc.tolist())
+    assert (loc[:, :3] >= 0).all() and (loc[:, 3:] <= np.array(size)).all()
+
+
+def test_config2_starts():
+    loc = grid.grid_locations((304, 304, 240), 96, 48)
+    assert sorted(set(loc[:, 0])) == [0, 48, 96, 144, 192, 208]
+    assert sorted(set(loc[:, 2])) == [0, 48, 96, 144]
+
+
+def test_size_errors():
+    with pytest.raises(ValueError):
+        grid.grid_locations((10, 10, 10), 12, 0)
+    with pytest.raises(ValueError):
+        grid.grid_locations((10, 10, 10), 4, 4)
+    with pytest.raises(ValueError):
+        grid.grid_locations((10, 10, 10), 4, 1)
+
+
+@pytest.mark.parametrize("padding_mode", [None, "edge", 0.0])
+def test_average_of_identity_model_is_identity(padding_mode):
+    rng = np.random.default_rng(0)
+    vol = rng.standard_normal((2, 20, 17, 13)).astype(np.float32)
+    out = grid.sliding_window(vol, lambda p: p, (8, 8, 6), (4, 2, 2), padding_mode, "average", 5)
+    assert out.shape == vol.shape
+    np.testing.assert_allclose(out, vol, rtol=1e-6, atol=1e-6)
+
+
+def test_count_map_is_separable_and_covers():
+    size, patch, overlap = (20, 17, 13), (8, 8, 6), (4, 2, 2)
+    loc = grid.grid_locations(size, patch, overlap)
+    ones = np.ones((len(loc), 1, *patch), dtype=np.float32)
+    _, cnt = grid.aggregate_average(ones, loc, size)
+    assert cnt.min() >= 1
+    per_axis = []
+    for s, p, o in zip(size, patch, overlap):
+        c = np.zeros(s)
+        for st in grid.axis_starts(s, p, o):
+            c[st:st + p] += 1
+        per_axis.append(c)
+    sep = per_axis[0][:, None, None] * per_axis[1][None, :, None] * per_axis[2][None, None, :]
+    np.testing.assert_array_equal(cnt[0], sep)
+
+
+def test_crop_mode_padded_identity():
+    rng = np.random.default_rng(1)
+    vol = rng.standard_normal((1, 16, 16, 16)).astype(np.float32)
+    out = grid.sliding_window(vol, lambda p: p, 8, 4, "edge", "crop", 4)
+    np.testing.assert_array_equal(out, vol)
+
+
+def test_edge_padding_shape():
+    vol = np.arange(2 * 4 * 4 * 4, dtype=np.float32).reshape(2, 4, 4, 4)
+    pad = grid.pad_volume(vol, (2, 4, 0), "edge")
+    assert pad.shape == (2, 6, 8, 4)
+    assert pad[0, 0, 0, 0] == vol[0, 0, 0, 0] and pad[1, -1, -1, -1] == vol[1, -1, -1, -1]
