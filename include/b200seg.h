@@ -1,0 +1,169 @@
+/*
+ * b200seg.h -- C ABI of libb200seg.so, the sm_100a (B200) implementation of the sliding-window 3D U-Net
+ * inference path of efirdc/Segmentation-Pipeline.
+ *
+ * The reference has NO FFI for this path: everything is Python calling ATen.  The entry
+ * points below are therefore the operator set a binding for that path needs; each one names the reference
+ * call it replaces (paths relative to /root/reference/segmentation_pipeline/).  The reference-side binding
+ * (a ctypes stub) is shown in INTEGRATION.md; the host-side mirror that uses it lives in
+ * segmentation-pipeline_b200/segmentation_pipeline/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - the caller (PyTorch) owns every buffer; the library allocates nothing that outlives a call;
+ *   - every launch is asynchronous on the cudaStream_t passed as `stream` (a void* to keep this header free
+ *     of CUDA headers);
+ *   - return value: 0 = ok, negative = error; b200seg_last_error() gives the message (thread local);
+ *   - there is NO CPU fallback: unsupported shapes / dtypes return an error.
+ *
+ * Activation layout ("blocked"):  [N][C8][Z][Y][X][8]  -- channels in chunks of 8 (one 16-byte bf16 vector per
+ * voxel and chunk), spatial dims in the reference's (W, H, D) order named (Z, Y, X) here, X contiguous.
+ * A b200seg_view selects the chunk range [c8_off, c8_off + ceil(c/8)) of a buffer holding c8_total chunks per
+ * sample, which is how torch.cat along channels (models/modular_unet.py:97,
+ * models/nested_residual_unet.py:92-101) is expressed without a copy.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_VERSION 100
+
+enum { B200SEG_F32 = 0, B200SEG_BF16 = 1 };
+
+enum {
+    B200SEG_OK = 0,
+    B200SEG_ERR_ARG = -1,      /* invalid argument / unsupported configuration */
+    B200SEG_ERR_CUDA = -2,     /* a CUDA runtime or driver call failed */
+    B200SEG_ERR_DEVICE = -3    /* not an sm_100 device */
+};
+
+typedef struct b200seg_view {
+    void* data;        /* base of the whole buffer [N][c8_total][Z][Y][X][8] */
+    int32_t dtype;     /* B200SEG_F32 or B200SEG_BF16 */
+    int32_t n;         /* samples */
+    int32_t c;         /* logical channels in this view */
+    int32_t c8_total;  /* chunks per sample in the underlying buffer */
+    int32_t c8_off;    /* first chunk of this view */
+    int32_t z, y, x;   /* spatial extent */
+} b200seg_view;
+
+/* Fused epilogue of every convolution:
+ *   v   = acc * scale[c] + shift[c]                         (folded BatchNorm3d eval / conv bias)
+ *   v   = v > 0 ? v : v * slope[c]                          (ReLU: 0, LeakyReLU: negative_slope, none: 1)
+ *   v  += residual[c]                                       (Block3d: `res_conv(x_in) + x`, components.py:67-68)
+ * Channels [0, split) go to dst0, channels [split, cout) to dst1 (used to run conv0 and res_conv, which read
+ * the same input, as ONE contraction with N = 2*Cout).  With softmax != 0 the channel softmax of
+ * modular_unet.py:100 / nested_residual_unet.py:104 is applied and fp32 NCDHW probabilities are written to
+ * out_ncdhw instead (cout <= 16).  scale/shift/slope are fp32 device arrays of length >= round_up(cout, 8). */
+typedef struct b200seg_epilogue {
+    const float* scale;
+    const float* shift;
+    const float* slope;
+    b200seg_view dst0;
+    b200seg_view dst1;       /* data == NULL when unused */
+    int32_t split;           /* channels routed to dst0 (multiple of 8 when dst1 is used) */
+    b200seg_view residual;   /* data == NULL when unused; added to dst0 channels only */
+    float* out_ncdhw;        /* softmax / final output, fp32 [N][cout][Z][Y][X]; NULL when unused */
+    int32_t softmax;         /* 1: softmax over channels before writing out_ncdhw; 0: raw values */
+} b200seg_epilogue;
+
+/* ------------------------------------------------------------------------------------------------ misc */
+const char* b200seg_last_error(void);
+int b200seg_version(void);
+/* Fills sm_count / compute capability of the current device; returns B200SEG_ERR_DEVICE if it is not sm_100. */
+int b200seg_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------ layout
+ * collate_subjects' torch.stack + .to(device) result (utils/utils.py:75-85), fp32 NCDHW, into the blocked
+ * layout (pad channels of the last chunk are zero filled), and back. */
+int b200seg_pack_ncdhw(const float* src, b200seg_view dst, void* stream);
+int b200seg_unpack_ncdhw(b200seg_view src, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ convolutions
+ * Direct (CUDA-core, fp32 accumulate) 3-D convolution for any kernel size / stride / padding, regular or
+ * transposed; fp32 or bf16 blocked activations.  This is the fp32 path (logit tolerance 1e-5) and the path for
+ * layer shapes the tensor-core engine does not take.  Replaces nn.Conv3d (components.py:46,51;
+ * modular_unet.py:83), F.conv3d with the blurred 4^3 weight (components.py:119) and F.conv_transpose3d
+ * (components.py:152).
+ *   weight: fp32 [k^3][cin_phys][cout_pad]  with cin_phys = 8 * ceil(in.c / 8) ... see pack_direct_weight in
+ *   segmentation_pipeline/models/_plan.py; for transposed convs the taps are already those of the gather form. */
+int b200seg_conv3d_direct(b200seg_view in, const float* weight, int32_t cout, int32_t ksize, int32_t stride,
+                          int32_t pad, int32_t transposed, const b200seg_epilogue* epi, void* stream);
+
+/* Tensor-core engine (tcgen05 + TMEM + TMA), bf16 activations, fp32 accumulate.  mode selects the geometry:
+ *   B200SEG_TC_K3   : kernel 3, stride 1, padding 1            (nn.Conv3d of Block3d / out_conv)
+ *   B200SEG_TC_DOWN : kernel 4, stride 2, padding 1            (BlurConv3d with the blur folded, :111-121)
+ *   B200SEG_TC_UP   : transposed kernel 4, stride 2, padding 1 (BlurConvTranspose3d folded, :144-154)
+ * wpacked is the bf16 operand image produced by pack_tc_weight (segmentation_pipeline/models/_plan.py), laid out
+ * exactly as the kernel stages it in shared memory; wpacked_bytes is checked against the geometry.
+ * cout <= 80 per call (the host splits wider layers). */
+enum { B200SEG_TC_K3 = 0, B200SEG_TC_DOWN = 1, B200SEG_TC_UP = 2 };
+int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpacked, int64_t wpacked_bytes, int32_t cout,
+                      const b200seg_epilogue* epi, void* stream);
+/* Bytes of the packed operand image the engine expects for (mode, cin chunks, cout). */
+int64_t b200seg_conv3d_tc_wbytes(int32_t mode, int32_t cin_chunks, int32_t cout);
+
+/* ------------------------------------------------------------------------------------------------ resampling
+ * nn.AvgPool3d(2, 2, count_include_pad=False) (modular_unet.py:40-41, nested_residual_unet.py:67) and
+ * nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True) (modular_unet.py:38-39, :68), writing
+ * into a chunk range of the consumer's concat buffer. */
+int b200seg_avgpool2(b200seg_view in, b200seg_view out, void* stream);
+int b200seg_upsample_trilinear2(b200seg_view in, b200seg_view out, void* stream);
+/* Copy a view into a chunk range of another buffer (concat member that was not produced in place). */
+int b200seg_copy_view(b200seg_view in, b200seg_view out, void* stream);
+/* Channel softmax / StochasticMatrix softmax (components.py:170-185) on fp32 NCDHW data, in place.
+ * groups = 1 for nn.Softmax(dim=1); for StochasticMatrix groups = C, diag_bias added to the diagonal. */
+int b200seg_softmax_ncdhw(float* data, int64_t n, int32_t channels, int64_t voxels, int32_t sm_channels,
+                          float diag_bias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ grid sampling
+ * tio.GridSampler.__getitem__ + collate (prediction.py:132-138): crops `count` patches of the fp32 volume
+ * [C][W][H][D] at padded-grid locations (int32 rows i0,j0,k0,i1,j1,k1) straight into the
+ * blocked layout.  Padding (torchio Pad by overlap//2) is never materialised: border = per-axis pad width,
+ * pad_mode 0 = none (border ignored), 1 = 'edge' (clamp), 2 = constant pad_value.
+ * locations_host is a HOST array (it travels as a kernel argument, no device copy needed). */
+int b200seg_grid_extract(const float* volume, int32_t c, int32_t w, int32_t h, int32_t d,
+                         const int32_t* locations_host, int32_t count, const int32_t border[3], int32_t pad_mode,
+                         float pad_value, b200seg_view dst, void* stream);
+
+/* tio.GridAggregator.add_batch, 'average' mode (prediction.py:141): out[:, i0:i1, j0:j1, k0:k1] += patch for the
+ * `count` patches of one batch, IN BATCH ORDER for every voxel (owner-computes gather over the batch's bounding
+ * box -- no atomics, bit-identical to the sequential CPU loop).  out is fp32 [C][PW][PH][PD] (padded extent).
+ * patches: fp32 [count][C][p0][p1][p2]; locations_host: HOST int32 [count][6]. */
+int b200seg_overlap_add(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,
+                        const int32_t* locations_host, int32_t count, void* stream);
+/* 'crop' mode: assign the centre crop of each patch (GridAggregator.crop_batch). */
+int b200seg_overlap_crop(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,
+                         const int32_t* locations_host, int32_t count, const int32_t border[3],
+                         int32_t volume_padded, void* stream);
+
+/* tio.GridAggregator.get_output_tensor (prediction.py:143) fused with CustomArgMax
+ * (transforms/custom_label_transforms.py:267): probs = out / count (count = cw[i]*ch[j]*cd[k], the separable
+ * per-axis coverage, int32 device arrays of the padded extent; pass NULL for crop mode), cropped by `border`;
+ * writes fp32 probs [C][W][H][D] (may be NULL), int64 labels [W][H][D] (may be NULL) and uint8 labels
+ * (may be NULL).  argmax ties resolve to the lowest index. */
+int b200seg_finalize(const float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const int32_t* cw,
+                     const int32_t* ch, const int32_t* cd, const int32_t border[3], float* probs,
+                     int64_t* labels_i64, uint8_t* labels_u8, void* stream);
+
+/* torch.argmax(data, dim=0, keepdim=True) on fp32 [C][V] -> int64 [V] and/or uint8 [V]. */
+int b200seg_argmax(const float* probs, int32_t c, int64_t voxels, int64_t* labels_i64, uint8_t* labels_u8,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------ evaluator
+ * Single pass over two label maps -> num_classes x num_classes joint histogram cm[target][prediction] (int64,
+ * ACCUMULATED into cm so cohorts can be summed), from which TP/FP/TN/FN of segmentation_evaluator.py:69-77
+ * and the volumes of label_map_evaluator.py:77-81 follow exactly.  label_bytes = 1 (uint8) or 8 (int64).
+ * Values outside [0, num_classes) are ignored.  num_classes <= 64. */
+int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes, int64_t voxels,
+                      int32_t num_classes, int64_t* cm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

@@ -1,0 +1,288 @@
+"""ctypes binding of libb200seg.so (include/b200seg.h) for PyTorch tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every function below passes raw
+``data_ptr()`` values and the current CUDA stream handle through the C ABI.  There is no fallback: if the
+shared library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+from typing import Optional, Sequence
+
+import torch
+
+F32, BF16 = 0, 1
+TC_K3, TC_DOWN, TC_UP = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("B200SEG_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libb200seg.so"))
+
+
+class View(Structure):
+    """Mirror of ``b200seg_view``: a chunk range of a blocked activation buffer [N][C8][Z][Y][X][8]."""
+    _fields_ = [("data", c_void_p), ("dtype", c_int32), ("n", c_int32), ("c", c_int32), ("c8_total", c_int32),
+                ("c8_off", c_int32), ("z", c_int32), ("y", c_int32), ("x", c_int32)]
+
+
+class Epilogue(Structure):
+    """Mirror of ``b200seg_epilogue``."""
+    _fields_ = [("scale", c_void_p), ("shift", c_void_p), ("slope", c_void_p), ("dst0", View), ("dst1", View),
+                ("split", c_int32), ("residual", View), ("out_ncdhw", c_void_p), ("softmax", c_int32)]
+
+
+_lib = None
+
+_SIGNATURES = {
+    "b200seg_last_error": (c_char_p, []),
+    "b200seg_version": (c_int32, []),
+    "b200seg_device_info": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "b200seg_pack_ncdhw": (c_int32, [c_void_p, View, c_void_p]),
+    "b200seg_unpack_ncdhw": (c_int32, [View, c_void_p, c_void_p]),
+    "b200seg_conv3d_direct": (c_int32, [View, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        POINTER(Epilogue), c_void_p]),
+    "b200seg_conv3d_tc": (c_int32, [c_int32, View, c_void_p, c_int64, c_int32, POINTER(Epilogue), c_void_p]),
+    "b200seg_conv3d_tc_wbytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "b200seg_avgpool2": (c_int32, [View, View, c_void_p]),
+    "b200seg_upsample_trilinear2": (c_int32, [View, View, c_void_p]),
+    "b200seg_copy_view": (c_int32, [View, View, c_void_p]),
+    "b200seg_softmax_ncdhw": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_float, c_void_p]),
+    "b200seg_grid_extract": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32), c_int32,
+                                       POINTER(c_int32), c_int32, c_float, View, c_void_p]),
+    "b200seg_overlap_add": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, POINTER(c_int32),
+                                      c_int32, c_void_p]),
+    "b200seg_overlap_crop": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, POINTER(c_int32),
+                                       c_int32, POINTER(c_int32), c_int32, c_void_p]),
+    "b200seg_finalize": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                   POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200seg_argmax": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200seg_confusion": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Loads the C-ABI library and declares every prototype.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"libb200seg.so not found at {p}: build it with "
+                           f"`python segmentation-pipeline_b200/build.py` (there is no CPU / PyTorch fallback)")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().b200seg_last_error().decode()
+        raise RuntimeError(f"b200seg {what} failed ({rc}): {msg}")
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b200seg operates on CUDA tensors only (no CPU fallback)")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"unsupported activation dtype {dtype}")
+
+
+def launches() -> int:
+    """Number of kernel launches issued through this binding so far (for bench.py's gpu_launches)."""
+    return _LAUNCHES[0]
+
+
+_LAUNCHES = [0]
+
+
+class Blocked:
+    """A blocked activation buffer [N][C8][Z][Y][X][8] held in a torch tensor, plus view construction."""
+
+    def __init__(self, n: int, c8_total: int, z: int, y: int, x: int, dtype: torch.dtype, device) -> None:
+        self.n, self.c8_total, self.z, self.y, self.x = n, c8_total, z, y, x
+        self.dtype = dtype
+        self.tensor = torch.empty((n, c8_total, z, y, x, 8), dtype=dtype, device=device)
+
+    def view(self, c: int, c8_off: int = 0, n: Optional[int] = None) -> View:
+        if c8_off + (c + 7) // 8 > self.c8_total:
+            raise RuntimeError("view exceeds buffer")
+        return View(self.tensor.data_ptr(), dtype_code(self.dtype), self.n if n is None else n, c, self.c8_total,
+                    c8_off, self.z, self.y, self.x)
+
+
+NULL_VIEW = View(None, 0, 0, 0, 0, 0, 0, 0, 0)
+
+
+def device_info():
+    sm, major, minor = c_int32(), c_int32(), c_int32()
+    _check(load_library().b200seg_device_info(sm, major, minor), "device_info")
+    return sm.value, major.value, minor.value
+
+
+def pack_ncdhw(src: torch.Tensor, dst: View) -> None:
+    _require_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_pack_ncdhw(_ptr(src), dst, _stream()), "pack_ncdhw")
+
+
+def unpack_ncdhw(src: View, dst: torch.Tensor) -> None:
+    _require_cuda(dst)
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_unpack_ncdhw(src, _ptr(dst), _stream()), "unpack_ncdhw")
+
+
+def make_epilogue(scale: torch.Tensor, shift: torch.Tensor, slope: torch.Tensor, dst0: View = NULL_VIEW,
+                  dst1: View = NULL_VIEW, split: int = 0, residual: View = NULL_VIEW,
+                  out_ncdhw: Optional[torch.Tensor] = None, softmax: bool = False) -> Epilogue:
+    _require_cuda(scale, shift, slope, out_ncdhw)
+    return Epilogue(scale.data_ptr(), shift.data_ptr(), slope.data_ptr(), dst0, dst1, split, residual,
+                    0 if out_ncdhw is None else out_ncdhw.data_ptr(), 1 if softmax else 0)
+
+
+def conv3d_direct(inp: View, weight: torch.Tensor, cout: int, ksize: int, stride: int, pad: int, transposed: bool,
+                  epi: Epilogue) -> None:
+    _require_cuda(weight)
+    assert weight.dtype == torch.float32 and weight.is_contiguous()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_conv3d_direct(inp, _ptr(weight), cout, ksize, stride, pad, 1 if transposed else 0,
+                                                ctypes.byref(epi), _stream()), "conv3d_direct")
+
+
+def conv3d_tc(mode: int, inp: View, wpacked: torch.Tensor, cout: int, epi: Epilogue) -> None:
+    _require_cuda(wpacked)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_conv3d_tc(mode, inp, _ptr(wpacked), wpacked.numel() * wpacked.element_size(), cout,
+                                            ctypes.byref(epi), _stream()), "conv3d_tc")
+
+
+def conv3d_tc_wbytes(mode: int, cin_chunks: int, cout: int) -> int:
+    return int(load_library().b200seg_conv3d_tc_wbytes(mode, cin_chunks, cout))
+
+
+def avgpool2(inp: View, out: View) -> None:
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_avgpool2(inp, out, _stream()), "avgpool2")
+
+
+def upsample_trilinear2(inp: View, out: View) -> None:
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_upsample_trilinear2(inp, out, _stream()), "upsample_trilinear2")
+
+
+def copy_view(inp: View, out: View) -> None:
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_copy_view(inp, out, _stream()), "copy_view")
+
+
+def softmax_ncdhw(data: torch.Tensor, sm_channels: int = 0, diag_bias: float = 0.0) -> None:
+    """In-place channel softmax on fp32 (N, C, ...) data; ``sm_channels`` = C of a StochasticMatrix head."""
+    _require_cuda(data)
+    assert data.dtype == torch.float32 and data.is_contiguous()
+    n, c = data.shape[:2]
+    vox = data[0, 0].numel()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_softmax_ncdhw(_ptr(data), n, c, vox, sm_channels, float(diag_bias), _stream()),
+           "softmax_ncdhw")
+
+
+def _i32(values: Sequence[int]):
+    arr = (c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+def grid_extract(volume: torch.Tensor, locations: Sequence[Sequence[int]], border: Sequence[int], pad_mode: int,
+                 pad_value: float, dst: View) -> None:
+    """volume: fp32 (C, W, H, D) on the device; locations: host rows [i0,j0,k0,i1,j1,k1] in padded coordinates."""
+    _require_cuda(volume)
+    assert volume.dtype == torch.float32 and volume.is_contiguous() and volume.dim() == 4
+    c, w, h, d = volume.shape
+    flat = [int(v) for row in locations for v in row]
+    _LAUNCHES[0] += (len(locations) + 63) // 64
+    _check(load_library().b200seg_grid_extract(_ptr(volume), c, w, h, d, _i32(flat), len(locations), _i32(border),
+                                               pad_mode, float(pad_value), dst, _stream()), "grid_extract")
+
+
+def overlap_add(out: torch.Tensor, patches: torch.Tensor, locations: Sequence[Sequence[int]]) -> None:
+    """out: fp32 (C, PW, PH, PD) accumulated in place; patches: fp32 (B, C, p0, p1, p2); host locations."""
+    _require_cuda(out, patches)
+    assert out.dtype == torch.float32 and patches.dtype == torch.float32
+    assert out.is_contiguous() and patches.is_contiguous()
+    c, pw, ph, pd = out.shape
+    assert patches.shape[1] == c and patches.shape[0] >= len(locations)
+    flat = [int(v) for row in locations for v in row]
+    _LAUNCHES[0] += (len(locations) + 63) // 64
+    _check(load_library().b200seg_overlap_add(_ptr(out), c, pw, ph, pd, _ptr(patches), _i32(flat), len(locations),
+                                              _stream()), "overlap_add")
+
+
+def overlap_crop(out: torch.Tensor, patches: torch.Tensor, locations: Sequence[Sequence[int]],
+                 border: Sequence[int], volume_padded: bool) -> None:
+    _require_cuda(out, patches)
+    assert out.dtype == torch.float32 and patches.dtype == torch.float32
+    assert out.is_contiguous() and patches.is_contiguous()
+    c, pw, ph, pd = out.shape
+    flat = [int(v) for row in locations for v in row]
+    _LAUNCHES[0] += len(locations)
+    _check(load_library().b200seg_overlap_crop(_ptr(out), c, pw, ph, pd, _ptr(patches), _i32(flat), len(locations),
+                                               _i32(border), 1 if volume_padded else 0, _stream()), "overlap_crop")
+
+
+def finalize(out: torch.Tensor, counts, border: Sequence[int], probs: Optional[torch.Tensor],
+             labels_i64: Optional[torch.Tensor], labels_u8: Optional[torch.Tensor]) -> None:
+    """counts: None (crop mode) or three int32 device tensors with the per-axis coverage of the padded grid."""
+    _require_cuda(out, probs, labels_i64, labels_u8)
+    c, pw, ph, pd = out.shape
+    cw = ch = cd = None
+    if counts is not None:
+        cw, ch, cd = counts
+        for t in (cw, ch, cd):
+            assert t.dtype == torch.int32 and t.is_cuda
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_finalize(_ptr(out), c, pw, ph, pd, _ptr(cw), _ptr(ch), _ptr(cd), _i32(border),
+                                           _ptr(probs), _ptr(labels_i64), _ptr(labels_u8), _stream()), "finalize")
+
+
+def argmax(probs: torch.Tensor, labels_i64: Optional[torch.Tensor] = None,
+           labels_u8: Optional[torch.Tensor] = None) -> None:
+    """probs: fp32 (C, ...) contiguous; labels: int64 / uint8 tensors with prod(...) elements."""
+    _require_cuda(probs, labels_i64, labels_u8)
+    assert probs.dtype == torch.float32 and probs.is_contiguous()
+    c = probs.shape[0]
+    vox = probs[0].numel()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_argmax(_ptr(probs), c, vox, _ptr(labels_i64), _ptr(labels_u8), _stream()), "argmax")
+
+
+def confusion(pred: torch.Tensor, target: torch.Tensor, num_classes: int, cm: torch.Tensor) -> None:
+    """Accumulates the (num_classes x num_classes) int64 joint histogram cm[target][pred]."""
+    _require_cuda(pred, target, cm)
+    assert pred.dtype == target.dtype and pred.dtype in (torch.uint8, torch.int64)
+    assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
+    assert cm.dtype == torch.int64 and cm.numel() == num_classes * num_classes and cm.is_contiguous()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_confusion(_ptr(pred), _ptr(target), pred.element_size(), pred.numel(), num_classes,
+                                            _ptr(cm), _stream()), "confusion")

@@ -1,0 +1,740 @@
+// HBM-bound kernels of the sliding-window path: layout conversion, pooling / trilinear resampling, channel
+// softmax, grid patch extraction, overlap-add aggregation, finalize (+argmax) and the confusion histogram.
+// All of them are pure streaming kernels: one 16/32-byte vector per thread access, x (the contiguous axis)
+// mapped to threadIdx.x, grids sized from the element count.
+#include "common.cuh"
+
+namespace b200seg {
+
+static constexpr int kThreads = 256;
+static inline unsigned blocks_for(long long n, int per_block = kThreads) {
+    return static_cast<unsigned>((n + per_block - 1) / per_block);
+}
+
+// =========================================================================================== pack / unpack
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pack_ncdhw_kernel(const float* __restrict__ src, DView dst, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long vox = dst.chunk_stride;
+    const int c8 = (dst.c + 7) / 8;
+    long long v = t % vox;
+    int cc = static_cast<int>((t / vox) % c8);
+    int n = static_cast<int>(t / (vox * c8));
+    Vec8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = cc * 8 + j;
+        r.v[j] = c < dst.c ? __ldg(src + (static_cast<long long>(n) * dst.c + c) * vox + v) : 0.f;
+    }
+    store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, r);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+unpack_ncdhw_kernel(DView src, float* __restrict__ dst, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long vox = src.chunk_stride;
+    const int c8 = (src.c + 7) / 8;
+    long long v = t % vox;
+    int cc = static_cast<int>((t / vox) % c8);
+    int n = static_cast<int>(t / (vox * c8));
+    Vec8 r = load_vec8<T>(src.data, n * src.sample_stride + (src.c8_off + cc) * src.chunk_stride + v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = cc * 8 + j;
+        if (c < src.c) dst[(static_cast<long long>(n) * src.c + c) * vox + v] = r.v[j];
+    }
+}
+
+// =========================================================================================== avgpool / upsample / copy
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+avgpool2_kernel(DView in, DView out, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int c8 = (out.c + 7) / 8;
+    int x = static_cast<int>(t % out.x);
+    long long r = t / out.x;
+    int y = static_cast<int>(r % out.y);
+    r /= out.y;
+    int z = static_cast<int>(r % out.z);
+    r /= out.z;
+    int cc = static_cast<int>(r % c8);
+    int n = static_cast<int>(r / c8);
+    Vec8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                Vec8 v = load_vec8<T>(in.data, vox_index(in, n, cc, 2 * z + dz, 2 * y + dy, 2 * x + dx));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc.v[j] += v.v[j];
+            }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = acc.v[j] / 8.0f;
+    store_vec8<T>(out.data, vox_index(out, n, cc, z, y, x), acc);
+}
+
+__device__ __forceinline__ void lin_coeff(int dst, int in_size, int out_size, int& i0, int& i1, float& l0,
+                                          float& l1) {
+    // align_corners=True: src = dst * (in-1)/(out-1)
+    float scale = out_size > 1 ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.f;
+    float src = scale * static_cast<float>(dst);
+    i0 = static_cast<int>(src);
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - static_cast<float>(i0);
+    l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+upsample_trilinear2_kernel(DView in, DView out, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int c8 = (out.c + 7) / 8;
+    int x = static_cast<int>(t % out.x);
+    long long r = t / out.x;
+    int y = static_cast<int>(r % out.y);
+    r /= out.y;
+    int z = static_cast<int>(r % out.z);
+    r /= out.z;
+    int cc = static_cast<int>(r % c8);
+    int n = static_cast<int>(r / c8);
+    int z0, z1, y0, y1, x0, x1;
+    float lz0, lz1, ly0, ly1, lx0, lx1;
+    lin_coeff(z, in.z, out.z, z0, z1, lz0, lz1);
+    lin_coeff(y, in.y, out.y, y0, y1, ly0, ly1);
+    lin_coeff(x, in.x, out.x, x0, x1, lx0, lx1);
+    Vec8 p000 = load_vec8<T>(in.data, vox_index(in, n, cc, z0, y0, x0));
+    Vec8 p001 = load_vec8<T>(in.data, vox_index(in, n, cc, z0, y0, x1));
+    Vec8 p010 = load_vec8<T>(in.data, vox_index(in, n, cc, z0, y1, x0));
+    Vec8 p011 = load_vec8<T>(in.data, vox_index(in, n, cc, z0, y1, x1));
+    Vec8 p100 = load_vec8<T>(in.data, vox_index(in, n, cc, z1, y0, x0));
+    Vec8 p101 = load_vec8<T>(in.data, vox_index(in, n, cc, z1, y0, x1));
+    Vec8 p110 = load_vec8<T>(in.data, vox_index(in, n, cc, z1, y1, x0));
+    Vec8 p111 = load_vec8<T>(in.data, vox_index(in, n, cc, z1, y1, x1));
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        o.v[j] = lz0 * (ly0 * (lx0 * p000.v[j] + lx1 * p001.v[j]) + ly1 * (lx0 * p010.v[j] + lx1 * p011.v[j])) +
+                 lz1 * (ly0 * (lx0 * p100.v[j] + lx1 * p101.v[j]) + ly1 * (lx0 * p110.v[j] + lx1 * p111.v[j]));
+    }
+    store_vec8<T>(out.data, vox_index(out, n, cc, z, y, x), o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+copy_view_kernel(DView in, DView out, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int c8 = (out.c + 7) / 8;
+    long long v = t % out.chunk_stride;
+    int cc = static_cast<int>((t / out.chunk_stride) % c8);
+    int n = static_cast<int>(t / (out.chunk_stride * c8));
+    Vec8 r = load_vec8<T>(in.data, n * in.sample_stride + (in.c8_off + cc) * in.chunk_stride + v);
+    store_vec8<T>(out.data, n * out.sample_stride + (out.c8_off + cc) * out.chunk_stride + v, r);
+}
+
+// =========================================================================================== softmax (NCDHW fp32, in place)
+__global__ void __launch_bounds__(kThreads)
+softmax_ncdhw_kernel(float* __restrict__ data, int channels, long long voxels, int sm_channels, float diag_bias,
+                     long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    if (sm_channels <= 0) {
+        long long v = t % voxels;
+        long long n = t / voxels;
+        float* p = data + n * channels * voxels + v;
+        float m = -INFINITY;
+        for (int c = 0; c < channels; ++c) m = fmaxf(m, p[c * voxels]);
+        float s = 0.f;
+        for (int c = 0; c < channels; ++c) s += expf(p[c * voxels] - m);
+        for (int c = 0; c < channels; ++c) p[c * voxels] = expf(p[c * voxels] - m) / s;
+    } else {
+        // StochasticMatrix: channel k = i * C + j ; softmax over i for every j ; +diag_bias where i == j
+        const int C = sm_channels;
+        long long v = t % voxels;
+        long long r = t / voxels;
+        int j = static_cast<int>(r % C);
+        long long n = r / C;
+        float* p = data + n * channels * voxels + v;
+        float m = -INFINITY;
+        for (int i = 0; i < C; ++i) m = fmaxf(m, p[(i * C + j) * voxels] + (i == j ? diag_bias : 0.f));
+        float s = 0.f;
+        for (int i = 0; i < C; ++i) s += expf(p[(i * C + j) * voxels] + (i == j ? diag_bias : 0.f) - m);
+        for (int i = 0; i < C; ++i) {
+            float* q = p + (i * C + j) * voxels;
+            *q = expf(*q + (i == j ? diag_bias : 0.f) - m) / s;
+        }
+    }
+}
+
+// =========================================================================================== grid extraction
+struct LocBatch {
+    int count;
+    int loc[64][6];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+grid_extract_kernel(const float* __restrict__ vol, int C, int W, int H, int D, LocBatch lb, int b0, int bw, int bh,
+                    int bd, int pad_mode, float pad_value, DView dst, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int c8 = (dst.c + 7) / 8;
+    int k = static_cast<int>(t % dst.x);
+    long long r = t / dst.x;
+    int j = static_cast<int>(r % dst.y);
+    r /= dst.y;
+    int i = static_cast<int>(r % dst.z);
+    r /= dst.z;
+    int cc = static_cast<int>(r % c8);
+    int b = static_cast<int>(r / c8);
+    int si = lb.loc[b][0] + i - bw, sj = lb.loc[b][1] + j - bh, sk = lb.loc[b][2] + k - bd;
+    bool inside = si >= 0 && si < W && sj >= 0 && sj < H && sk >= 0 && sk < D;
+    if (pad_mode == 1) {
+        si = min(max(si, 0), W - 1);
+        sj = min(max(sj, 0), H - 1);
+        sk = min(max(sk, 0), D - 1);
+        inside = true;
+    }
+    Vec8 o;
+    const long long vox = 1LL * W * H * D;
+    const long long off = (static_cast<long long>(si) * H + sj) * D + sk;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int c = cc * 8 + q;
+        o.v[q] = (c < C) ? (inside ? __ldg(vol + c * vox + off) : pad_value) : 0.f;
+    }
+    store_vec8<T>(dst.data, vox_index(dst, b0 + b, cc, i, j, k), o);
+}
+
+// =========================================================================================== overlap-add
+// Owner-computes gather: thread (c, i, j, k4) of the batch bounding box sums, in batch order, every patch of
+// the batch that covers its voxels.  VEC = 4 uses 128-bit accesses (needs k extents/offsets multiple of 4).
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+overlap_add_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
+                   LocBatch lb, int p0, int p1, int p2, int bi0, int bj0, int bk0, int bw, int bh, int bd,
+                   long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int bdv = bd / VEC;
+    int kk = static_cast<int>(t % bdv) * VEC + bk0;
+    long long r = t / bdv;
+    int j = static_cast<int>(r % bh) + bj0;
+    r /= bh;
+    int i = static_cast<int>(r % bw) + bi0;
+    int c = static_cast<int>(r / bw);
+    float* o = out + ((static_cast<long long>(c) * PW + i) * PH + j) * PD + kk;
+    float acc[VEC];
+    if constexpr (VEC == 4) {
+        float4 v = *reinterpret_cast<const float4*>(o);
+        acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[VEC - 1] = v.w;
+    } else {
+        acc[0] = *o;
+    }
+    bool touched = false;
+    const long long pvox = 1LL * p0 * p1 * p2;
+    for (int b = 0; b < lb.count; ++b) {
+        int i0 = lb.loc[b][0], j0 = lb.loc[b][1], k0 = lb.loc[b][2];
+        if (i < i0 || i >= lb.loc[b][3] || j < j0 || j >= lb.loc[b][4] || kk < k0 || kk >= lb.loc[b][5]) continue;
+        const float* p = patches + (static_cast<long long>(b) * C + c) * pvox +
+                         (static_cast<long long>(i - i0) * p1 + (j - j0)) * p2 + (kk - k0);
+        if constexpr (VEC == 4) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(p));
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[VEC - 1] += v.w;
+        } else {
+            acc[0] += __ldg(p);
+        }
+        touched = true;
+    }
+    if (!touched) return;
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[VEC - 1]);
+    } else {
+        *o = acc[0];
+    }
+}
+
+// 'crop' mode: every patch assigns the centre crop of itself; patches are processed in order, later wins.
+__global__ void __launch_bounds__(kThreads)
+overlap_crop_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
+                    LocBatch lb, int b, int p0, int p1, int p2, int ci0, int cj0, int ck0, int cw, int chh, int cd,
+                    int li, int lj, int lk, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    int k = static_cast<int>(t % cd);
+    long long r = t / cd;
+    int j = static_cast<int>(r % chh);
+    r /= chh;
+    int i = static_cast<int>(r % cw);
+    int c = static_cast<int>(r / cw);
+    const long long pvox = 1LL * p0 * p1 * p2;
+    float v = __ldg(patches + (static_cast<long long>(b) * C + c) * pvox +
+                    (static_cast<long long>(li + i) * p1 + (lj + j)) * p2 + (lk + k));
+    out[((static_cast<long long>(c) * PW + ci0 + i) * PH + cj0 + j) * PD + ck0 + k] = v;
+}
+
+// =========================================================================================== finalize (+ argmax)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, const int* __restrict__ cw,
+                const int* __restrict__ ch, const int* __restrict__ cd, int b0, int b1, int b2, int W, int H, int D,
+                float* __restrict__ probs, long long* __restrict__ lab64, uint8_t* __restrict__ lab8,
+                long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int dv = D / VEC;
+    int k = static_cast<int>(t % dv) * VEC;
+    long long r = t / dv;
+    int j = static_cast<int>(r % H);
+    int i = static_cast<int>(r / H);
+    const long long pvox = 1LL * PW * PH * PD;
+    const long long vox = 1LL * W * H * D;
+    const long long src = (static_cast<long long>(i + b0) * PH + (j + b1)) * PD + (k + b2);
+    const long long dst = (static_cast<long long>(i) * H + j) * D + k;
+    float cnt[VEC];
+    if (cw != nullptr) {
+        int cij = __ldg(cw + i + b0) * __ldg(ch + j + b1);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) cnt[q] = static_cast<float>(cij * __ldg(cd + k + b2 + q));
+    }
+    float best[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        best[q] = -INFINITY;
+        arg[q] = 0;
+    }
+    for (int c = 0; c < C; ++c) {
+        float v[VEC];
+        if constexpr (VEC == 4) {
+            float4 f = __ldg(reinterpret_cast<const float4*>(out + c * pvox + src));
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[VEC - 1] = f.w;
+        } else {
+            v[0] = __ldg(out + c * pvox + src);
+        }
+        if (cw != nullptr) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) v[q] = v[q] / cnt[q];
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            // torch.argmax: first maximal index; NaN counts as maximal
+            if (v[q] > best[q] || (v[q] != v[q] && best[q] == best[q])) {
+                best[q] = v[q];
+                arg[q] = c;
+            }
+        }
+        if (probs != nullptr) {
+            if constexpr (VEC == 4) {
+                *reinterpret_cast<float4*>(probs + c * vox + dst) = make_float4(v[0], v[1], v[2], v[VEC - 1]);
+            } else {
+                probs[c * vox + dst] = v[0];
+            }
+        }
+    }
+    if (lab64 != nullptr) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) lab64[dst + q] = arg[q];
+    }
+    if (lab8 != nullptr) {
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<uchar4*>(lab8 + dst) = make_uchar4(arg[0], arg[1], arg[2], arg[VEC - 1]);
+        } else {
+            lab8[dst] = static_cast<uint8_t>(arg[0]);
+        }
+    }
+}
+
+// =========================================================================================== confusion histogram
+// Per-lane private columns in shared memory: hist[bin][lane] is only ever touched by lane `lane` of one warp,
+// so increments are plain read-modify-writes with bank == lane (no atomics, no conflicts).  One int64 global
+// atomic per bin per block at the end.
+template <typename L>
+__global__ void __launch_bounds__(kThreads)
+confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long long voxels, int nc,
+                 unsigned long long* __restrict__ cm, int warps_with_hist) {
+    extern __shared__ unsigned int hist[];  // [warp][bin][32]
+    const int bins = nc * nc;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    for (int i = threadIdx.x; i < warps_with_hist * bins * 32; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    unsigned int* mine = hist + (warp % warps_with_hist) * bins * 32 + lane;
+    const bool shared_cols = warps_with_hist < static_cast<int>(blockDim.x / 32);
+    constexpr int PER = 16 / sizeof(L);  // labels per 16-byte load
+    const long long nvec = voxels / PER;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long v = blockIdx.x * 1LL * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        uint4 pr = __ldg(reinterpret_cast<const uint4*>(pred) + v);
+        uint4 tr = __ldg(reinterpret_cast<const uint4*>(targ) + v);
+        const L* pp = reinterpret_cast<const L*>(&pr);
+        const L* tp = reinterpret_cast<const L*>(&tr);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            long long p = static_cast<long long>(pp[q]), tt = static_cast<long long>(tp[q]);
+            if (p >= 0 && p < nc && tt >= 0 && tt < nc) {
+                int bin = static_cast<int>(tt) * nc + static_cast<int>(p);
+                if (shared_cols) atomicAdd(mine + bin * 32, 1u);
+                else mine[bin * 32] += 1u;
+            }
+        }
+    }
+    // tail (voxels not a multiple of PER): first thread of the grid
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long long v = nvec * PER; v < voxels; ++v) {
+            long long p = static_cast<long long>(pred[v]), tt = static_cast<long long>(targ[v]);
+            if (p >= 0 && p < nc && tt >= 0 && tt < nc) {
+                int bin = static_cast<int>(tt) * nc + static_cast<int>(p);
+                if (shared_cols) atomicAdd(mine + bin * 32, 1u);
+                else mine[bin * 32] += 1u;
+            }
+        }
+    }
+    __syncthreads();
+    for (int bin = warp; bin < bins; bin += blockDim.x / 32) {
+        unsigned long long s = 0;
+        for (int w = 0; w < warps_with_hist; ++w) s += hist[(w * bins + bin) * 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s) atomicAdd(cm + bin, s);
+    }
+}
+
+// argmax over channels of [C][V] fp32
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+argmax_kernel(const float* __restrict__ probs, int C, long long voxels, long long* __restrict__ lab64,
+              uint8_t* __restrict__ lab8, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    long long v0 = t * VEC;
+    float best[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        best[q] = -INFINITY;
+        arg[q] = 0;
+    }
+    for (int c = 0; c < C; ++c) {
+        float v[VEC];
+        if constexpr (VEC == 4) {
+            float4 f = __ldg(reinterpret_cast<const float4*>(probs + c * voxels + v0));
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[VEC - 1] = f.w;
+        } else {
+            v[0] = __ldg(probs + c * voxels + v0);
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q)
+            if (v[q] > best[q] || (v[q] != v[q] && best[q] == best[q])) {
+                best[q] = v[q];
+                arg[q] = c;
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        if (lab64) lab64[v0 + q] = arg[q];
+        if (lab8) lab8[v0 + q] = static_cast<uint8_t>(arg[q]);
+    }
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+#define DISPATCH_DTYPE(dtype, ...)                          \
+    do {                                                    \
+        if ((dtype) == B200SEG_F32) {                       \
+            using T = float;                                \
+            __VA_ARGS__;                                    \
+        } else {                                            \
+            using T = __nv_bfloat16;                        \
+            __VA_ARGS__;                                    \
+        }                                                   \
+    } while (0)
+
+extern "C" {
+
+int b200seg_pack_ncdhw(const float* src, b200seg_view dst, void* stream) {
+    B200SEG_CHECK_ARG(src != nullptr, "pack_ncdhw: null src");
+    int rc = validate_view(dst, "pack_ncdhw dst");
+    if (rc) return rc;
+    DView d = make_dview(dst);
+    long long total = 1LL * d.n * ((d.c + 7) / 8) * d.chunk_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_DTYPE(dst.dtype, (pack_ncdhw_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(src, d, total)));
+    return check_launch("pack_ncdhw");
+}
+
+int b200seg_unpack_ncdhw(b200seg_view src, float* dst, void* stream) {
+    B200SEG_CHECK_ARG(dst != nullptr, "unpack_ncdhw: null dst");
+    int rc = validate_view(src, "unpack_ncdhw src");
+    if (rc) return rc;
+    DView d = make_dview(src);
+    long long total = 1LL * d.n * ((d.c + 7) / 8) * d.chunk_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_DTYPE(src.dtype, (unpack_ncdhw_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(d, dst, total)));
+    return check_launch("unpack_ncdhw");
+}
+
+static int check_pair(const b200seg_view& in, const b200seg_view& out, const char* what) {
+    int rc = validate_view(in, what);
+    if (rc) return rc;
+    rc = validate_view(out, what);
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(in.dtype == out.dtype, "%s: dtype mismatch", what);
+    B200SEG_CHECK_ARG(in.n == out.n && in.c == out.c, "%s: n/c mismatch (%d,%d) vs (%d,%d)", what, in.n, in.c, out.n,
+                      out.c);
+    return B200SEG_OK;
+}
+
+int b200seg_avgpool2(b200seg_view in, b200seg_view out, void* stream) {
+    int rc = check_pair(in, out, "avgpool2");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(out.z == in.z / 2 && out.y == in.y / 2 && out.x == in.x / 2, "avgpool2: out extent must be in/2");
+    DView di = make_dview(in), dout = make_dview(out);
+    long long total = 1LL * dout.n * ((dout.c + 7) / 8) * dout.chunk_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_DTYPE(in.dtype, (avgpool2_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(di, dout, total)));
+    return check_launch("avgpool2");
+}
+
+int b200seg_upsample_trilinear2(b200seg_view in, b200seg_view out, void* stream) {
+    int rc = check_pair(in, out, "upsample_trilinear2");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(out.z == in.z * 2 && out.y == in.y * 2 && out.x == in.x * 2,
+                      "upsample_trilinear2: out extent must be 2*in");
+    DView di = make_dview(in), dout = make_dview(out);
+    long long total = 1LL * dout.n * ((dout.c + 7) / 8) * dout.chunk_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_DTYPE(in.dtype, (upsample_trilinear2_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(di, dout, total)));
+    return check_launch("upsample_trilinear2");
+}
+
+int b200seg_copy_view(b200seg_view in, b200seg_view out, void* stream) {
+    int rc = check_pair(in, out, "copy_view");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(out.z == in.z && out.y == in.y && out.x == in.x, "copy_view: extent mismatch");
+    DView di = make_dview(in), dout = make_dview(out);
+    long long total = 1LL * dout.n * ((dout.c + 7) / 8) * dout.chunk_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_DTYPE(in.dtype, (copy_view_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(di, dout, total)));
+    return check_launch("copy_view");
+}
+
+int b200seg_softmax_ncdhw(float* data, int64_t n, int32_t channels, int64_t voxels, int32_t sm_channels,
+                          float diag_bias, void* stream) {
+    B200SEG_CHECK_ARG(data != nullptr && n > 0 && channels > 0 && voxels > 0, "softmax_ncdhw: bad arguments");
+    B200SEG_CHECK_ARG(sm_channels <= 0 || sm_channels * sm_channels == channels,
+                      "softmax_ncdhw: StochasticMatrix needs channels == C*C (C=%d, channels=%d)", sm_channels, channels);
+    long long total = n * voxels * (sm_channels > 0 ? sm_channels : 1);
+    softmax_ncdhw_kernel<<<blocks_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        data, channels, voxels, sm_channels, diag_bias, total);
+    return check_launch("softmax_ncdhw");
+}
+
+int b200seg_grid_extract(const float* volume, int32_t c, int32_t w, int32_t h, int32_t d,
+                         const int32_t* locations_host, int32_t count, const int32_t border[3], int32_t pad_mode,
+                         float pad_value, b200seg_view dst, void* stream) {
+    B200SEG_CHECK_ARG(volume != nullptr && locations_host != nullptr && count > 0, "grid_extract: bad arguments");
+    int rc = validate_view(dst, "grid_extract dst");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(dst.n >= count && dst.c == c, "grid_extract: dst holds %d samples / %d channels, need %d / %d", dst.n,
+                      dst.c, count, c);
+    B200SEG_CHECK_ARG(pad_mode >= 0 && pad_mode <= 2, "grid_extract: pad_mode %d", pad_mode);
+    int bw = pad_mode ? border[0] : 0, bh = pad_mode ? border[1] : 0, bd = pad_mode ? border[2] : 0;
+    DView dd = make_dview(dst);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int b0 = 0; b0 < count; b0 += 64) {
+        LocBatch lb;
+        lb.count = count - b0 < 64 ? count - b0 : 64;
+        for (int b = 0; b < lb.count; ++b) {
+            for (int q = 0; q < 6; ++q) lb.loc[b][q] = locations_host[(b0 + b) * 6 + q];
+            B200SEG_CHECK_ARG(lb.loc[b][3] - lb.loc[b][0] == dst.z && lb.loc[b][4] - lb.loc[b][1] == dst.y &&
+                                  lb.loc[b][5] - lb.loc[b][2] == dst.x,
+                              "grid_extract: location %d extent differs from the patch view", b0 + b);
+            if (pad_mode == 0) {
+                B200SEG_CHECK_ARG(lb.loc[b][0] >= 0 && lb.loc[b][3] <= w && lb.loc[b][1] >= 0 && lb.loc[b][4] <= h &&
+                                      lb.loc[b][2] >= 0 && lb.loc[b][5] <= d,
+                                  "grid_extract: location %d outside the volume", b0 + b);
+            }
+        }
+        long long total = 1LL * lb.count * ((c + 7) / 8) * dd.chunk_stride;
+        DISPATCH_DTYPE(dst.dtype, (grid_extract_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(
+                                      volume, c, w, h, d, lb, b0, bw, bh, bd, pad_mode, pad_value, dd, total)));
+        rc = check_launch("grid_extract");
+        if (rc) return rc;
+    }
+    return B200SEG_OK;
+}
+
+int b200seg_overlap_add(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,
+                        const int32_t* locations_host, int32_t count, void* stream) {
+    B200SEG_CHECK_ARG(out && patches && locations_host && count > 0 && c > 0, "overlap_add: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int p0 = locations_host[3] - locations_host[0], p1 = locations_host[4] - locations_host[1],
+              p2 = locations_host[5] - locations_host[2];
+    for (int b0 = 0; b0 < count; b0 += 64) {
+        LocBatch lb;
+        lb.count = count - b0 < 64 ? count - b0 : 64;
+        int bb[6] = {1 << 30, 1 << 30, 1 << 30, 0, 0, 0};
+        bool vec = (pd % 4 == 0) && (p2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
+        for (int b = 0; b < lb.count; ++b) {
+            const int32_t* l = locations_host + (b0 + b) * 6;
+            for (int q = 0; q < 6; ++q) lb.loc[b][q] = l[q];
+            B200SEG_CHECK_ARG(l[3] - l[0] == p0 && l[4] - l[1] == p1 && l[5] - l[2] == p2,
+                              "overlap_add: patches of one call must share one size");
+            B200SEG_CHECK_ARG(l[0] >= 0 && l[1] >= 0 && l[2] >= 0 && l[3] <= pw && l[4] <= ph && l[5] <= pd,
+                              "overlap_add: location %d outside the output", b0 + b);
+            for (int q = 0; q < 3; ++q) {
+                bb[q] = l[q] < bb[q] ? l[q] : bb[q];
+                bb[q + 3] = l[q + 3] > bb[q + 3] ? l[q + 3] : bb[q + 3];
+            }
+            vec = vec && (l[2] % 4 == 0);
+        }
+        const int bw = bb[3] - bb[0], bh = bb[4] - bb[1], bd = bb[5] - bb[2];
+        const float* pp = patches + 1LL * b0 * c * p0 * p1 * p2;
+        if (vec) {
+            long long total = 1LL * c * bw * bh * (bd / 4);
+            overlap_add_kernel<4><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0],
+                                                                        bb[1], bb[2], bw, bh, bd, total);
+        } else {
+            long long total = 1LL * c * bw * bh * bd;
+            overlap_add_kernel<1><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0],
+                                                                        bb[1], bb[2], bw, bh, bd, total);
+        }
+        int rc = check_launch("overlap_add");
+        if (rc) return rc;
+    }
+    return B200SEG_OK;
+}
+
+int b200seg_overlap_crop(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,
+                         const int32_t* locations_host, int32_t count, const int32_t border[3],
+                         int32_t volume_padded, void* stream) {
+    B200SEG_CHECK_ARG(out && patches && locations_host && count > 0 && c > 0, "overlap_crop: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int size[3] = {pw, ph, pd};
+    for (int b = 0; b < count; ++b) {
+        const int32_t* l = locations_host + b * 6;
+        int ini[3], fin[3], left[3], crop[3], psz[3];
+        for (int q = 0; q < 3; ++q) {
+            int b_ini = border[q], b_fin = border[q];
+            if (!volume_padded) {
+                if (l[q] == 0) b_ini = 0;
+                if (l[q + 3] == size[q]) b_fin = 0;
+            }
+            ini[q] = l[q] + b_ini;
+            fin[q] = l[q + 3] - b_fin;
+            psz[q] = l[q + 3] - l[q];
+            crop[q] = fin[q] - ini[q];
+            left[q] = (psz[q] - crop[q]) / 2;  // centre crop, as GridAggregator.crop_batch
+            B200SEG_CHECK_ARG(crop[q] > 0, "overlap_crop: empty crop");
+        }
+        LocBatch lb;
+        lb.count = 0;
+        long long total = 1LL * c * crop[0] * crop[1] * crop[2];
+        overlap_crop_kernel<<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, patches, lb, b, psz[0], psz[1],
+                                                                   psz[2], ini[0], ini[1], ini[2], crop[0], crop[1],
+                                                                   crop[2], left[0], left[1], left[2], total);
+        int rc = check_launch("overlap_crop");
+        if (rc) return rc;
+    }
+    return B200SEG_OK;
+}
+
+int b200seg_finalize(const float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const int32_t* cw,
+                     const int32_t* ch, const int32_t* cd, const int32_t border[3], float* probs,
+                     int64_t* labels_i64, uint8_t* labels_u8, void* stream) {
+    B200SEG_CHECK_ARG(out && c > 0 && pw > 0 && ph > 0 && pd > 0, "finalize: bad arguments");
+    B200SEG_CHECK_ARG((cw == nullptr) == (ch == nullptr) && (cw == nullptr) == (cd == nullptr),
+                      "finalize: give all three count arrays or none");
+    B200SEG_CHECK_ARG(labels_u8 == nullptr || c <= 256, "finalize: uint8 labels need <= 256 classes");
+    const int W = pw - 2 * border[0], H = ph - 2 * border[1], D = pd - 2 * border[2];
+    B200SEG_CHECK_ARG(W > 0 && H > 0 && D > 0, "finalize: border larger than the volume");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bool vec = (D % 4 == 0) && (pd % 4 == 0) && (border[2] % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+               (probs == nullptr || (reinterpret_cast<uintptr_t>(probs) & 15) == 0) &&
+               (labels_u8 == nullptr || (reinterpret_cast<uintptr_t>(labels_u8) & 3) == 0);
+    if (vec) {
+        long long total = 1LL * W * H * (D / 4);
+        finalize_kernel<4><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1],
+                                                                 border[2], W, H, D, probs,
+                                                                 reinterpret_cast<long long*>(labels_i64), labels_u8,
+                                                                 total);
+    } else {
+        long long total = 1LL * W * H * D;
+        finalize_kernel<1><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1],
+                                                                 border[2], W, H, D, probs,
+                                                                 reinterpret_cast<long long*>(labels_i64), labels_u8,
+                                                                 total);
+    }
+    return check_launch("finalize");
+}
+
+int b200seg_argmax(const float* probs, int32_t c, int64_t voxels, int64_t* labels_i64, uint8_t* labels_u8,
+                   void* stream) {
+    B200SEG_CHECK_ARG(probs && c > 0 && voxels > 0 && (labels_i64 || labels_u8), "argmax: bad arguments");
+    B200SEG_CHECK_ARG(labels_u8 == nullptr || c <= 256, "argmax: uint8 labels need <= 256 classes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (voxels % 4 == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0) {
+        long long total = voxels / 4;
+        argmax_kernel<4><<<blocks_for(total), kThreads, 0, s>>>(probs, c, voxels,
+                                                               reinterpret_cast<long long*>(labels_i64), labels_u8,
+                                                               total);
+    } else {
+        argmax_kernel<1><<<blocks_for(voxels), kThreads, 0, s>>>(probs, c, voxels,
+                                                                reinterpret_cast<long long*>(labels_i64), labels_u8,
+                                                                voxels);
+    }
+    return check_launch("argmax");
+}
+
+int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes, int64_t voxels,
+                      int32_t num_classes, int64_t* cm, void* stream) {
+    B200SEG_CHECK_ARG(pred && target && cm && voxels > 0, "confusion: bad arguments");
+    B200SEG_CHECK_ARG(label_bytes == 1 || label_bytes == 8, "confusion: label_bytes must be 1 or 8");
+    B200SEG_CHECK_ARG(num_classes >= 1 && num_classes <= 64, "confusion: num_classes %d not in [1,64]", num_classes);
+    B200SEG_CHECK_ARG((reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0,
+                      "confusion: label maps must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    B200SEG_CHECK_CUDA(cudaGetDevice(&dev));
+    B200SEG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int bins = num_classes * num_classes;
+    const int warps = kThreads / 32;
+    int warps_with_hist = warps;
+    while (warps_with_hist > 1 && 1LL * warps_with_hist * bins * 32 * 4 > 96 * 1024) warps_with_hist /= 2;
+    size_t smem = 1ULL * warps_with_hist * bins * 32 * 4;
+    B200SEG_CHECK_ARG(smem <= 200 * 1024, "confusion: histogram does not fit shared memory");
+    const long long per = label_bytes == 1 ? 16 : 2;
+    long long want = (voxels / per + kThreads - 1) / kThreads;
+    int per_sm = smem > 48 * 1024 ? 2 : 4;
+    unsigned grid = static_cast<unsigned>(want < 1LL * sms * per_sm ? (want > 0 ? want : 1) : 1LL * sms * per_sm);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (label_bytes == 1) {
+        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(confusion_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(smem)));
+        confusion_kernel<uint8_t><<<grid, kThreads, smem, s>>>(static_cast<const uint8_t*>(pred),
+                                                                static_cast<const uint8_t*>(target), voxels,
+                                                                num_classes,
+                                                                reinterpret_cast<unsigned long long*>(cm),
+                                                                warps_with_hist);
+    } else {
+        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(confusion_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(smem)));
+        confusion_kernel<long long><<<grid, kThreads, smem, s>>>(static_cast<const long long*>(pred),
+                                                                  static_cast<const long long*>(target), voxels,
+                                                                  num_classes,
+                                                                  reinterpret_cast<unsigned long long*>(cm),
+                                                                  warps_with_hist);
+    }
+    return check_launch("confusion");
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""SegmentationEvaluator -- same interface and float32 statistics as the reference's
+evaluators/segmentation_evaluator.py:56-102, but the voxel work is ONE pass of b200seg_confusion over the two
+label maps (an L x L joint histogram) instead of 2 compares + 8 boolean passes per label on the CPU.
+TP / FP / TN / FN are exact integers derived from the histogram; they are cast to float32 before the
+divisions exactly like the reference's ``.sum().float()`` (:74-77)."""
+from __future__ import annotations
+
+from typing import Dict, Sequence
+
+import torch
+
+from .evaluator import Evaluator
+from .labeled_tensor import LabeledTensor
+
+MAX_CLASSES = 64
+
+
+def _device_labels(image, device):
+    data = image["data"] if not hasattr(image, "data") else image.data
+    return data.to(device).contiguous()
+
+
+def confusion_counts(pred: torch.Tensor, target: torch.Tensor, label_values: Dict[str, int]):
+    """-> {label_name: (TP, FP, TN, FN)} as Python ints, computed on the device."""
+    import b200seg
+    device = pred.device if pred.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    num_classes = max(int(v) for v in label_values.values()) + 1
+    if num_classes > MAX_CLASSES:
+        raise NotImplementedError(f"label values up to {num_classes - 1}: the device histogram handles values "
+                                  f"below {MAX_CLASSES}")
+    pred = pred.to(device).contiguous()
+    target = target.to(device).contiguous()
+    if pred.dtype != target.dtype or pred.dtype not in (torch.uint8, torch.int64):
+        pred, target = pred.to(torch.int64), target.to(torch.int64)
+    if pred.numel() != target.numel():
+        raise RuntimeError("prediction and target label maps differ in size")
+    cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=device)
+    b200seg.confusion(pred, target, num_classes, cm)
+    cm = cm.cpu()
+    total = pred.numel()
+    out = {}
+    for name, value in label_values.items():
+        v = int(value)
+        tp = int(cm[v, v])
+        fp = int(cm[:, v].sum()) - tp
+        fn = int(cm[v, :].sum()) - tp
+        out[name] = (tp, fp, total - tp - fp - fn, fn)
+    return out
+
+
+class SegmentationEvaluator(Evaluator):
+    """Per-label TP/FP/TN/FN, Dice, Jaccard, precision, recall and volumes between two label maps that carry a
+    ``'label_values'`` ``{name: value}`` property.  Output: ``{'subject_stats': DataFrame,
+    'summary_stats': LabeledTensor}``."""
+
+    def __init__(
+            self,
+            prediction_label_map_name: str,
+            target_label_map_name: str,
+            stats_to_output: Sequence[str] = ('target_volume', 'prediction_volume',
+                                              'TP', 'FP', 'TN', 'FN', 'dice', 'precision', 'recall'),
+            summary_stats_to_output: Sequence[str] = ('mean', 'std', 'min', 'max'),
+    ):
+        self.prediction_label_map_name = prediction_label_map_name
+        self.target_label_map_name = target_label_map_name
+        self.stats_to_output = stats_to_output
+        self.summary_stats_to_output = summary_stats_to_output
+
+    def __call__(self, subjects):
+        label_values = subjects[0][self.prediction_label_map_name]['label_values']
+        label_names = list(label_values.keys())
+        subject_names = [subject['name'] for subject in subjects]
+        subject_stats = LabeledTensor(dim_names=['subject', 'label', 'stat'],
+                                      dim_keys=[subject_names, label_names, self.stats_to_output])
+        device = torch.device("cuda", torch.cuda.current_device())
+        for subject in subjects:
+            pred = _device_labels(subject[self.prediction_label_map_name], device)
+            target = _device_labels(subject[self.target_label_map_name], device)
+            counts = confusion_counts(pred, target, label_values)
+            for label_name in label_names:
+                TP, FP, TN, FN = (torch.tensor(float(c), dtype=torch.float32) for c in counts[label_name])
+                stats = {
+                    'target_volume': TP + FN,
+                    'prediction_volume': TP + FP,
+                    'TP': TP, 'FP': FP, 'TN': TN, 'FN': FN,
+                    'dice': 2 * TP / (2 * TP + FP + FN),
+                    'jaccard': TP / (TP + FP + FN),
+                    'precision': TP / (TP + FP),
+                    'recall': TP / (TP + FN),
+                }
+                for stat_name in self.stats_to_output:
+                    subject_stats[subject['name'], label_name, stat_name] = stats[stat_name].item()
+        summary_stats = subject_stats.compute_summary_stats(self.summary_stats_to_output)
+        return {'subject_stats': subject_stats.to_dataframe(), 'summary_stats': summary_stats}

@@ -1,0 +1,241 @@
+"""Predictors -- host-side mirror of the reference's segmentation_pipeline/prediction.py (Predictor :41-54,
+StandardPredict :57-102, PatchPredict :105-152, add_evaluation_labels :155-170) with the same constructor
+arguments, attributes and return values, driving libb200seg instead of torchio + ATen:
+
+  PatchPredict.predict       volume -> device once; patches are cut on the device straight into the network's
+                             blocked input buffer (b200seg_grid_extract, padding never materialised); the
+                             network runs as one native plan per patch batch; b200seg_overlap_add accumulates
+                             in the reference's patch order (bit-identical sums); b200seg_finalize divides by
+                             the separable coverage count, crops the padding and emits probabilities + labels.
+  add_evaluation_labels      argmax on the device (b200seg_argmax), ties -> lowest index, int64 (1, W, H, D).
+"""
+from __future__ import annotations
+
+import copy
+from abc import ABC, abstractmethod
+from typing import Any, Dict, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _tio
+from .grid import PatchGrid, triple
+from .models import _engine
+from .models.components import _NativeForward, StochasticMatrix
+from .utils import Config, collate_subjects
+
+LABELS_KEY = "_b200_labels"   # device uint8 label map stashed next to 'y_pred' by PatchPredict
+
+
+def _lib():
+    import b200seg
+    b200seg.load_library()
+    return b200seg
+
+
+def split_and_flip(x: torch.Tensor) -> torch.Tensor:
+    """Sagittal halves folded into the batch, second half mirrored (reference prediction.py:16-20)."""
+    halves = list(x.split(x.shape[2] // 2, dim=2))
+    halves[1] = halves[1].flip(2)
+    return torch.cat(halves, dim=0)
+
+
+def reverse_split_and_flip(x: torch.Tensor) -> torch.Tensor:
+    halves = list(x.split(x.shape[0] // 2, dim=0))
+    halves[1] = halves[1].flip(2)
+    return torch.cat(halves, dim=2)
+
+
+def apply_stochastic_matrix(y_pred, y_prior):
+    n, c = y_prior.shape[:2]
+    y_pred = y_pred.reshape(n, c, c, *y_prior.shape[2:])
+    return (y_pred * y_prior[:, None]).sum(dim=1)
+
+
+def _require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("the b200 predictors run on a CUDA device only (no CPU fallback)")
+    return device
+
+
+class Predictor(ABC, Config):
+    """Representation to get model predictions"""
+
+    @abstractmethod
+    def predict(
+        self,
+        model: nn.Module,
+        device: torch.device,
+        subjects: Sequence[Any],
+        label_attributes: Optional[Dict[str, Any]] = None,
+    ) -> Tuple[Sequence[Any], Dict[str, torch.Tensor]]:
+        """Creates predictions for subjects and adds the predictions as an image with name 'y_pred' and
+        batch with with key 'y_pred'"""
+        raise NotImplementedError()
+
+
+class StandardPredict(Predictor):
+    """ Creates predictions on whole images"""
+
+    def __init__(
+            self,
+            image_names: Sequence[str] = ("X",),
+            sagittal_split: bool = False,
+            refine_image: str = None,
+    ):
+        image_names = list(image_names)
+        if refine_image is not None and refine_image not in image_names:
+            image_names.append(refine_image)
+        self.image_names = image_names
+        self.sagittal_split = sagittal_split
+        self.refine_image = refine_image
+
+    def predict(self, model, device, subjects, label_attributes=None):
+        device = _require_cuda(device)
+        batch = collate_subjects(subjects, image_names=self.image_names, device=device)
+        label_attributes = {} if label_attributes is None else label_attributes
+        if self.sagittal_split:
+            y_pred = reverse_split_and_flip(model(split_and_flip(batch['X']).contiguous()))
+        else:
+            y_pred = model(batch["X"])
+        batch['y_pred'] = y_pred
+        out_subjects = []
+        for i, subject in enumerate(subjects):
+            image = _tio.make_label_map(y_pred[i].detach().cpu(), **copy.deepcopy(label_attributes))
+            subject.add_image(image, "y_pred")
+            out_subjects.append(_tio.enforce_consistent_affine(subject, "X"))
+        return out_subjects, batch
+
+
+class PatchPredict(Predictor):
+    """ Creates predictions on patches and aggregates"""
+
+    def __init__(
+        self,
+        image_names: Sequence[str] = ("X",),
+        patch_batch_size: int = 16,
+        patch_size=None,
+        patch_overlap=(0, 0, 0),
+        padding_mode: Union[str, float, None] = None,
+        overlap_mode: str = "average",
+    ):
+        self.image_names = image_names
+        self.patch_batch_size = patch_batch_size
+        self.patch_size = patch_size
+        self.patch_overlap = patch_overlap
+        self.padding_mode = padding_mode
+        self.overlap_mode = overlap_mode
+
+    # ------------------------------------------------------------------ device pipeline for one volume
+    def predict_volume(self, model: nn.Module, volume: torch.Tensor, want_probs: bool = True,
+                       want_labels: bool = True):
+        """volume: fp32 (C, W, H, D) already on the device.  Returns (probs fp32 (C_out, W, H, D) or None,
+        labels uint8 (W, H, D) or None), both on the device."""
+        lib = _lib()
+        if self.overlap_mode not in ("average", "crop"):
+            raise ValueError(f'Overlap mode must be "crop" or "average" but "{self.overlap_mode}" was passed')
+        if not volume.is_cuda:
+            raise RuntimeError("predict_volume expects the volume on the CUDA device")
+        volume = volume.detach().to(torch.float32).contiguous()
+        grid = PatchGrid(volume.shape[1:], self.patch_size, self.patch_overlap, self.padding_mode)
+        p0, p1, p2 = grid.patch_size
+        device = volume.device
+        native = isinstance(model, _NativeForward) and not isinstance(model, StochasticMatrix)
+        compiled = None
+        if native:
+            if model.training:
+                raise NotImplementedError("PatchPredict needs model.eval() (inference path only)")
+            precision = _engine._resolve_precision(model, volume)
+            compiled = _engine.compiled_for(model, precision, device)
+            if compiled.plan.out_scale != 0:
+                raise RuntimeError("PatchPredict needs a network whose output extent equals its input extent")
+        out = None
+        for locations in grid.batches(self.patch_batch_size):
+            b = len(locations)
+            if native:
+                in_buf = compiled.input_buffer(b, p0, p1, p2)
+                lib.grid_extract(volume, locations, grid.border, grid.pad_mode_code, grid.pad_value,
+                                 in_buf.view(volume.shape[0]))
+                y = compiled.run_blocked(b, p0, p1, p2)
+            else:
+                # arbitrary nn.Module (e.g. a TTA ensemble around native members): hand it NCDHW patches
+                staging = lib.Blocked(b, (volume.shape[0] + 7) // 8, p0, p1, p2, torch.float32, device)
+                lib.grid_extract(volume, locations, grid.border, grid.pad_mode_code, grid.pad_value,
+                                 staging.view(volume.shape[0]))
+                x = torch.empty((b, volume.shape[0], p0, p1, p2), dtype=torch.float32, device=device)
+                lib.unpack_ncdhw(staging.view(volume.shape[0]), x)
+                with torch.no_grad():
+                    y = model(x)
+                y = y.detach().to(torch.float32).contiguous()
+            if out is None:
+                out = torch.zeros((y.shape[1], *grid.padded_shape), dtype=torch.float32, device=device)
+            if self.overlap_mode == "average":
+                lib.overlap_add(out, y, locations)
+            else:
+                lib.overlap_crop(out, y, locations, [o // 2 for o in grid.patch_overlap], grid.volume_padded)
+        counts = None
+        if self.overlap_mode == "average":
+            counts = [torch.tensor(c, dtype=torch.int32, device=device) for c in grid.axis_counts()]
+        w, h, d = grid.spatial_shape
+        probs = torch.empty((out.shape[0], w, h, d), dtype=torch.float32, device=device) if want_probs else None
+        labels = torch.empty((w, h, d), dtype=torch.uint8, device=device) \
+            if want_labels and out.shape[0] <= 256 else None
+        lib.finalize(out, counts, grid.border, probs, None, labels)
+        return probs, labels
+
+    def predict(self, model, device, subjects, label_attributes=None):
+        device = _require_cuda(device)
+        label_attributes = {} if label_attributes is None else label_attributes
+        out_subjects = []
+        for subject in subjects:
+            volume = subject["X"]["data"]
+            with torch.no_grad():
+                probs, labels = self.predict_volume(model, volume.to(device, non_blocking=True))
+            image = _tio.make_label_map(probs.cpu(), **copy.deepcopy(label_attributes))
+            if labels is not None:
+                image[LABELS_KEY] = labels
+            subject.add_image(image, "y_pred")
+            out_subjects.append(_tio.enforce_consistent_affine(subject, "X"))
+        batch = collate_subjects(subjects, image_names=self.image_names, device=device)
+        batch["y_pred"] = torch.stack([subject["y_pred"]["data"] for subject in out_subjects])
+        return out_subjects, batch
+
+
+def _argmax_labels(image) -> torch.Tensor:
+    """(C, W, H, D) probabilities / one-hot -> (1, W, H, D) int64 on the CPU, computed on the device."""
+    data = image["data"]
+    if data.shape[0] == 1:
+        return data.long()
+    lib = _lib()
+    stash = image.get(LABELS_KEY) if hasattr(image, "get") else None
+    if stash is not None:
+        return stash.to(torch.int64).cpu()[None]
+    device = torch.device("cuda", torch.cuda.current_device())
+    probs = data.detach().to(device=device, dtype=torch.float32).contiguous()
+    labels = torch.empty(probs.shape[1:], dtype=torch.int64, device=device)
+    lib.argmax(probs, labels, None)
+    return labels.cpu()[None]
+
+
+def add_evaluation_labels(subjects: Sequence[Any]):
+    """Adds 'y_pred_eval' / 'y_eval' label maps (int64, (1, W, H, D)) next to 'y_pred' / 'y'.
+
+    The reference (prediction.py:155-170) inverts the subject's label-transform history; for the one-hot
+    targets every shipped config uses, that inverse is ``CustomArgMax``
+    (transforms/custom_label_transforms.py:264-272), which is what runs here, on the device.  Subjects whose
+    history contains other invertible label transforms need real torchio and are outside this path."""
+    for subject in subjects:
+        for name, eval_name in (("y_pred", "y_pred_eval"), ("y", "y_eval")):
+            if name not in subject:
+                continue
+            source = subject[name]
+            attributes = {k: copy.deepcopy(v) for k, v in dict(source).items()
+                          if k not in ("data", "affine", LABELS_KEY, "tensor", "path", "type", "stem")}
+            attributes["one_hot"] = False
+            image = _tio.make_label_map(_argmax_labels(source), affine=source["affine"], **attributes) \
+                if not _tio.HAVE_TORCHIO else _tio.make_label_map(_argmax_labels(source), affine=source.affine)
+            if _tio.HAVE_TORCHIO:
+                for k, v in attributes.items():
+                    image[k] = v
+            subject.add_image(image, eval_name)

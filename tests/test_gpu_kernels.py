@@ -1,0 +1,311 @@
+"""GPU parity tests of the individual libb200seg kernels against the CPU oracle (through the C ABI).
+
+Bit-exact for integer / index / byte work (extraction, overlap-add order, argmax, confusion counts); fp32
+kernels within 1e-5 (max|d| / max|ref|); the bf16 tensor-core engine against an fp32 CPU convolution of the
+same bf16-rounded operands within 1e-2 (output rounding to bf16 is 2^-9 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import evalstats, grid as ogrid
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import b200seg
+    b200seg.load_library()
+    sm, major, minor = b200seg.device_info()
+    assert major == 10
+    return b200seg
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def to_blocked(lib, x, dtype):
+    n, c, z, y, xx = x.shape
+    buf = lib.Blocked(n, (c + 7) // 8, z, y, xx, dtype, "cuda")
+    lib.pack_ncdhw(dev(x), buf.view(c))
+    return buf
+
+
+def from_blocked(lib, buf, c):
+    out = torch.empty((buf.n, c, buf.z, buf.y, buf.x), dtype=torch.float32, device="cuda")
+    lib.unpack_ncdhw(buf.view(c), out)
+    return out.cpu()
+
+
+# ----------------------------------------------------------------------------------------------- layout / resampling
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pack_unpack_roundtrip(lib, dtype):
+    x = torch.randn(2, 11, 5, 6, 7)
+    back = from_blocked(lib, to_blocked(lib, x, dtype), 11)
+    ref = x if dtype == torch.float32 else x.to(dtype).float()
+    assert torch.equal(back, ref)
+
+
+def test_pack_zero_fills_padding_channels(lib):
+    x = torch.randn(1, 3, 4, 4, 4)
+    buf = to_blocked(lib, x, torch.float32)
+    assert torch.equal(buf.tensor[0, 0, ..., 3:].cpu(), torch.zeros(4, 4, 4, 5))
+
+
+def test_avgpool_and_trilinear_match_torch(lib):
+    x = torch.randn(2, 16, 8, 6, 10)
+    src = to_blocked(lib, x, torch.float32)
+    dst = lib.Blocked(2, 2, 4, 3, 5, torch.float32, "cuda")
+    lib.avgpool2(src.view(16), dst.view(16))
+    assert rel_err(from_blocked(lib, dst, 16), F.avg_pool3d(x, 2, 2, count_include_pad=False)) <= 1e-6
+    up = lib.Blocked(2, 4, 16, 12, 20, torch.float32, "cuda")   # written into chunks [1, 3) of a wider buffer
+    lib.upsample_trilinear2(src.view(16), up.view(16, 1))
+    got = torch.empty(2, 16, 16, 12, 20, device="cuda")
+    lib.unpack_ncdhw(up.view(16, 1), got)
+    ref = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    assert rel_err(got.cpu(), ref) <= 2e-6
+
+
+def test_softmax_and_stochastic_matrix(lib):
+    from oracle import unet
+    x = torch.randn(2, 5, 3, 4, 5)
+    y = dev(x.clone())
+    lib.softmax_ncdhw(y)
+    assert rel_err(y.cpu(), torch.softmax(x, 1)) <= 1e-6
+    x = torch.randn(1, 9, 3, 3, 3)
+    y = dev(x.clone())
+    lib.softmax_ncdhw(y, 3, 1.5)
+    assert rel_err(y.cpu(), unet.stochastic_matrix(x, 3, 1.5)) <= 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- grid
+@pytest.mark.parametrize("padding_mode,overlap", [(None, (4, 2, 2)), ("edge", (4, 2, 2)), (0.5, (4, 4, 0))])
+def test_grid_extract_bit_exact(lib, padding_mode, overlap):
+    rng = np.random.default_rng(3)
+    vol = rng.standard_normal((3, 20, 17, 13)).astype(np.float32)
+    patch = (8, 8, 6)
+    padded = ogrid.pad_volume(vol, overlap, padding_mode)
+    loc = ogrid.grid_locations(padded.shape[1:], patch, overlap)
+    ref = ogrid.extract_patches(padded, loc)
+    border = [o // 2 for o in overlap]
+    mode = 0 if padding_mode is None else (1 if padding_mode == "edge" else 2)
+    buf = lib.Blocked(len(loc), 1, *patch, torch.float32, "cuda")
+    lib.grid_extract(dev(torch.from_numpy(vol)), loc.tolist(), border, mode,
+                     0.0 if padding_mode in (None, "edge") else padding_mode, buf.view(3))
+    got = from_blocked(lib, buf, 3).numpy()
+    np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("size,patch,overlap,pad", [
+    ((20, 17, 13), (8, 8, 6), (4, 2, 2), None),        # scalar path (odd extents)
+    ((32, 24, 40), (16, 16, 16), (8, 8, 8), "edge"),   # 128-bit path
+    ((24, 24, 24), (16, 16, 16), (8, 8, 8), None),
+])
+def test_overlap_add_and_finalize_bit_exact(lib, size, patch, overlap, pad):
+    rng = np.random.default_rng(4)
+    border = [o // 2 if pad is not None else 0 for o in overlap]
+    padded_shape = tuple(s + 2 * b for s, b in zip(size, border))
+    loc = ogrid.grid_locations(padded_shape, patch, overlap)
+    patches = rng.standard_normal((len(loc), 3, *patch)).astype(np.float32)
+    out_ref, cnt_ref = ogrid.aggregate_average(patches, loc, padded_shape)
+    probs_ref = ogrid.finalize(out_ref, cnt_ref, overlap, pad is not None)
+    out = torch.zeros((3, *padded_shape), device="cuda")
+    dp = dev(torch.from_numpy(patches))
+    for b0 in range(0, len(loc), 5):     # ragged batches, as PatchPredict feeds them
+        lib.overlap_add(out, dp[b0:b0 + 5].contiguous(), loc[b0:b0 + 5].tolist())
+    np.testing.assert_array_equal(out.cpu().numpy(), out_ref)
+    counts = []
+    for s, p, o in zip(padded_shape, patch, overlap):
+        c = np.zeros(s, np.int32)
+        for st in ogrid.axis_starts(s, p, o):
+            c[st:st + p] += 1
+        counts.append(dev(torch.from_numpy(c)))
+    probs = torch.empty((3, *size), device="cuda")
+    lab64 = torch.empty(size, dtype=torch.int64, device="cuda")
+    lab8 = torch.empty(size, dtype=torch.uint8, device="cuda")
+    lib.finalize(out, counts, border, probs, lab64, lab8)
+    np.testing.assert_array_equal(probs.cpu().numpy(), probs_ref)
+    ref_lab = evalstats.argmax_labels(probs_ref)[0]
+    np.testing.assert_array_equal(lab64.cpu().numpy(), ref_lab)
+    np.testing.assert_array_equal(lab8.cpu().numpy(), ref_lab.astype(np.uint8))
+
+
+def test_overlap_crop_matches_oracle(lib):
+    rng = np.random.default_rng(5)
+    for pad in (None, "edge"):
+        size, patch, overlap = (20, 16, 12), (8, 8, 6), (4, 2, 2)
+        border = [o // 2 if pad is not None else 0 for o in overlap]
+        padded_shape = tuple(s + 2 * b for s, b in zip(size, border))
+        loc = ogrid.grid_locations(padded_shape, patch, overlap)
+        patches = rng.standard_normal((len(loc), 2, *patch)).astype(np.float32)
+        ref = ogrid.aggregate_crop(patches, loc, padded_shape, overlap, pad is not None)
+        out = torch.zeros((2, *padded_shape), device="cuda")
+        lib.overlap_crop(out, dev(torch.from_numpy(patches)), loc.tolist(), [o // 2 for o in overlap], pad is not None)
+        np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+def test_argmax_ties_and_bit_exact(lib):
+    rng = np.random.default_rng(6)
+    for vox in (4 * 1000, 1003):
+        p = rng.integers(0, 4, size=(5, vox)).astype(np.float32)   # many ties
+        lab = torch.empty(vox, dtype=torch.int64, device="cuda")
+        lab8 = torch.empty(vox, dtype=torch.uint8, device="cuda")
+        lib.argmax(dev(torch.from_numpy(p)), lab, lab8)
+        np.testing.assert_array_equal(lab.cpu().numpy(), np.argmax(p, axis=0))
+        np.testing.assert_array_equal(lab8.cpu().numpy(), np.argmax(p, axis=0).astype(np.uint8))
+
+
+@pytest.mark.parametrize("dtype,nc,vox", [(torch.uint8, 2, 1 << 20), (torch.uint8, 10, 999_983),
+                                          (torch.int64, 17, 300_001), (torch.uint8, 40, 250_000)])
+def test_confusion_bit_exact(lib, dtype, nc, vox):
+    rng = np.random.default_rng(7)
+    p = rng.integers(0, nc + 2, size=vox)      # includes values outside [0, nc): must be ignored
+    t = rng.integers(0, nc + 2, size=vox)
+    cm = torch.zeros((nc, nc), dtype=torch.int64, device="cuda")
+    lib.confusion(dev(torch.from_numpy(p).to(dtype)), dev(torch.from_numpy(t).to(dtype)), nc, cm)
+    np.testing.assert_array_equal(cm.cpu().numpy(), evalstats.confusion_matrix(p, t, nc))
+    lib.confusion(dev(torch.from_numpy(p).to(dtype)), dev(torch.from_numpy(t).to(dtype)), nc, cm)   # accumulates
+    np.testing.assert_array_equal(cm.cpu().numpy(), 2 * evalstats.confusion_matrix(p, t, nc))
+
+
+# ----------------------------------------------------------------------------------------------- convolutions
+def _epi(lib, cout, dst=None, out=None, softmax=False, bias=None, slope=1.0, residual=None):
+    cpad = (cout + 7) // 8 * 8
+    scale = torch.ones(cpad)
+    shift = torch.zeros(cpad)
+    if bias is not None:
+        shift[:cout] = bias
+    sl = torch.ones(cpad)
+    sl[:cout] = slope
+    keep = (dev(scale), dev(shift), dev(sl))
+    epi = lib.make_epilogue(*keep, dst0=dst if dst is not None else lib.NULL_VIEW,
+                            residual=residual if residual is not None else lib.NULL_VIEW, out_ncdhw=out,
+                            softmax=softmax)
+    return epi, keep
+
+
+@pytest.mark.parametrize("k,stride,pad,transposed,ext", [(3, 1, 1, False, (5, 9, 7)), (4, 2, 1, False, (8, 6, 10)),
+                                                         (4, 2, 1, True, (3, 5, 4))])
+def test_conv_direct_fp32(lib, k, stride, pad, transposed, ext):
+    from segmentation_pipeline.models import _plan
+    g = torch.Generator().manual_seed(11)
+    cin, cout = 11, 13
+    x = torch.randn(2, cin, *ext, generator=g)
+    if transposed:
+        w = torch.randn(cin, cout, k, k, k, generator=g) * 0.1
+        ref = F.conv_transpose3d(x, w, stride=stride, padding=pad)
+    else:
+        w = torch.randn(cout, cin, k, k, k, generator=g) * 0.1
+        ref = F.conv3d(x, w, stride=stride, padding=pad)
+    bias = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(ref + bias.view(1, -1, 1, 1, 1), 0.1)
+    op = _plan.ConvOp({(3, False): 0, (4, False): 1, (4, True): 2}[(k, transposed)], _plan.Ref("in", 0, cin),
+                      [(0, cin)], w, np.ones(cout, np.float32), np.zeros(cout, np.float32), np.ones(cout, np.float32))
+    wd = dev(_plan.pack_direct_weight(op, 2))
+    src = to_blocked(lib, x, torch.float32)
+    dst = lib.Blocked(2, 2, *ref.shape[2:], torch.float32, "cuda")
+    epi, keep = _epi(lib, cout, dst=dst.view(cout), bias=bias, slope=0.1)
+    lib.conv3d_direct(src.view(cin), wd, cout, k, stride, pad, transposed, epi)
+    assert rel_err(from_blocked(lib, dst, cout), ref) <= 1e-5
+
+
+TC_CASES = [
+    # mode, cin, cout, extent (n, z, y, x)
+    (0, 16, 16, (1, 4, 16, 8)),       # one exact tile
+    (0, 24, 40, (2, 13, 20, 19)),     # ragged tiles, lone chunk, N spill, batch
+    (0, 2, 40, (1, 6, 18, 10)),       # first layer: 2 channels in one lone chunk
+    (0, 80, 80, (1, 12, 16, 16)),     # widest N, two z tiles
+    (0, 40, 8, (1, 5, 9, 9)),         # narrow output
+    (1, 16, 16, (1, 8, 20, 12)),
+    (1, 40, 40, (2, 12, 36, 20)),
+    (2, 16, 16, (1, 3, 5, 9)),
+    (2, 40, 40, (2, 7, 17, 11)),
+    (2, 80, 80, (1, 4, 6, 6)),
+]
+
+
+@pytest.mark.parametrize("mode,cin,cout,ext", TC_CASES)
+def test_conv_tc_matches_fp32_oracle(lib, mode, cin, cout, ext):
+    from segmentation_pipeline.models import _plan
+    g = torch.Generator().manual_seed(100 + mode * 31 + cin + cout)
+    n = ext[0]
+    x = torch.randn(n, cin, *ext[1:], generator=g).to(torch.bfloat16).float()
+    if mode == 2:
+        w = (torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.05).to(torch.bfloat16).float()
+        ref = F.conv_transpose3d(x, w, stride=2, padding=1)
+    elif mode == 1:
+        w = (torch.randn(cout, cin, 4, 4, 4, generator=g) * 0.05).to(torch.bfloat16).float()
+        ref = F.conv3d(x, w, stride=2, padding=1)
+    else:
+        w = (torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+        ref = F.conv3d(x, w, padding=1)
+    bias = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(ref.shape, generator=g).to(torch.bfloat16).float()
+    ref = F.relu(ref + bias.view(1, -1, 1, 1, 1)) + res
+    chunks = (cin + 7) // 8
+    phys = _plan.physical_weight(w, mode == 2, [(0, cin)], chunks, 0, cout)
+    packed = dev(_plan.pack_tc_weight(mode, phys, chunks, cout))
+    assert packed.numel() * 2 == lib.conv3d_tc_wbytes(mode, chunks, cout)
+    src = to_blocked(lib, x, torch.bfloat16)
+    rbuf = to_blocked(lib, res, torch.bfloat16)
+    c8 = (cout + 7) // 8
+    dst = lib.Blocked(n, c8 + 1, *ref.shape[2:], torch.bfloat16, "cuda")    # output lands in chunks [1, 1+c8)
+    dst.tensor.zero_()
+    epi, keep = _epi(lib, cout, dst=dst.view(cout, 1), bias=bias, slope=0.0, residual=rbuf.view(cout))
+    lib.conv3d_tc(mode, src.view(cin), packed, cout, epi)
+    torch.cuda.synchronize()
+    got = torch.empty(ref.shape, device="cuda")
+    lib.unpack_ncdhw(dst.view(cout, 1), got)
+    assert rel_err(got.cpu(), ref) <= 1e-2
+    assert dst.tensor[:, 0].abs().max().item() == 0          # neighbouring chunk untouched
+
+
+def test_conv_tc_softmax_head(lib):
+    from segmentation_pipeline.models import _plan
+    g = torch.Generator().manual_seed(77)
+    for cout in (2, 10):
+        x = torch.randn(2, 40, 7, 18, 9, generator=g).to(torch.bfloat16).float()
+        w = (torch.randn(cout, 40, 3, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+        bias = torch.randn(cout, generator=g)
+        ref = torch.softmax(F.conv3d(x, w, bias, padding=1), 1)
+        phys = _plan.physical_weight(w, False, [(0, 40)], 5, 0, cout)
+        packed = dev(_plan.pack_tc_weight(0, phys, 5, cout))
+        out = torch.empty(ref.shape, device="cuda")
+        epi, keep = _epi(lib, cout, out=out, softmax=True, bias=bias)
+        lib.conv3d_tc(0, to_blocked(lib, x, torch.bfloat16).view(40), packed, cout, epi)
+        assert (out.cpu() - ref).abs().max() <= 2e-5
+        assert torch.allclose(out.sum(1).cpu(), torch.ones(2, 7, 18, 9), atol=1e-5)
+
+
+def test_conv_tc_fused_two_destinations(lib):
+    """conv0 || res_conv as one contraction: channels [0,40) -> ReLU'd tensor, [40,80) -> bias-only tensor."""
+    from segmentation_pipeline.models import _plan
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(1, 16, 6, 16, 16, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(80, 16, 3, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+    bias = torch.randn(80, generator=g) * 0.1
+    full = F.conv3d(x, w, bias, padding=1)
+    phys = _plan.physical_weight(w, False, [(0, 16)], 2, 0, 80)
+    packed = dev(_plan.pack_tc_weight(0, phys, 2, 80))
+    d0 = lib.Blocked(1, 5, 6, 16, 16, torch.bfloat16, "cuda")
+    d1 = lib.Blocked(1, 5, 6, 16, 16, torch.bfloat16, "cuda")
+    slope = torch.ones(80)
+    slope[:40] = 0.0
+    keep = (dev(torch.ones(80)), dev(bias), dev(slope))
+    epi = lib.make_epilogue(*keep, dst0=d0.view(40), dst1=d1.view(40), split=40)
+    lib.conv3d_tc(0, to_blocked(lib, x, torch.bfloat16).view(16), packed, 80, epi)
+    assert rel_err(from_blocked(lib, d0, 40), F.relu(full[:, :40])) <= 1e-2
+    assert rel_err(from_blocked(lib, d1, 40), full[:, 40:]) <= 1e-2
+
+
+def test_errors_are_loud(lib):
+    x = lib.Blocked(1, 1, 4, 4, 4, torch.float32, "cuda")
+    with pytest.raises(RuntimeError, match="bf16"):
+        keep = (dev(torch.ones(8)), dev(torch.zeros(8)), dev(torch.ones(8)))
+        epi = lib.make_epilogue(*keep, dst0=x.view(8))
+        lib.conv3d_tc(0, x.view(8), dev(torch.zeros(16)), 8, epi)
+    with pytest.raises(RuntimeError):
+        lib.pack_ncdhw(torch.zeros(1, 1, 2, 2, 2), x.view(1))      # CPU tensor: no fallback

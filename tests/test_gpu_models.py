@@ -1,0 +1,229 @@
+"""GPU parity of whole networks and of the sliding-window predictor against the committed golden fixtures
+(produced by the reference's own modules) and the CPU oracle.  Tolerances are the ones BASELINE.json states:
+fp32 path max rel err <= 1e-5, bf16 path <= 2e-2 on the network outputs; labels >= 99.9 % agreement in bf16;
+counts / Dice bit-exact given identical labels."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import evalstats, grid as ogrid, unet
+from helpers import GOLDEN, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def build_model(meta):
+    from torch import nn
+    from segmentation_pipeline import models as M
+    if meta["class"] == "NestedResUNet":
+        return M.NestedResUNet(meta["input_channels"], meta["output_channels"], meta["filters"],
+                               dropout_p=meta.get("dropout_p", 0.0))
+    block = meta["block"]
+    bp = {"residual": block.get("residual", False)}
+    if block.get("norm") == "none":
+        bp["normalization_class"] = None
+    if block.get("norm") == "instance":
+        bp["normalization_class"] = nn.InstanceNorm3d
+    if block.get("act") == "leaky_relu":
+        bp["activation_class"] = nn.LeakyReLU
+        bp["activation_params"] = {"negative_slope": block["slope"]}
+    if block.get("conv") == "ws":
+        bp["conv_class"] = M.WSConv3d
+        bp["conv_params"] = {"kernel_size": 3, "padding": 1}
+    kw = {}
+    if meta["down"] == "blur":
+        kw.update(downsample_class=M.BlurConv3d, downsample_params={"kernel_size": 3, "stride": 2, "padding": 1},
+                  upsample_class=M.BlurConvTranspose3d,
+                  upsample_params={"kernel_size": 3, "stride": 2, "padding": 1, "output_padding": 0})
+    if meta["hypothesis"] == "identity":
+        kw.update(hypothesis_class=nn.Identity, hypothesis_params={})
+    return M.ModularUNet(meta["in_channels"], meta["out_channels"], meta["filters"], meta["depth"], block_params=bp,
+                         **kw)
+
+
+FP32_CASES = ["models_modular_blur", "models_modular_default", "models_modular_leaky_logits", "models_nested",
+              "models_nested_10class"]
+
+
+@pytest.mark.parametrize("name", FP32_CASES)
+def test_fp32_network_matches_reference_fixture(name):
+    from segmentation_pipeline.models import set_precision
+    meta, sd, x, y = load_case(name)
+    model = build_model(meta)
+    model.load_state_dict(sd, strict=True)
+    model.eval().cuda()
+    set_precision("fp32")
+    try:
+        with torch.no_grad():
+            out = model(x.cuda())
+    finally:
+        set_precision("auto")
+    assert out.shape == y.shape and out.dtype == torch.float32
+    assert rel_err(out.cpu(), y) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["models_modular_blur", "models_modular_default", "models_modular_leaky_logits",
+                                  "models_nested", "models_nested_10class"])
+def test_bf16_network_within_tolerance(name):
+    from segmentation_pipeline.models import set_precision
+    meta, sd, x, y = load_case(name)
+    model = build_model(meta)
+    model.load_state_dict(sd, strict=True)
+    model.eval().cuda()
+    set_precision("bf16")
+    try:
+        with torch.no_grad():
+            out = model(x.cuda())
+    finally:
+        set_precision("auto")
+    assert rel_err(out.cpu(), y) <= 2e-2
+    if meta["hypothesis"] == "softmax":
+        # label agreement, ignoring voxels whose top-2 margin is below the bf16 resolution of the logits
+        top2 = torch.topk(y, 2, dim=1).values
+        decided = (top2[:, 0] - top2[:, 1]) > 0.05
+        agree = (out.cpu().argmax(1) == y.argmax(1))[decided].float().mean().item()
+        assert agree >= 0.999
+
+
+def test_autocast_selects_bf16_path():
+    meta, sd, x, y = load_case("models_modular_blur")
+    model = build_model(meta)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model(x.cuda())
+    assert out.dtype == torch.float32
+    assert 1e-7 < rel_err(out.cpu(), y) <= 2e-2     # really the bf16 path, and within tolerance
+
+
+def test_unsupported_and_training_mode_raise():
+    from torch import nn
+    meta, sd, x, y = load_case("models_modular_ws_instnorm")
+    model = build_model(meta)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    with pytest.raises(NotImplementedError):
+        model(x.cuda())           # InstanceNorm3d is not lowered: loud error, no silent ATen path
+    meta, sd, x, y = load_case("models_modular_default")
+    model = build_model(meta).cuda().train()
+    with pytest.raises(NotImplementedError):
+        model(x.cuda())
+    with pytest.raises(RuntimeError):
+        model.eval()(x)           # CPU tensor
+
+
+def test_components_forward():
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.models import set_precision
+    z = np.load(f"{GOLDEN}/components.npz")
+    t = lambda k: torch.from_numpy(z[k])
+    set_precision("fp32")
+    try:
+        bc = M.BlurConv3d(8, 8, kernel_size=3, stride=2, padding=1)
+        bc.weight.data.copy_(t("blur_w"))
+        assert rel_err(bc.eval().cuda()(t("blur_x").cuda()).cpu(), t("blur_y")) <= 1e-5
+        bt = M.BlurConvTranspose3d(8, 8, kernel_size=3, stride=2, padding=1, output_padding=0)
+        bt.weight.data.copy_(t("blurT_w"))
+        assert rel_err(bt.eval().cuda()(t("blur_x").cuda()).cpu(), t("blurT_y")) <= 1e-5
+        sm = M.StochasticMatrix(2, diag_bias=1.5)
+        assert rel_err(sm(t("sm_x").cuda()).cpu(), t("sm_y")) <= 1e-6
+        # ensembles around a native member
+        base = M.ModularUNet(1, 2, [8, 8], 2)
+        base.load_state_dict({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ens_sd/")})
+        base.eval().cuda()
+        x = t("ens_x").cuda()
+        with torch.no_grad():
+            assert rel_err(M.EnsembleFlips(base, "mean")(x).cpu(), t("ens_flips_mean")) <= 1e-5
+            assert rel_err(M.EnsembleOrientations(base, "mean")(x).cpu(), t("ens_orient_mean")) <= 1e-5
+            maj = M.EnsembleFlips(base, "majority")(x).cpu()
+        assert (maj.numpy() == z["ens_flips_majority"]).mean() >= 0.999
+    finally:
+        set_precision("auto")
+
+
+# ----------------------------------------------------------------------------------------------- predictors
+def _small_model():
+    meta, sd, _, _ = load_case("models_modular_blur")
+    model = build_model(meta)
+    model.load_state_dict(sd)
+    return meta, sd, model.eval().cuda()
+
+
+@pytest.mark.parametrize("padding_mode,overlap_mode", [(None, "average"), ("edge", "average"), ("edge", "crop")])
+def test_patch_predict_matches_oracle_sliding_window(padding_mode, overlap_mode):
+    from segmentation_pipeline import _tio
+    from segmentation_pipeline.models import set_precision
+    from segmentation_pipeline.prediction import PatchPredict, add_evaluation_labels
+    meta, sd, model = _small_model()
+    g = torch.Generator().manual_seed(21)
+    vol = torch.randn(2, 40, 36, 28, generator=g)
+    ref = ogrid.sliding_window(vol.numpy(), lambda p: unet.modular_unet_forward(sd, torch.from_numpy(p), meta).numpy(),
+                               (16, 16, 16), (8, 8, 4), padding_mode, overlap_mode, patch_batch_size=5)
+    subject = _tio.Subject(X=_tio.ScalarImage(tensor=vol), name="s0")
+    predictor = PatchPredict(patch_batch_size=5, patch_size=(16, 16, 16), patch_overlap=(8, 8, 4),
+                             padding_mode=padding_mode, overlap_mode=overlap_mode)
+    set_precision("fp32")
+    try:
+        subjects, batch = predictor.predict(model, torch.device("cuda"), [subject], {"label_values": {"lesion": 1}})
+    finally:
+        set_precision("auto")
+    y_pred = subjects[0]["y_pred"]
+    assert y_pred["data"].device.type == "cpu" and y_pred["label_values"] == {"lesion": 1}
+    assert batch["X"].is_cuda and batch["y_pred"].shape == (1, 2, 40, 36, 28)
+    assert rel_err(y_pred["data"], torch.from_numpy(ref)) <= 1e-5
+    add_evaluation_labels(subjects)
+    lab = subjects[0]["y_pred_eval"]["data"]
+    assert lab.dtype == torch.int64 and lab.shape == (1, 40, 36, 28)
+    # labels are the argmax of the probabilities we returned, bit-exactly (ties -> lowest index)
+    np.testing.assert_array_equal(lab.numpy(), evalstats.argmax_labels(y_pred["data"].numpy()))
+
+
+def test_patch_predict_config_attributes():
+    from segmentation_pipeline.prediction import PatchPredict, StandardPredict
+    p = PatchPredict(patch_batch_size=32, patch_size=96, patch_overlap=12, padding_mode=None,
+                     overlap_mode='average', image_names=['X'])
+    assert p.get_config() == dict(image_names=['X'], patch_batch_size=32, patch_size=96, patch_overlap=12,
+                                  padding_mode=None, overlap_mode='average')
+    assert StandardPredict(sagittal_split=True).get_config()["sagittal_split"] is True
+
+
+def test_standard_predict_sagittal_split():
+    from segmentation_pipeline import _tio, models as M
+    from segmentation_pipeline.models import set_precision
+    from segmentation_pipeline.prediction import StandardPredict
+    meta, sd, x, _ = load_case("models_nested")
+    model = M.NestedResUNet(3, 2, 8, dropout_p=0.2)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    g = torch.Generator().manual_seed(22)
+    vols = [torch.randn(3, 32, 16, 8, generator=g) for _ in range(2)]
+    ref = unet.reverse_split_and_flip(unet.nested_res_unet_forward(sd, unet.split_and_flip(torch.stack(vols))))
+    subjects = [_tio.Subject(X=_tio.ScalarImage(tensor=v), name=f"s{i}") for i, v in enumerate(vols)]
+    set_precision("fp32")
+    try:
+        out, batch = StandardPredict(sagittal_split=True).predict(model, torch.device("cuda"), subjects)
+    finally:
+        set_precision("auto")
+    assert rel_err(batch["y_pred"].cpu(), ref) <= 1e-5
+    assert rel_err(out[1]["y_pred"]["data"], ref[1]) <= 1e-5
+
+
+def test_segmentation_evaluator_matches_reference_fixture():
+    from segmentation_pipeline import _tio
+    from segmentation_pipeline.evaluators import LabelMapEvaluator, SegmentationEvaluator
+    z = np.load(f"{GOLDEN}/evaluator.npz")
+    label_values = dict(zip([str(s) for s in z["label_names"]], [int(v) for v in z["label_vals"]]))
+    stats = [str(s) for s in z["stats"]]
+    subjects = []
+    for i in range(3):
+        subjects.append(_tio.Subject(
+            name=f"s{i}",
+            pred=_tio.LabelMap(tensor=torch.from_numpy(z[f"pred{i}"]), label_values=label_values),
+            targ=_tio.LabelMap(tensor=torch.from_numpy(z[f"targ{i}"]), label_values=label_values)))
+    res = SegmentationEvaluator("pred", "targ", stats_to_output=stats)(subjects)
+    got = res["subject_stats"][stats].to_numpy(dtype=np.float64)
+    exp = z["subject_stats_values"]
+    assert ((got == exp) | (np.isnan(got) & np.isnan(exp))).all()
+    np.testing.assert_array_equal(res["summary_stats"].data.numpy(), z["summary_stats"])
+    vol = LabelMapEvaluator("pred")(subjects)["subject_stats"][["volume"]].to_numpy(dtype=np.float64)
+    np.testing.assert_array_equal(vol, z["volumes"])
