@@ -81,8 +81,9 @@ def test_bf16_network_within_tolerance(name):
         # label agreement, ignoring voxels whose top-2 margin is below the bf16 resolution of the logits
         top2 = torch.topk(y, 2, dim=1).values
         decided = (top2[:, 0] - top2[:, 1]) > 0.05
-        agree = (out.cpu().argmax(1) == y.argmax(1))[decided].float().mean().item()
-        assert agree >= 0.999
+        if decided.any():
+            agree = (out.cpu().argmax(1) == y.argmax(1))[decided].float().mean().item()
+            assert agree >= 0.999
 
 
 def test_autocast_selects_bf16_path():
