@@ -32,9 +32,11 @@ using namespace ptx;
 constexpr int kHX = 10, kHY = 18;                 // halo extent of a 8 x 16 tile
 constexpr int kChunkBytes = kHX * kHY * 16;       // 2880: one 8-channel chunk of one halo plane
 constexpr int kAStageBytes = 2 * kChunkBytes;     // 5760
-constexpr int kNA = 8;                            // A ring depth
-constexpr int kNBuf = 2;                          // B ring depth
+constexpr int kNA = 4;                            // A ring depth
+constexpr int kMaxBuf = 2;                        // B ring depth (1 or 2, chosen per launch)
 constexpr int kThreadsTc = 192;
+constexpr int kMaxZin = 28;                       // input planes a tile may walk (DOWN: 2*TZ+2, TZ <= 12)
+constexpr int kMaxBlk = 4;                        // MMAs (column blocks) per step and plane
 
 struct TcMaps {
     CUtensorMap m[8];  // K3/UP: [0] = 2-chunk box, [1] = 1-chunk box.  DOWN: [pp] 2-chunk, [4+pp] 1-chunk.
@@ -51,6 +53,7 @@ struct TcParams {
     int bimg_stride;  // bytes between consecutive B images in wpacked
     int maxp;         // planes per MMA
     int n_pass, n_bimg;  // passes and B images per pass
+    int nbuf;         // B ring depth
     int chunk_base;   // in.c8_off
     int c8_total;     // in.c8_total
     int tiles_x, tiles_y, tiles_z;
@@ -60,7 +63,7 @@ struct TcParams {
     DEpilogue epi;
 };
 
-__device__ __forceinline__ uint32_t pad16(uint32_t n) { return (n + 15u) & ~15u; }
+__host__ __device__ __forceinline__ uint32_t pad16(uint32_t n) { return (n + 15u) & ~15u; }
 
 // byte offset / LBO of the A operand for step `st`
 __device__ __forceinline__ void step_desc(int mode, bool lone, int pp, int st, uint32_t& off, uint32_t& lbo) {
@@ -114,21 +117,60 @@ __device__ __forceinline__ void plane_window(int mode, int TZ, int zi, int& lo, 
     }
 }
 
+// One MMA of a (plane, step): accumulator column, instruction descriptor, B row offset (16-byte units), accumulate flag
+struct MmaBlk {
+    uint32_t dcol, idesc, brow, acc;
+};
+struct PlaneTab {
+    MmaBlk blk[2][kMaxBlk];  // [0] = normal step, [1] = the very first step of a pass (first-touch split)
+    int nblk[2];
+};
+
+__device__ inline void build_plane_tab(const TcParams& p, int zi, PlaneTab& t) {
+    int lo, hi, jlo, ft;
+    plane_window(p.mode, p.TZ, zi, lo, hi, jlo, ft);
+    for (int first = 0; first < 2; ++first) {
+        const int split = first ? min(max(ft, lo), hi + 1) : hi + 1;
+        int nb = 0;
+        for (int q = lo; q <= hi;) {
+            const bool overwrite = q >= split;
+            const int lim = overwrite ? hi + 1 : split;
+            const int np = min(p.maxp, lim - q);
+            MmaBlk b;
+            b.dcol = q * p.Cpad;
+            b.idesc = make_idesc_bf16(128, pad16(np * p.Cpad));
+            b.brow = (jlo + (q - lo)) * p.Cpad;
+            b.acc = overwrite ? 0u : 1u;
+            if (nb < kMaxBlk) t.blk[first][nb] = b;
+            ++nb;
+            q += np;
+        }
+        t.nblk[first] = nb;
+    }
+}
+
 template <uint32_t kTmemCols>
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(kThreadsTc, 2)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + kNA * kAStageBytes;
     const int bbuf_bytes = (p.bimg_stride + 127) & ~127;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kNBuf * bbuf_bytes);
+    uint8_t* after_b = sB + p.nbuf * bbuf_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(after_b);
     uint64_t* full_a = bars;
     uint64_t* empty_a = bars + kNA;
     uint64_t* full_b = bars + 2 * kNA;
-    uint64_t* empty_b = full_b + kNBuf;
-    uint64_t* acc_full = empty_b + kNBuf;
+    uint64_t* empty_b = full_b + kMaxBuf;
+    uint64_t* acc_full = empty_b + kMaxBuf;
     uint64_t* acc_empty = acc_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    // tables: A step descriptors [lone][pp][9], per-plane MMA blocks, epilogue parameters
+    uint32_t* step_tab = tmem_slot + 2;                                   // 2 * 4 * 9 words
+    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(step_tab + 72);     // kMaxZin entries (8-byte aligned)
+    float* s_scale = reinterpret_cast<float*>(plane_tab + kMaxZin);
+    float* s_shift = s_scale + p.Cpad;
+    float* s_slope = s_shift + p.Cpad;
 
     const int warp = threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -148,7 +190,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_init(&full_a[i], 1);
             mbar_init(&empty_a[i], 1);
         }
-        for (int i = 0; i < kNBuf; ++i) {
+        for (int i = 0; i < kMaxBuf; ++i) {
             mbar_init(&full_b[i], 1);
             mbar_init(&empty_b[i], 1);
         }
@@ -157,6 +199,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    // cooperative table build
+    for (int i = threadIdx.x; i < 72; i += blockDim.x) {
+        const int lone = i / 36, pp = (i / 9) % 4, st = i % 9;
+        uint32_t off, lbo;
+        step_desc(p.mode, lone != 0, pp, st, off, lbo);
+        step_tab[i] = (off >> 4) | ((lbo >> 4) << 16);
+    }
+    for (int zi = threadIdx.x; zi < p.zin_count; zi += blockDim.x) build_plane_tab(p, zi, plane_tab[zi]);
+    for (int c = threadIdx.x; c < p.Cpad; c += blockDim.x) {
+        s_scale[c] = p.epi.scale[c];
+        s_shift[c] = p.epi.shift[c];
+        s_slope[c] = p.epi.slope[c];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -175,7 +230,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     const int nsteps = lone ? p.steps_lone : p.steps_full;
                     // ---- B image
                     {
-                        const uint32_t s = b_it % kNBuf, ph = (b_it / kNBuf) & 1;
+                        const uint32_t s = b_it % p.nbuf, ph = (b_it / p.nbuf) & 1;
                         mbar_wait(&empty_b[s], ph ^ 1);
                         const uint32_t bytes = nsteps * 2 * p.NB * 16;
                         mbar_arrive_expect_tx(&full_b[s], bytes);
@@ -218,7 +273,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         // =============================================================== MMA issuer
         if (elect_one()) {
             uint32_t a_it = 0, b_it = 0;
-            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+            // descriptor high words: SBO | version(1) at bit 46 ; A: SBO = 160 B, B: SBO = 128 B
+            const uint64_t a_hi = (static_cast<uint64_t>((kHX * 16) >> 4) | (1ull << 14)) << 32;
+            const uint64_t b_hi = (static_cast<uint64_t>(128 >> 4) | (1ull << 14)) << 32;
+            const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
+            const uint32_t b_step16 = 2 * p.NB;                         // one step of a B image, in 16-byte units
             for (int pass = 0; pass < p.n_pass; ++pass) {
                 if (pass > 0) {
                     mbar_wait(acc_empty, (pass - 1) & 1);
@@ -228,10 +288,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     const int g = bi % p.G;
                     const bool lone = p.lone_last && g == p.G - 1;
                     const int nsteps = lone ? p.steps_lone : p.steps_full;
-                    const uint32_t bs = b_it % kNBuf, bph = (b_it / kNBuf) & 1;
+                    const uint32_t bs = b_it % p.nbuf, bph = (b_it / p.nbuf) & 1;
                     mbar_wait(&full_b[bs], bph);
                     tc_fence_after();
-                    const uint32_t bimg = sB_u + bs * bbuf_bytes;
+                    const uint32_t bimg16 = sB16 + bs * (bbuf_bytes >> 4);
                     int zi_start = 0, zi_step = 1, pp = 0;
                     if (p.mode == B200SEG_TC_DOWN) {
                         zi_start = bi / (4 * p.G);
@@ -240,29 +300,46 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     } else if (p.mode == B200SEG_TC_UP) {
                         pp = pass;
                     }
+                    const uint32_t* steps = step_tab + (lone ? 36 : 0) + pp * 9;
                     for (int zi = zi_start; zi < p.zin_count; zi += zi_step) {
                         const uint32_t s = a_it % kNA, ph = (a_it / kNA) & 1;
                         mbar_wait(&full_a[s], ph);
                         tc_fence_after();
-                        int lo, hi, jlo, ft;
-                        plane_window(p.mode, p.TZ, zi, lo, hi, jlo, ft);
-                        const uint32_t a_base = sA_u + s * kAStageBytes;
-                        for (int st = 0; st < nsteps; ++st) {
-                            uint32_t a_off, a_lbo;
-                            step_desc(p.mode, lone, pp, st, a_off, a_lbo);
-                            const uint64_t adesc = make_desc_kmajor_noswz(a_base + a_off, a_lbo, kHX * 16);
-                            const uint32_t b_step = bimg + st * (2 * p.NB * 16);
-                            // planes [lo, split) accumulate; planes [split, hi] overwrite (first touch)
-                            const int split = (bi == 0 && st == 0) ? min(max(ft, lo), hi + 1) : hi + 1;
-                            for (int q = lo; q <= hi;) {
-                                const bool overwrite = q >= split;
-                                const int lim = overwrite ? hi + 1 : split;
-                                const int np = min(p.maxp, lim - q);
-                                const uint64_t bdesc =
-                                    make_desc_kmajor_noswz(b_step + (jlo + (q - lo)) * p.Cpad * 16, p.NB * 16, 128);
-                                umma_bf16(tmem + q * p.Cpad, adesc, bdesc, make_idesc_bf16(128, pad16(np * p.Cpad)),
-                                          overwrite ? 0u : 1u);
-                                q += np;
+                        const PlaneTab& pt = plane_tab[zi];
+                        const uint32_t a16 = sA16 + s * (kAStageBytes >> 4);
+                        int st = 0;
+                        if (bi == 0) {
+                            // first step of the pass: first-touch split
+                            const uint64_t adesc = a_hi | static_cast<uint64_t>(steps[0] + a16);
+                            const int nb = pt.nblk[1];
+                            for (int b = 0; b < nb; ++b) {
+                                const MmaBlk k = pt.blk[1][b];
+                                umma_bf16(tmem + k.dcol, adesc, b_hi | static_cast<uint64_t>((bimg16 + k.brow) | b_lbo),
+                                          k.idesc, k.acc);
+                            }
+                            st = 1;
+                        }
+                        const int nb = pt.nblk[0];
+                        const MmaBlk k0 = pt.blk[0][0];
+                        if (nb == 1) {
+                            const uint32_t d0 = tmem + k0.dcol;
+                            uint32_t blo = (bimg16 + st * b_step16 + k0.brow) | b_lbo;
+#pragma unroll 1
+                            for (; st < nsteps; ++st) {
+                                umma_bf16(d0, a_hi | static_cast<uint64_t>(steps[st] + a16), b_hi | static_cast<uint64_t>(blo),
+                                          k0.idesc, 1u);
+                                blo += b_step16;
+                            }
+                        } else {
+#pragma unroll 1
+                            for (; st < nsteps; ++st) {
+                                const uint64_t adesc = a_hi | static_cast<uint64_t>(steps[st] + a16);
+                                const uint32_t bst = bimg16 + st * b_step16;
+                                for (int b = 0; b < nb; ++b) {
+                                    const MmaBlk k = pt.blk[0][b];
+                                    umma_bf16(tmem + k.dcol, adesc, b_hi | static_cast<uint64_t>((bst + k.brow) | b_lbo),
+                                              k.idesc, 1u);
+                                }
                             }
                         }
                         umma_commit(&empty_a[s]);
@@ -301,20 +378,52 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 if (oz >= p.out_z) break;
                 const uint32_t taddr = tmem + (static_cast<uint32_t>(lg * 32) << 16) + q * p.Cpad;
                 if (e.out_ncdhw == nullptr) {
-                    for (int cc = 0; cc < c8; cc += 2) {
-                        uint32_t r0[8], r1[8];
-                        tmem_ld8(taddr + cc * 8, r0);
-                        if (cc + 1 < c8) tmem_ld8(taddr + (cc + 1) * 8, r1);
+                    // 5 chunks (40 channels) per round: all TMEM loads, then all residual loads, then math + stores
+                    for (int c0 = 0; c0 < c8; c0 += 5) {
+                        uint32_t r[5][8];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
+                        uint4 res[5];
+                        const bool has_res = e.residual.data != nullptr;
+                        if (valid && has_res) {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j)
+                                if (c0 + j < c8 && c0 + j < e.split_c8)
+                                    res[j] = __ldg(reinterpret_cast<const uint4*>(e.residual.data) +
+                                                   vox_index(e.residual, n, c0 + j, oz, oy, ox));
+                        }
                         tmem_ld_wait();
                         if (valid) {
-                            Vec8 a;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) a.v[j] = __uint_as_float(r0[j]);
-                            epi_store_chunk<__nv_bfloat16>(e, cc, n, oz, oy, ox, a);
-                            if (cc + 1 < c8) {
+                            for (int j = 0; j < 5; ++j) {
+                                const int cc = c0 + j;
+                                if (cc >= c8) continue;
+                                float v[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) a.v[j] = __uint_as_float(r1[j]);
-                                epi_store_chunk<__nv_bfloat16>(e, cc + 1, n, oz, oy, ox, a);
+                                for (int i = 0; i < 8; ++i) {
+                                    const int c = cc * 8 + i;
+                                    float t = fmaf(__uint_as_float(r[j][i]), s_scale[c], s_shift[c]);
+                                    v[i] = t > 0.f ? t : t * s_slope[c];
+                                }
+                                const bool to0 = cc < e.split_c8;
+                                if (to0 && has_res) {
+                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        float2 f = __bfloat1622float2(h[i]);
+                                        v[2 * i] += f.x;
+                                        v[2 * i + 1] += f.y;
+                                    }
+                                }
+                                uint4 o;
+                                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                                if (to0)
+                                    reinterpret_cast<uint4*>(e.dst0.data)[vox_index(e.dst0, n, cc, oz, oy, ox)] = o;
+                                else
+                                    reinterpret_cast<uint4*>(e.dst1.data)[vox_index(e.dst1, n, cc - e.split_c8, oz, oy, ox)] = o;
                             }
                         }
                     }
@@ -326,18 +435,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     tmem_ld_wait();
                     if (valid) {
                         float v[16];
-                        Vec8 a;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) a.v[j] = __uint_as_float(r0[j]);
-                        epi_affine_act(e, 0, a);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = a.v[j];
+                        for (int j = 0; j < 8; ++j) {
+                            float t = fmaf(__uint_as_float(r0[j]), s_scale[j], s_shift[j]);
+                            v[j] = t > 0.f ? t : t * s_slope[j];
+                        }
                         if (c8 > 1) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) a.v[j] = __uint_as_float(r1[j]);
-                            epi_affine_act(e, 8, a);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[8 + j] = a.v[j];
+                            for (int j = 0; j < 8; ++j) {
+                                float t = fmaf(__uint_as_float(r1[j]), s_scale[8 + j], s_shift[8 + j]);
+                                v[8 + j] = t > 0.f ? t : t * s_slope[8 + j];
+                            }
                         }
                         const long long vox = 1LL * p.out_z * p.out_y * p.out_x;
                         float* dst = e.out_ncdhw + static_cast<long long>(n) * e.cout * vox +
@@ -409,7 +517,7 @@ static int tc_geometry(int mode, int cin_chunks, int cout, TcGeom* g) {
     g->n_pass = mode == B200SEG_TC_UP ? 4 : 1;
     g->n_bimg = mode == B200SEG_TC_DOWN ? 8 * g->G : g->G;
     g->bimg_stride = g->steps_full * 2 * g->NB * 16;
-    g->TZmax = (512 - 16) / g->Cpad;
+    g->TZmax = (256 - 16) / g->Cpad;   // <= 256 TMEM columns per CTA so that two CTAs share an SM
     if (g->TZmax > 12) g->TZmax = 12;
     return B200SEG_OK;
 }
@@ -496,6 +604,18 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     int ntz = (oz + tzmax - 1) / tzmax;
     int TZ = (oz + ntz - 1) / ntz;
     if (mode == B200SEG_TC_UP && (TZ & 1)) ++TZ;
+    {
+        // small grids: thinner z tiles until there are at least two waves of CTAs (or TZ bottoms out)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int plane_tiles = (mode == B200SEG_TC_UP ? ((in.x + 7) / 8) * ((in.y + 15) / 16)
+                                                       : ((ox + 7) / 8) * ((oy + 15) / 16)) * in.n;
+        const int tz_min = mode == B200SEG_TC_UP ? 2 : 1;
+        while (TZ > tz_min && plane_tiles * ((oz + TZ - 1) / TZ) < 4 * sms) {
+            TZ = (TZ + 1) / 2;
+            if (mode == B200SEG_TC_UP && (TZ & 1)) ++TZ;
+        }
+    }
     p.TZ = TZ;
     p.tiles_z = (oz + TZ - 1) / TZ;
     if (mode == B200SEG_TC_UP) {
@@ -543,9 +663,13 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     }
     // ---- launch
     const int bbuf = (g.bimg_stride + 127) & ~127;
-    const size_t smem = static_cast<size_t>(kNA) * kAStageBytes + static_cast<size_t>(kNBuf) * bbuf +
-                        (2 * kNA + 2 * kNBuf + 2) * 8 + 16;
+    const size_t fixed = static_cast<size_t>(kNA) * kAStageBytes + (2 * kNA + 2 * kMaxBuf + 2) * 8 + 16 + 72 * 4 +
+                         sizeof(PlaneTab) * kMaxZin + 3 * static_cast<size_t>(g.Cpad) * 4 + 64;
+    // double-buffer the weights when two CTAs per SM still fit (113 KB each)
+    p.nbuf = (fixed + 2 * static_cast<size_t>(bbuf) <= 112 * 1024) ? 2 : 1;
+    const size_t smem = fixed + static_cast<size_t>(p.nbuf) * bbuf;
     B200SEG_CHECK_ARG(smem <= 227 * 1024, "conv3d_tc: %zu bytes of shared memory needed", smem);
+    B200SEG_CHECK_ARG(p.zin_count <= kMaxZin, "conv3d_tc: tile walks %d input planes (max %d)", p.zin_count, kMaxZin);
     const uint32_t cols_needed = TZ * g.Cpad + 16;
     dim3 grid(static_cast<unsigned>(p.tiles_x * p.tiles_y * p.tiles_z), static_cast<unsigned>(in.n));
     cudaStream_t s = static_cast<cudaStream_t>(stream);

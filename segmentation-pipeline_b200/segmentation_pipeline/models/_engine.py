@@ -19,6 +19,7 @@ from . import _plan
 from ._plan import DOWN, K3, UP, ConvOp, Plan, PoolOp, Ref, SoftmaxOp, UpsampleOp, c8
 
 _PRECISION = [os.environ.get("B200SEG_PRECISION", "auto")]
+TRACE = None    # set to a list to record (call, extent, (start, end) CUDA events) per op (tools/profile_layers.py)
 TC_MAX_COUT = 80
 
 
@@ -202,6 +203,10 @@ class CompiledPlan:
             return ws[ref.buf].view(ref.c, ref.off)
 
         for call in self.calls:
+            if TRACE is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+                TRACE.append((call, (n, z, y, x), ev))
             if isinstance(call, _ConvCall):
                 epi = lib.make_epilogue(call.scale, call.shift, call.slope, view(call.dst0), view(call.dst1),
                                         call.split, view(call.residual), out if call.final else None, call.softmax)
@@ -219,6 +224,8 @@ class CompiledPlan:
                 lib.softmax_ncdhw(out, call.sm_channels, call.diag_bias)
             else:  # pragma: no cover
                 raise RuntimeError(f"unknown op {call}")
+            if TRACE is not None:
+                ev[1].record()
         if not wrote_final:
             lib.unpack_ncdhw(ws["out"].view(self.plan.out_channels), out)
         return out

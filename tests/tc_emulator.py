@@ -80,7 +80,7 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
         oz, oy, ox = Z // 2, Y // 2, X // 2
     else:
         oz, oy, ox = 2 * Z, 2 * Y, 2 * X
-    tzmax = min(12, (512 - 16) // cpad)
+    tzmax = min(12, (256 - 16) // cpad)
     if mode == UP:
         tzmax &= ~1
     if TZ is None:
