@@ -39,7 +39,7 @@ UNIT = "Mvoxel/s"
 VOLUME = (2, 256, 256, 192)
 PATCH, OVERLAP, PADDING = 96, 48, "edge"
 FILTERS = [40, 40, 80, 80, 120, 120]
-PATCH_BATCH = 16
+PATCH_BATCH = int(os.environ.get("B200SEG_PATCH_BATCH", "48"))
 FLOP_PER_PATCH = 668.74e9          # 2 * MACs of the reference layer list at 96^3
 N_PATCHES = 144
 WORKLOAD = ("config2: msseg2 ModularUNet 2->2 filters [40,40,80,80,120,120] depth 6 residual blur-down/up, "

@@ -1,5 +1,5 @@
 // Tensor-core convolution engine for sm_100a: implicit GEMM on tcgen05.mma with TMEM accumulators, operands
-// staged by TMA, one CTA per output tile.
+// staged by TMA, persistent CTAs.
 //
 // Geometry (all three modes share it)
 //   * GEMM M = 128 output positions of one z-plane: a 16 (y) x 8 (x) patch of voxels; row m = y*8 + x.
@@ -19,8 +19,16 @@
 //     multiple of 16 multiplies zeros ("spill" columns add 0 to the next plane's accumulator).
 //   * accumulators: TZ planes x Cpad fp32 columns in TMEM; first touch of a plane uses accumulate=0.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> folded BN / bias, activation, residual, bf16 store or softmax -> fp32 NCDHW).
+// Execution: persistent CTAs loop over work units (tile x pass).
+//   warp 0  A producer : ring of halo planes (TMA box loads), in consumption order
+//   warp 2  B producer : ring of weight images (one bulk copy per chunk group)
+//   warp 1  MMA issuer : per plane, the steps of the image are issued from an UNROLLED loop whose descriptor
+//                        deltas are compile-time constants, so one MMA costs a couple of uniform adds
+//   epilogue warps     : TMEM -> registers -> folded BN / bias, activation, residual, bf16 store
+//                        (or softmax -> fp32 NCDHW for the last layer)
+// kSets == 1: two CTAs per SM, one accumulator set each (the CTAs overlap each other's epilogue);
+// kSets == 2: one CTA per SM, two accumulator sets (epilogue of unit u overlaps the MMAs of unit u+1).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,9 +40,7 @@ using namespace ptx;
 constexpr int kHX = 10, kHY = 18;                 // halo extent of a 8 x 16 tile
 constexpr int kChunkBytes = kHX * kHY * 16;       // 2880: one 8-channel chunk of one halo plane
 constexpr int kAStageBytes = 2 * kChunkBytes;     // 5760
-constexpr int kNA = 4;                            // A ring depth
-constexpr int kMaxBuf = 2;                        // B ring depth (1 or 2, chosen per launch)
-constexpr int kThreadsTc = 192;
+constexpr int kMaxA = 12;                         // A ring depth (upper bound)
 constexpr int kMaxZin = 28;                       // input planes a tile may walk (DOWN: 2*TZ+2, TZ <= 12)
 constexpr int kMaxBlk = 4;                        // MMAs (column blocks) per step and plane
 
@@ -51,9 +57,11 @@ struct TcParams {
     int lone_last;   // 1 if the last group has one chunk
     int steps_full, steps_lone;
     int bimg_stride;  // bytes between consecutive B images in wpacked
+    int bbuf_bytes;   // bytes of one B image slot in shared memory
     int maxp;         // planes per MMA
     int n_pass, n_bimg;  // passes and B images per pass
-    int nbuf;         // B ring depth
+    int na, nbuf;     // A ring depth, B ring depth
+    int batch;
     int chunk_base;   // in.c8_off
     int c8_total;     // in.c8_total
     int tiles_x, tiles_y, tiles_z;
@@ -65,35 +73,45 @@ struct TcParams {
 
 __host__ __device__ __forceinline__ uint32_t pad16(uint32_t n) { return (n + 15u) & ~15u; }
 
-// byte offset / LBO of the A operand for step `st`
-__device__ __forceinline__ void step_desc(int mode, bool lone, int pp, int st, uint32_t& off, uint32_t& lbo) {
-    if (mode == B200SEG_TC_K3) {
-        if (!lone) {
-            off = ((st / 3) * kHX + (st % 3)) * 16;
-            lbo = kChunkBytes;
-        } else if (st < 3) {
-            off = (st * kHX) * 16;  // taps (dy=st,dx=0) + (dy=st,dx=1)
-            lbo = 16;
-        } else if (st == 3) {
-            off = 2 * 16;           // taps (0,2) + (1,2)
-            lbo = kHX * 16;
-        } else {
-            off = (2 * kHX + 1) * 16;  // (2,1) with zero weights + (2,2)
-            lbo = 16;
-        }
-    } else {
-        const int py = pp >> 1, px = pp & 1;
-        // first halo offset used by this parity: DOWN parity 1 -> 0, parity 0 -> 1 ; UP parity 0 -> 0, parity 1 -> 1
-        const int sy0 = (mode == B200SEG_TC_DOWN) ? (1 - py) : py;
-        const int sx0 = (mode == B200SEG_TC_DOWN) ? (1 - px) : px;
-        if (!lone) {
-            off = ((sy0 + st / 2) * kHX + (sx0 + st % 2)) * 16;
-            lbo = kChunkBytes;
-        } else {
-            off = ((sy0 + st) * kHX + sx0) * 16;  // taps (sy, sx) + (sy, sx+1)
-            lbo = 16;
-        }
+// ------------------------------------------------------------------------------------------------ step tables
+// A-descriptor low word of step `st`, relative to the stage base and the parity base:
+//   (halo offset in 16-byte units) | (LBO in 16-byte units) << 16.        These are compile-time constants.
+enum StepKind { kK3Full = 0, kK3Lone = 1, kS2Full = 2, kS2Lone = 3 };
+
+template <int KIND> struct Steps;
+template <> struct Steps<kK3Full> {
+    static constexpr int n = 9;
+    __device__ static constexpr uint32_t delta(int st) {
+        return static_cast<uint32_t>((st / 3) * kHX + (st % 3)) | (static_cast<uint32_t>(kChunkBytes >> 4) << 16);
     }
+};
+template <> struct Steps<kK3Lone> {
+    // taps (dy,0)+(dy,1) for dy = 0..2 ; (0,2)+(1,2) ; (2,1)[zero weights]+(2,2)
+    static constexpr int n = 5;
+    __device__ static constexpr uint32_t delta(int st) {
+        return st < 3 ? (static_cast<uint32_t>(st * kHX) | (1u << 16))
+             : st == 3 ? (2u | (static_cast<uint32_t>(kHX) << 16))
+                       : (static_cast<uint32_t>(2 * kHX + 1) | (1u << 16));
+    }
+};
+template <> struct Steps<kS2Full> {
+    static constexpr int n = 4;
+    __device__ static constexpr uint32_t delta(int st) {
+        return static_cast<uint32_t>((st / 2) * kHX + (st % 2)) | (static_cast<uint32_t>(kChunkBytes >> 4) << 16);
+    }
+};
+template <> struct Steps<kS2Lone> {
+    static constexpr int n = 2;
+    __device__ static constexpr uint32_t delta(int st) { return static_cast<uint32_t>(st * kHX) | (1u << 16); }
+};
+
+// Parity base (16-byte units) of the stride-2 modes: DOWN parity 1 -> halo offset 0, parity 0 -> 1; UP: parity.
+__device__ __forceinline__ uint32_t parity_base(int mode, int pp) {
+    if (mode == B200SEG_TC_K3) return 0;
+    const int py = pp >> 1, px = pp & 1;
+    const int sy0 = (mode == B200SEG_TC_DOWN) ? (1 - py) : py;
+    const int sx0 = (mode == B200SEG_TC_DOWN) ? (1 - px) : px;
+    return static_cast<uint32_t>(sy0 * kHX + sx0);
 }
 
 // planes touched by input plane zi: [lo, hi], B row block of plane lo, first plane that is touched for the first time
@@ -149,25 +167,63 @@ __device__ inline void build_plane_tab(const TcParams& p, int zi, PlaneTab& t) {
     }
 }
 
-template <uint32_t kTmemCols>
-__global__ void __launch_bounds__(kThreadsTc, 2)
+constexpr uint64_t kADescHi = (static_cast<uint64_t>((kHX * 16) >> 4) | (1ull << 14)) << 32;  // SBO 160 B, version 1
+constexpr uint64_t kBDescHi = (static_cast<uint64_t>(128 >> 4) | (1ull << 14)) << 32;         // SBO 128 B, version 1
+
+// Issue steps [st0, n) of one plane: descriptor deltas are immediates, the B image advances by bstep16 per step.
+template <int KIND>
+__device__ __forceinline__ void issue_plane(int st0, uint32_t a16, uint32_t b16, uint32_t b_lbo, uint32_t bstep16,
+                                            uint32_t tacc, const PlaneTab& pt) {
+    const int nb = pt.nblk[0];
+    const MmaBlk k0 = pt.blk[0][0];
+    const uint32_t d0 = tacc + k0.dcol;
+    if (nb == 1) {
+        uint32_t bsum = b16 + k0.brow;
+#pragma unroll
+        for (int st = 0; st < Steps<KIND>::n; ++st) {
+            if (st >= st0)
+                umma_bf16(d0, kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(st)),
+                          kBDescHi | static_cast<uint64_t>(bsum | b_lbo), k0.idesc, 1u);
+            bsum += bstep16;
+        }
+    } else {
+        const MmaBlk k1 = pt.blk[0][1];
+        const MmaBlk k2 = pt.blk[0][nb > 2 ? 2 : 1];
+        const uint32_t d1 = tacc + k1.dcol, d2 = tacc + k2.dcol;
+        uint32_t bs0 = b16 + k0.brow, bs1 = b16 + k1.brow, bs2 = b16 + k2.brow;
+#pragma unroll
+        for (int st = 0; st < Steps<KIND>::n; ++st) {
+            if (st >= st0) {
+                const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(st));
+                umma_bf16(d0, adesc, kBDescHi | static_cast<uint64_t>(bs0 | b_lbo), k0.idesc, 1u);
+                umma_bf16(d1, adesc, kBDescHi | static_cast<uint64_t>(bs1 | b_lbo), k1.idesc, 1u);
+                if (nb > 2) umma_bf16(d2, adesc, kBDescHi | static_cast<uint64_t>(bs2 | b_lbo), k2.idesc, 1u);
+            }
+            bs0 += bstep16;
+            bs1 += bstep16;
+            bs2 += bstep16;
+        }
+    }
+}
+
+template <int kSets>
+__global__ void __launch_bounds__(kSets == 2 ? 384 : 224, kSets == 2 ? 1 : 2)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    constexpr int kEpiWarp0 = kSets == 2 ? 4 : 3;
+    constexpr int kEpiWarps = kSets == 2 ? 8 : 4;
+    constexpr uint32_t kTmemCols = kSets == 2 ? 512 : 256;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + kNA * kAStageBytes;
-    const int bbuf_bytes = (p.bimg_stride + 127) & ~127;
-    uint8_t* after_b = sB + p.nbuf * bbuf_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(after_b);
-    uint64_t* full_a = bars;
-    uint64_t* empty_a = bars + kNA;
-    uint64_t* full_b = bars + 2 * kNA;
-    uint64_t* empty_b = full_b + kMaxBuf;
-    uint64_t* acc_full = empty_b + kMaxBuf;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    // tables: A step descriptors [lone][pp][9], per-plane MMA blocks, epilogue parameters
-    uint32_t* step_tab = tmem_slot + 2;                                   // 2 * 4 * 9 words
-    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(step_tab + 72);     // kMaxZin entries (8-byte aligned)
+    uint8_t* sA = smem;                               // na x 5760
+    uint8_t* sB = smem + p.na * kAStageBytes;         // nbuf x bbuf_bytes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nbuf * p.bbuf_bytes);
+    uint64_t* full_a = bars;                 // [kMaxA]
+    uint64_t* empty_a = bars + kMaxA;        // [kMaxA]
+    uint64_t* full_b = bars + 2 * kMaxA;     // [2]
+    uint64_t* empty_b = full_b + 2;          // [2]
+    uint64_t* acc_full = empty_b + 2;        // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(tmem_slot + 2);     // kMaxZin entries
     float* s_scale = reinterpret_cast<float*>(plane_tab + kMaxZin);
     float* s_shift = s_scale + p.Cpad;
     float* s_slope = s_shift + p.Cpad;
@@ -175,37 +231,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int warp = threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
 
-    // ---- tile coordinates
-    int tile = blockIdx.x;
-    const int tx = tile % p.tiles_x;
-    tile /= p.tiles_x;
-    const int ty = tile % p.tiles_y;
-    const int tz = tile / p.tiles_y;
-    const int n = blockIdx.y;
-    const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
-    const int chunk0 = n * p.c8_total + p.chunk_base;
-
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kNA; ++i) {
+        for (int i = 0; i < kMaxA; ++i) {
             mbar_init(&full_a[i], 1);
             mbar_init(&empty_a[i], 1);
         }
-        for (int i = 0; i < kMaxBuf; ++i) {
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&full_b[i], 1);
             mbar_init(&empty_b[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], kEpiWarps * 32);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 128);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
-    // cooperative table build
-    for (int i = threadIdx.x; i < 72; i += blockDim.x) {
-        const int lone = i / 36, pp = (i / 9) % 4, st = i % 9;
-        uint32_t off, lbo;
-        step_desc(p.mode, lone != 0, pp, st, off, lbo);
-        step_tab[i] = (off >> 4) | ((lbo >> 4) << 16);
-    }
     for (int zi = threadIdx.x; zi < p.zin_count; zi += blockDim.x) build_plane_tab(p, zi, plane_tab[zi]);
     for (int c = threadIdx.x; c < p.Cpad; c += blockDim.x) {
         s_scale[c] = p.epi.scale[c];
@@ -216,55 +255,73 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int n_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.batch;
+    const int n_img_planes = p.mode == B200SEG_TC_DOWN ? p.TZ + 1 : p.zin_count;
 
     if (warp == 0) {
-        // =============================================================== TMA producer
+        // =============================================================== A producer
         if (elect_one()) {
             const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : 2;
             for (int i = 0; i < nmap; ++i) prefetch_tmap(&maps.m[i]);
-            uint32_t a_it = 0, b_it = 0;
-            for (int pass = 0; pass < p.n_pass; ++pass) {
-                for (int bi = 0; bi < p.n_bimg; ++bi) {
-                    const int g = bi % p.G;
-                    const bool lone = p.lone_last && g == p.G - 1;
-                    const int nsteps = lone ? p.steps_lone : p.steps_full;
-                    // ---- B image
-                    {
+            uint32_t a_it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; t /= p.tiles_y;
+                const int tz = t % p.tiles_z;
+                const int n = t / p.tiles_z;
+                const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
+                const int chunk0 = n * p.c8_total + p.chunk_base;
+                for (int pass = 0; pass < p.n_pass; ++pass) {
+                    for (int bi = 0; bi < p.n_bimg; ++bi) {
+                        const int g = bi % p.G;
+                        const bool lone = p.lone_last && g == p.G - 1;
+                        const uint32_t plane_bytes = lone ? kChunkBytes : kAStageBytes;
+                        int zi0 = 0, zstep = 1, pp = 0;
+                        if (p.mode == B200SEG_TC_DOWN) {
+                            zi0 = bi / (4 * p.G);
+                            zstep = 2;
+                            pp = (bi / p.G) % 4;
+                        }
+                        for (int j = 0; j < n_img_planes; ++j, ++a_it) {
+                            const int zi = zi0 + j * zstep;
+                            const uint32_t s = a_it % p.na, ph = (a_it / p.na) & 1;
+                            mbar_wait(&empty_a[s], ph ^ 1);
+                            mbar_arrive_expect_tx(&full_a[s], plane_bytes);
+                            uint8_t* dst = sA + s * kAStageBytes;
+                            if (p.mode == B200SEG_TC_K3) {
+                                tma_load_4d(dst, &maps.m[lone ? 1 : 0], &full_a[s], (x0 - 1) * 8, y0 - 1,
+                                            z0 - 1 + zi, chunk0 + 2 * g);
+                            } else if (p.mode == B200SEG_TC_UP) {
+                                // tile origin is in low-res input coordinates; z0 counts OUTPUT planes (even)
+                                tma_load_4d(dst, &maps.m[lone ? 1 : 0], &full_a[s], (x0 - 1) * 8, y0 - 1,
+                                            z0 / 2 - 1 + zi, chunk0 + 2 * g);
+                            } else {
+                                tma_load_5d(dst, &maps.m[(lone ? 4 : 0) + pp], &full_a[s], 0, x0 - 1, y0 - 1,
+                                            2 * z0 - 1 + zi, chunk0 + 2 * g);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // =============================================================== B producer
+        if (elect_one()) {
+            uint32_t b_it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int pass = 0; pass < p.n_pass; ++pass) {
+                    for (int bi = 0; bi < p.n_bimg; ++bi, ++b_it) {
+                        const int g = bi % p.G;
+                        const bool lone = p.lone_last && g == p.G - 1;
+                        const int nsteps = lone ? p.steps_lone : p.steps_full;
+                        const uint32_t bytes = nsteps * 2 * p.NB * 16;
                         const uint32_t s = b_it % p.nbuf, ph = (b_it / p.nbuf) & 1;
                         mbar_wait(&empty_b[s], ph ^ 1);
-                        const uint32_t bytes = nsteps * 2 * p.NB * 16;
                         mbar_arrive_expect_tx(&full_b[s], bytes);
-                        const uint8_t* src = p.wpacked + static_cast<size_t>(pass * p.n_bimg + bi) * p.bimg_stride;
-                        bulk_load(sB + s * bbuf_bytes, src, bytes, &full_b[s]);
-                        ++b_it;
-                    }
-                    // ---- A stages
-                    int zi_start = 0, zi_step = 1, pp = 0;
-                    if (p.mode == B200SEG_TC_DOWN) {
-                        zi_start = bi / (4 * p.G);  // z parity
-                        zi_step = 2;
-                        pp = (bi / p.G) % 4;
-                    } else if (p.mode == B200SEG_TC_UP) {
-                        pp = pass;
-                    }
-                    (void)pp;
-                    for (int zi = zi_start; zi < p.zin_count; zi += zi_step) {
-                        const uint32_t s = a_it % kNA, ph = (a_it / kNA) & 1;
-                        mbar_wait(&empty_a[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&full_a[s], lone ? kChunkBytes : kAStageBytes);
-                        uint8_t* dst = sA + s * kAStageBytes;
-                        if (p.mode == B200SEG_TC_K3) {
-                            tma_load_4d(dst, &maps.m[lone ? 1 : 0], &full_a[s], (x0 - 1) * 8, y0 - 1, z0 - 1 + zi,
-                                        chunk0 + 2 * g);
-                        } else if (p.mode == B200SEG_TC_UP) {
-                            // tile origin is in low-res input coordinates; z0 counts OUTPUT planes (even)
-                            tma_load_4d(dst, &maps.m[lone ? 1 : 0], &full_a[s], (x0 - 1) * 8, y0 - 1,
-                                        z0 / 2 - 1 + zi, chunk0 + 2 * g);
-                        } else {
-                            tma_load_5d(dst, &maps.m[(lone ? 4 : 0) + pp], &full_a[s], 0, x0 - 1, y0 - 1,
-                                        2 * z0 - 1 + zi, chunk0 + 2 * g);
-                        }
-                        ++a_it;
+                        bulk_load(sB + s * p.bbuf_bytes,
+                                  p.wpacked + static_cast<size_t>(pass * p.n_bimg + bi) * p.bimg_stride, bytes,
+                                  &full_b[s]);
                     }
                 }
             }
@@ -272,209 +329,216 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     } else if (warp == 1) {
         // =============================================================== MMA issuer
         if (elect_one()) {
-            uint32_t a_it = 0, b_it = 0;
+            uint32_t a_it = 0, b_it = 0, unit = 0;
             const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
-            // descriptor high words: SBO | version(1) at bit 46 ; A: SBO = 160 B, B: SBO = 128 B
-            const uint64_t a_hi = (static_cast<uint64_t>((kHX * 16) >> 4) | (1ull << 14)) << 32;
-            const uint64_t b_hi = (static_cast<uint64_t>(128 >> 4) | (1ull << 14)) << 32;
             const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
-            const uint32_t b_step16 = 2 * p.NB;                         // one step of a B image, in 16-byte units
-            for (int pass = 0; pass < p.n_pass; ++pass) {
-                if (pass > 0) {
-                    mbar_wait(acc_empty, (pass - 1) & 1);
+            const uint32_t bstep16 = 2 * p.NB;                          // one step of a B image, in 16-byte units
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
+                    const uint32_t set = kSets == 2 ? (unit & 1) : 0;
+                    mbar_wait(&acc_empty[set], ((kSets == 2 ? (unit >> 1) : unit) & 1) ^ 1);
                     tc_fence_after();
-                }
-                for (int bi = 0; bi < p.n_bimg; ++bi) {
-                    const int g = bi % p.G;
-                    const bool lone = p.lone_last && g == p.G - 1;
-                    const int nsteps = lone ? p.steps_lone : p.steps_full;
-                    const uint32_t bs = b_it % p.nbuf, bph = (b_it / p.nbuf) & 1;
-                    mbar_wait(&full_b[bs], bph);
-                    tc_fence_after();
-                    const uint32_t bimg16 = sB16 + bs * (bbuf_bytes >> 4);
-                    int zi_start = 0, zi_step = 1, pp = 0;
-                    if (p.mode == B200SEG_TC_DOWN) {
-                        zi_start = bi / (4 * p.G);
-                        zi_step = 2;
-                        pp = (bi / p.G) % 4;
-                    } else if (p.mode == B200SEG_TC_UP) {
-                        pp = pass;
-                    }
-                    const uint32_t* steps = step_tab + (lone ? 36 : 0) + pp * 9;
-                    for (int zi = zi_start; zi < p.zin_count; zi += zi_step) {
-                        const uint32_t s = a_it % kNA, ph = (a_it / kNA) & 1;
-                        mbar_wait(&full_a[s], ph);
+                    const uint32_t tacc = tmem + set * 256;
+                    for (int bi = 0; bi < p.n_bimg; ++bi, ++b_it) {
+                        const int g = bi % p.G;
+                        const bool lone = p.lone_last && g == p.G - 1;
+                        int zi0 = 0, zstep = 1, pp = 0;
+                        if (p.mode == B200SEG_TC_DOWN) {
+                            zi0 = bi / (4 * p.G);
+                            zstep = 2;
+                            pp = (bi / p.G) % 4;
+                        } else if (p.mode == B200SEG_TC_UP) {
+                            pp = pass;
+                        }
+                        const int kind = (p.mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
+                        const uint32_t pbase = parity_base(p.mode, pp);
+                        const uint32_t bs = b_it % p.nbuf;
+                        mbar_wait(&full_b[bs], (b_it / p.nbuf) & 1);
                         tc_fence_after();
-                        const PlaneTab& pt = plane_tab[zi];
-                        const uint32_t a16 = sA16 + s * (kAStageBytes >> 4);
-                        int st = 0;
-                        if (bi == 0) {
-                            // first step of the pass: first-touch split
-                            const uint64_t adesc = a_hi | static_cast<uint64_t>(steps[0] + a16);
-                            const int nb = pt.nblk[1];
-                            for (int b = 0; b < nb; ++b) {
-                                const MmaBlk k = pt.blk[1][b];
-                                umma_bf16(tmem + k.dcol, adesc, b_hi | static_cast<uint64_t>((bimg16 + k.brow) | b_lbo),
-                                          k.idesc, k.acc);
-                            }
-                            st = 1;
-                        }
-                        const int nb = pt.nblk[0];
-                        const MmaBlk k0 = pt.blk[0][0];
-                        if (nb == 1) {
-                            const uint32_t d0 = tmem + k0.dcol;
-                            uint32_t blo = (bimg16 + st * b_step16 + k0.brow) | b_lbo;
-#pragma unroll 1
-                            for (; st < nsteps; ++st) {
-                                umma_bf16(d0, a_hi | static_cast<uint64_t>(steps[st] + a16), b_hi | static_cast<uint64_t>(blo),
-                                          k0.idesc, 1u);
-                                blo += b_step16;
-                            }
-                        } else {
-#pragma unroll 1
-                            for (; st < nsteps; ++st) {
-                                const uint64_t adesc = a_hi | static_cast<uint64_t>(steps[st] + a16);
-                                const uint32_t bst = bimg16 + st * b_step16;
-                                for (int b = 0; b < nb; ++b) {
-                                    const MmaBlk k = pt.blk[0][b];
-                                    umma_bf16(tmem + k.dcol, adesc, b_hi | static_cast<uint64_t>((bst + k.brow) | b_lbo),
-                                              k.idesc, 1u);
+                        const uint32_t b16 = sB16 + bs * (p.bbuf_bytes >> 4);
+                        const PlaneTab* pt = plane_tab + zi0;
+                        for (int j = 0; j < n_img_planes; ++j, ++a_it, pt += zstep) {
+                            const uint32_t s = a_it % p.na;
+                            mbar_wait(&full_a[s], (a_it / p.na) & 1);
+                            tc_fence_after();
+                            const uint32_t a16 = sA16 + s * (kAStageBytes >> 4) + pbase;
+                            int st0 = 0;
+                            if (bi == 0) {
+                                // first step of the pass: first-touch split (planes seen for the first time overwrite)
+                                uint32_t d0;
+                                switch (kind) {
+                                    case kK3Full: d0 = Steps<kK3Full>::delta(0); break;
+                                    case kK3Lone: d0 = Steps<kK3Lone>::delta(0); break;
+                                    case kS2Full: d0 = Steps<kS2Full>::delta(0); break;
+                                    default: d0 = Steps<kS2Lone>::delta(0); break;
                                 }
+                                const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + d0);
+                                const int nb = pt->nblk[1];
+                                for (int b = 0; b < nb; ++b) {
+                                    const MmaBlk k = pt->blk[1][b];
+                                    umma_bf16(tacc + k.dcol, adesc, kBDescHi | static_cast<uint64_t>((b16 + k.brow) | b_lbo),
+                                              k.idesc, k.acc);
+                                }
+                                st0 = 1;
                             }
+                            switch (kind) {
+                                case kK3Full: issue_plane<kK3Full>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
+                                case kK3Lone: issue_plane<kK3Lone>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
+                                case kS2Full: issue_plane<kS2Full>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
+                                default: issue_plane<kS2Lone>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
+                            }
+                            umma_commit(&empty_a[s]);
                         }
-                        umma_commit(&empty_a[s]);
-                        ++a_it;
+                        umma_commit(&empty_b[bs]);
                     }
-                    umma_commit(&empty_b[bs]);
-                    ++b_it;
+                    umma_commit(&acc_full[set]);
                 }
-                umma_commit(acc_full);
             }
         }
-    } else {
-        // =============================================================== epilogue (warps 2..5)
-        const int lg = warp & 3;            // TMEM lane quarter this warp may read
+    } else if (warp >= kEpiWarp0) {
+        // =============================================================== epilogue
+        const int lg = warp & 3;            // TMEM lane quarter this warp may read (= warp id % 4)
+        const int half = (warp - kEpiWarp0) >> 2;   // with 8 warps, two share a lane quarter and split the items
+        constexpr int kHalves = kEpiWarps / 4;
         const int m = lg * 32 + lane;       // accumulator row
         const int my = m >> 3, mx = m & 7;
         const DEpilogue& e = p.epi;
         const int c8 = p.Cpad / 8;
-        for (int pass = 0; pass < p.n_pass; ++pass) {
-            mbar_wait(acc_full, pass & 1);
-            tc_fence_after();
-            int oy, ox;
-            bool valid;
-            if (p.mode == B200SEG_TC_UP) {
-                const int py = pass >> 1, px = pass & 1;
-                oy = 2 * (y0 + my) + py;
-                ox = 2 * (x0 + mx) + px;
-                valid = (y0 + my) < p.out_y && (x0 + mx) < p.out_x;
-            } else {
-                oy = y0 + my;
-                ox = x0 + mx;
-                valid = oy < p.out_y && ox < p.out_x;
-            }
-            for (int q = 0; q < p.TZ; ++q) {
-                const int oz = z0 + q;
-                if (oz >= p.out_z) break;
-                const uint32_t taddr = tmem + (static_cast<uint32_t>(lg * 32) << 16) + q * p.Cpad;
+        const bool has_res = e.residual.data != nullptr;
+        uint32_t unit = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tx = t % p.tiles_x; t /= p.tiles_x;
+            const int ty = t % p.tiles_y; t /= p.tiles_y;
+            const int tz = t % p.tiles_z;
+            const int n = t / p.tiles_z;
+            const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
+            for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
+                const uint32_t set = kSets == 2 ? (unit & 1) : 0;
+                mbar_wait(&acc_full[set], (kSets == 2 ? (unit >> 1) : unit) & 1);
+                tc_fence_after();
+                int oy, ox;
+                bool valid;
+                if (p.mode == B200SEG_TC_UP) {
+                    const int py = pass >> 1, px = pass & 1;
+                    oy = 2 * (y0 + my) + py;
+                    ox = 2 * (x0 + mx) + px;
+                    valid = (y0 + my) < p.out_y && (x0 + mx) < p.out_x;
+                } else {
+                    oy = y0 + my;
+                    ox = x0 + mx;
+                    valid = oy < p.out_y && ox < p.out_x;
+                }
+                const uint32_t tbase = tmem + set * 256 + (static_cast<uint32_t>(lg * 32) << 16);
                 if (e.out_ncdhw == nullptr) {
-                    // 5 chunks (40 channels) per round: all TMEM loads, then all residual loads, then math + stores
-                    for (int c0 = 0; c0 < c8; c0 += 5) {
-                        uint32_t r[5][8];
-#pragma unroll
-                        for (int j = 0; j < 5; ++j)
-                            if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
-                        uint4 res[5];
-                        const bool has_res = e.residual.data != nullptr;
-                        if (valid && has_res) {
+                    int item = 0;
+                    for (int q = 0; q < p.TZ; ++q) {
+                        const int oz = z0 + q;
+                        if (oz >= p.out_z) break;
+                        const uint32_t taddr = tbase + q * p.Cpad;
+                        // 5 chunks (40 channels) per round: TMEM loads, residual loads, then math + stores
+                        for (int c0 = 0; c0 < c8; c0 += 5, ++item) {
+                            if (kHalves == 2 && (item & 1) != half) continue;
+                            uint32_t r[5][8];
 #pragma unroll
                             for (int j = 0; j < 5; ++j)
-                                if (c0 + j < c8 && c0 + j < e.split_c8)
-                                    res[j] = __ldg(reinterpret_cast<const uint4*>(e.residual.data) +
-                                                   vox_index(e.residual, n, c0 + j, oz, oy, ox));
-                        }
-                        tmem_ld_wait();
-                        if (valid) {
+                                if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
+                            uint4 res[5];
+                            if (valid && has_res) {
 #pragma unroll
-                            for (int j = 0; j < 5; ++j) {
-                                const int cc = c0 + j;
-                                if (cc >= c8) continue;
-                                float v[8];
+                                for (int j = 0; j < 5; ++j)
+                                    if (c0 + j < c8 && c0 + j < e.split_c8)
+                                        res[j] = __ldg(reinterpret_cast<const uint4*>(e.residual.data) +
+                                                       vox_index(e.residual, n, c0 + j, oz, oy, ox));
+                            }
+                            tmem_ld_wait();
+                            if (valid) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int c = cc * 8 + i;
-                                    float t = fmaf(__uint_as_float(r[j][i]), s_scale[c], s_shift[c]);
-                                    v[i] = t > 0.f ? t : t * s_slope[c];
-                                }
-                                const bool to0 = cc < e.split_c8;
-                                if (to0 && has_res) {
-                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
+                                for (int j = 0; j < 5; ++j) {
+                                    const int cc = c0 + j;
+                                    if (cc >= c8) continue;
+                                    float v[8];
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        float2 f = __bfloat1622float2(h[i]);
-                                        v[2 * i] += f.x;
-                                        v[2 * i + 1] += f.y;
+                                    for (int i = 0; i < 8; ++i) {
+                                        const int c = cc * 8 + i;
+                                        float tv = fmaf(__uint_as_float(r[j][i]), s_scale[c], s_shift[c]);
+                                        v[i] = tv > 0.f ? tv : tv * s_slope[c];
                                     }
-                                }
-                                uint4 o;
-                                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+                                    const bool to0 = cc < e.split_c8;
+                                    if (to0 && has_res) {
+                                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                                if (to0)
-                                    reinterpret_cast<uint4*>(e.dst0.data)[vox_index(e.dst0, n, cc, oz, oy, ox)] = o;
-                                else
-                                    reinterpret_cast<uint4*>(e.dst1.data)[vox_index(e.dst1, n, cc - e.split_c8, oz, oy, ox)] = o;
+                                        for (int i = 0; i < 4; ++i) {
+                                            float2 f = __bfloat1622float2(h[i]);
+                                            v[2 * i] += f.x;
+                                            v[2 * i + 1] += f.y;
+                                        }
+                                    }
+                                    uint4 o;
+                                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                                    if (to0)
+                                        reinterpret_cast<uint4*>(e.dst0.data)[vox_index(e.dst0, n, cc, oz, oy, ox)] = o;
+                                    else
+                                        reinterpret_cast<uint4*>(e.dst1.data)[vox_index(e.dst1, n, cc - e.split_c8, oz, oy, ox)] = o;
+                                }
                             }
                         }
                     }
                 } else {
                     // final layer: affine (+bias), optional channel softmax, fp32 NCDHW store (cout <= 16)
-                    uint32_t r0[8], r1[8];
-                    tmem_ld8(taddr, r0);
-                    if (c8 > 1) tmem_ld8(taddr + 8, r1);
-                    tmem_ld_wait();
-                    if (valid) {
-                        float v[16];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float t = fmaf(__uint_as_float(r0[j]), s_scale[j], s_shift[j]);
-                            v[j] = t > 0.f ? t : t * s_slope[j];
-                        }
-                        if (c8 > 1) {
+                    for (int q = half; q < p.TZ; q += kHalves) {
+                        const int oz = z0 + q;
+                        if (oz >= p.out_z) break;
+                        const uint32_t taddr = tbase + q * p.Cpad;
+                        uint32_t r0[8], r1[8];
+                        tmem_ld8(taddr, r0);
+                        if (c8 > 1) tmem_ld8(taddr + 8, r1);
+                        tmem_ld_wait();
+                        if (valid) {
+                            float v[16];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float t = fmaf(__uint_as_float(r1[j]), s_scale[8 + j], s_shift[8 + j]);
-                                v[8 + j] = t > 0.f ? t : t * s_slope[8 + j];
+                                float tv = fmaf(__uint_as_float(r0[j]), s_scale[j], s_shift[j]);
+                                v[j] = tv > 0.f ? tv : tv * s_slope[j];
                             }
-                        }
-                        const long long vox = 1LL * p.out_z * p.out_y * p.out_x;
-                        float* dst = e.out_ncdhw + static_cast<long long>(n) * e.cout * vox +
-                                     (static_cast<long long>(oz) * p.out_y + oy) * p.out_x + ox;
-                        if (e.softmax) {
-                            float mx_ = -INFINITY;
+                            if (c8 > 1) {
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (c < e.cout) mx_ = fmaxf(mx_, v[c]);
-                            float s = 0.f;
-#pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (c < e.cout) {
-                                    v[c] = expf(v[c] - mx_);
-                                    s += v[c];
+                                for (int j = 0; j < 8; ++j) {
+                                    float tv = fmaf(__uint_as_float(r1[j]), s_scale[8 + j], s_shift[8 + j]);
+                                    v[8 + j] = tv > 0.f ? tv : tv * s_slope[8 + j];
                                 }
+                            }
+                            const long long vox = 1LL * p.out_z * p.out_y * p.out_x;
+                            float* dst = e.out_ncdhw + static_cast<long long>(n) * e.cout * vox +
+                                         (static_cast<long long>(oz) * p.out_y + oy) * p.out_x + ox;
+                            if (e.softmax) {
+                                float mx_ = -INFINITY;
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (c < e.cout) dst[c * vox] = v[c] / s;
-                        } else {
+                                for (int c = 0; c < 16; ++c)
+                                    if (c < e.cout) mx_ = fmaxf(mx_, v[c]);
+                                float sum = 0.f;
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (c < e.cout) dst[c * vox] = v[c];
+                                for (int c = 0; c < 16; ++c)
+                                    if (c < e.cout) {
+                                        v[c] = expf(v[c] - mx_);
+                                        sum += v[c];
+                                    }
+#pragma unroll
+                                for (int c = 0; c < 16; ++c)
+                                    if (c < e.cout) dst[c * vox] = v[c] / sum;
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 16; ++c)
+                                    if (c < e.cout) dst[c * vox] = v[c];
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[set]);
             }
-            tc_fence_before();
-            mbar_arrive(acc_empty);
         }
     }
     tc_fence_before();
@@ -517,7 +581,7 @@ static int tc_geometry(int mode, int cin_chunks, int cout, TcGeom* g) {
     g->n_pass = mode == B200SEG_TC_UP ? 4 : 1;
     g->n_bimg = mode == B200SEG_TC_DOWN ? 8 * g->G : g->G;
     g->bimg_stride = g->steps_full * 2 * g->NB * 16;
-    g->TZmax = (256 - 16) / g->Cpad;   // <= 256 TMEM columns per CTA so that two CTAs share an SM
+    g->TZmax = (256 - 16) / g->Cpad;   // one accumulator set = 256 TMEM columns
     if (g->TZmax > 12) g->TZmax = 12;
     return B200SEG_OK;
 }
@@ -577,6 +641,15 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     rc = make_depilogue(epi, cout, in.n, oz, oy, ox, B200SEG_BF16, &de);
     if (rc) return rc;
 
+    int dev = 0, sms = 148;
+    B200SEG_CHECK_CUDA(cudaGetDevice(&dev));
+    B200SEG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // variant 2 (default): one CTA per SM, two accumulator sets; variant 1: two CTAs per SM, one set each
+    static const int variant = [] {
+        const char* v = getenv("B200SEG_TC_VARIANT");
+        return (v && v[0] == '1') ? 1 : 2;
+    }();
+
     TcParams p{};
     p.mode = mode;
     p.Cpad = g.Cpad;
@@ -588,6 +661,7 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     p.bimg_stride = g.bimg_stride;
     p.n_pass = g.n_pass;
     p.n_bimg = g.n_bimg;
+    p.batch = in.n;
     p.chunk_base = in.c8_off;
     p.c8_total = in.c8_total;
     p.wpacked = static_cast<const uint8_t*>(wpacked);
@@ -605,9 +679,7 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     int TZ = (oz + ntz - 1) / ntz;
     if (mode == B200SEG_TC_UP && (TZ & 1)) ++TZ;
     {
-        // small grids: thinner z tiles until there are at least two waves of CTAs (or TZ bottoms out)
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        // small grids: thinner z tiles until every CTA slot has work (or TZ bottoms out)
         const int plane_tiles = (mode == B200SEG_TC_UP ? ((in.x + 7) / 8) * ((in.y + 15) / 16)
                                                        : ((ox + 7) / 8) * ((oy + 15) / 16)) * in.n;
         const int tz_min = mode == B200SEG_TC_UP ? 2 : 1;
@@ -632,10 +704,8 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
         p.zin_count = mode == B200SEG_TC_K3 ? TZ + 2 : 2 * TZ + 2;
     }
     p.out_z = oz;
-    if (de.out_ncdhw != nullptr) {
-        p.out_y = oy;
-        p.out_x = ox;
-    }
+    B200SEG_CHECK_ARG(p.zin_count <= kMaxZin, "conv3d_tc: tile walks %d input planes (max %d)", p.zin_count, kMaxZin);
+    B200SEG_CHECK_ARG(TZ * g.Cpad + 16 <= 256, "conv3d_tc: accumulator set exceeds 256 TMEM columns");
     // ---- tensor maps
     TcMaps maps;
     memset(&maps, 0, sizeof maps);
@@ -661,28 +731,30 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
             }
         }
     }
-    // ---- launch
-    const int bbuf = (g.bimg_stride + 127) & ~127;
-    const size_t fixed = static_cast<size_t>(kNA) * kAStageBytes + (2 * kNA + 2 * kMaxBuf + 2) * 8 + 16 + 72 * 4 +
-                         sizeof(PlaneTab) * kMaxZin + 3 * static_cast<size_t>(g.Cpad) * 4 + 64;
-    // double-buffer the weights when two CTAs per SM still fit (113 KB each)
-    p.nbuf = (fixed + 2 * static_cast<size_t>(bbuf) <= 112 * 1024) ? 2 : 1;
-    const size_t smem = fixed + static_cast<size_t>(p.nbuf) * bbuf;
-    B200SEG_CHECK_ARG(smem <= 227 * 1024, "conv3d_tc: %zu bytes of shared memory needed", smem);
-    B200SEG_CHECK_ARG(p.zin_count <= kMaxZin, "conv3d_tc: tile walks %d input planes (max %d)", p.zin_count, kMaxZin);
-    const uint32_t cols_needed = TZ * g.Cpad + 16;
-    dim3 grid(static_cast<unsigned>(p.tiles_x * p.tiles_y * p.tiles_z), static_cast<unsigned>(in.n));
+    // ---- shared memory: weight image ring (double-buffered when it fits) + A plane ring
+    p.bbuf_bytes = (g.bimg_stride + 127) & ~127;
+    const size_t misc = (2 * kMaxA + 8) * 8 + 16 + sizeof(PlaneTab) * kMaxZin + 3 * static_cast<size_t>(g.Cpad) * 4 + 256;
+    const size_t budget = variant == 2 ? 224 * 1024 : 112 * 1024;
+    p.nbuf = (misc + 2 * static_cast<size_t>(p.bbuf_bytes) + 4 * kAStageBytes <= budget) ? 2 : 1;
+    B200SEG_CHECK_ARG(misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + 3 * kAStageBytes <= budget,
+                      "conv3d_tc: weight image of %d bytes does not fit shared memory", p.bbuf_bytes);
+    long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / kAStageBytes);
+    if (na > kMaxA) na = kMaxA;
+    p.na = static_cast<int>(na);
+    const size_t smem = misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * kAStageBytes;
+    // ---- launch (persistent)
+    const long long n_tiles = 1LL * p.tiles_x * p.tiles_y * p.tiles_z * in.n;
+    const long long max_ctas = 1LL * sms * (variant == 2 ? 1 : 2);
+    dim3 grid(static_cast<unsigned>(n_tiles < max_ctas ? n_tiles : max_ctas));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define LAUNCH_TC(COLS)                                                                                          \
-    do {                                                                                                         \
-        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                static_cast<int>(smem)));                                        \
-        conv_tc_kernel<COLS><<<grid, kThreadsTc, smem, s>>>(maps, p);                                            \
-    } while (0)
-    if (cols_needed <= 64) LAUNCH_TC(64);
-    else if (cols_needed <= 128) LAUNCH_TC(128);
-    else if (cols_needed <= 256) LAUNCH_TC(256);
-    else LAUNCH_TC(512);
-#undef LAUNCH_TC
+    if (variant == 2) {
+        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(smem)));
+        conv_tc_kernel<2><<<grid, 384, smem, s>>>(maps, p);
+    } else {
+        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(smem)));
+        conv_tc_kernel<1><<<grid, 224, smem, s>>>(maps, p);
+    }
     return check_launch("conv3d_tc");
 }
