@@ -139,7 +139,7 @@ __device__ __forceinline__ void plane_window(int mode, int TZ, int zi, int& lo, 
 struct MmaBlk {
     uint32_t dcol, idesc, brow, acc;
 };
-struct PlaneTab {
+struct alignas(16) PlaneTab {
     MmaBlk blk[2][kMaxBlk];  // [0] = normal step, [1] = the very first step of a pass (first-touch split)
     int nblk[2];
 };
@@ -171,11 +171,28 @@ constexpr uint64_t kADescHi = (static_cast<uint64_t>((kHX * 16) >> 4) | (1ull <<
 constexpr uint64_t kBDescHi = (static_cast<uint64_t>(128 >> 4) | (1ull << 14)) << 32;         // SBO 128 B, version 1
 
 // Issue steps [st0, n) of one plane: descriptor deltas are immediates, the B image advances by bstep16 per step.
+// The normal-step MMA blocks of one plane, held in registers (prefetched one plane ahead by the issuer).
+struct PlaneRegs {
+    MmaBlk k0, k1, k2;
+    int nb;
+};
+__device__ __forceinline__ PlaneRegs load_plane_regs(const PlaneTab* pt) {
+    PlaneRegs r;
+    const uint4 a = *reinterpret_cast<const uint4*>(&pt->blk[0][0]);
+    const uint4 b = *reinterpret_cast<const uint4*>(&pt->blk[0][1]);
+    const uint4 c = *reinterpret_cast<const uint4*>(&pt->blk[0][2]);
+    r.k0 = MmaBlk{a.x, a.y, a.z, a.w};
+    r.k1 = MmaBlk{b.x, b.y, b.z, b.w};
+    r.k2 = MmaBlk{c.x, c.y, c.z, c.w};
+    r.nb = pt->nblk[0];
+    return r;
+}
+
 template <int KIND>
 __device__ __forceinline__ void issue_plane(int st0, uint32_t a16, uint32_t b16, uint32_t b_lbo, uint32_t bstep16,
-                                            uint32_t tacc, const PlaneTab& pt) {
-    const int nb = pt.nblk[0];
-    const MmaBlk k0 = pt.blk[0][0];
+                                            uint32_t tacc, const PlaneRegs& pr) {
+    const int nb = pr.nb;
+    const MmaBlk k0 = pr.k0;
     const uint32_t d0 = tacc + k0.dcol;
     if (nb == 1) {
         uint32_t bsum = b16 + k0.brow;
@@ -187,8 +204,8 @@ __device__ __forceinline__ void issue_plane(int st0, uint32_t a16, uint32_t b16,
             bsum += bstep16;
         }
     } else {
-        const MmaBlk k1 = pt.blk[0][1];
-        const MmaBlk k2 = pt.blk[0][nb > 2 ? 2 : 1];
+        const MmaBlk k1 = pr.k1;
+        const MmaBlk k2 = nb > 2 ? pr.k2 : pr.k1;
         const uint32_t d1 = tacc + k1.dcol, d2 = tacc + k2.dcol;
         uint32_t bs0 = b16 + k0.brow, bs1 = b16 + k1.brow, bs2 = b16 + k2.brow;
 #pragma unroll
@@ -223,8 +240,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint64_t* acc_full = empty_b + 2;        // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(tmem_slot + 2);     // kMaxZin entries
-    float* s_scale = reinterpret_cast<float*>(plane_tab + kMaxZin);
+    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(
+        (reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~static_cast<uintptr_t>(15));   // kMaxZin entries, 16-byte aligned
+    float* s_scale = reinterpret_cast<float*>(
+        (reinterpret_cast<uintptr_t>(plane_tab + kMaxZin) + 15) & ~static_cast<uintptr_t>(15));   // float4 reads
     float* s_shift = s_scale + p.Cpad;
     float* s_slope = s_shift + p.Cpad;
 
@@ -329,38 +348,59 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     } else if (warp == 1) {
         // =============================================================== MMA issuer
         if (elect_one()) {
-            uint32_t a_it = 0, b_it = 0, unit = 0;
+            // everything the loop needs lives in registers: no divisions, no parameter re-loads per MMA
+            const int mode = p.mode, na = p.na, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G, n_pass = p.n_pass;
+            const bool lone_last = p.lone_last != 0;
+            uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, unit = 0;
             const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+            const uint32_t bbuf16 = static_cast<uint32_t>(p.bbuf_bytes) >> 4;
             const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
             const uint32_t bstep16 = 2 * p.NB;                          // one step of a B image, in 16-byte units
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
+                for (int pass = 0; pass < n_pass; ++pass, ++unit) {
                     const uint32_t set = kSets == 2 ? (unit & 1) : 0;
                     mbar_wait(&acc_empty[set], ((kSets == 2 ? (unit >> 1) : unit) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tacc = tmem + set * 256;
-                    for (int bi = 0; bi < p.n_bimg; ++bi, ++b_it) {
-                        const int g = bi % p.G;
-                        const bool lone = p.lone_last && g == p.G - 1;
+                    int g = 0, gq = 0;   // bi = gq * G + g
+                    for (int bi = 0; bi < n_bimg; ++bi) {
+                        const bool lone = lone_last && g == G - 1;
                         int zi0 = 0, zstep = 1, pp = 0;
-                        if (p.mode == B200SEG_TC_DOWN) {
-                            zi0 = bi / (4 * p.G);
+                        if (mode == B200SEG_TC_DOWN) {
+                            zi0 = gq >> 2;
                             zstep = 2;
-                            pp = (bi / p.G) % 4;
-                        } else if (p.mode == B200SEG_TC_UP) {
+                            pp = gq & 3;
+                        } else if (mode == B200SEG_TC_UP) {
                             pp = pass;
                         }
-                        const int kind = (p.mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
-                        const uint32_t pbase = parity_base(p.mode, pp);
-                        const uint32_t bs = b_it % p.nbuf;
-                        mbar_wait(&full_b[bs], (b_it / p.nbuf) & 1);
+                        if (++g == G) {
+                            g = 0;
+                            ++gq;
+                        }
+                        const int kind = (mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
+                        const uint32_t pbase = parity_base(mode, pp);
+                        const uint32_t bs = b_s;
+                        mbar_wait(&full_b[bs], b_ph);
                         tc_fence_after();
-                        const uint32_t b16 = sB16 + bs * (p.bbuf_bytes >> 4);
+                        if (++b_s == static_cast<uint32_t>(nbuf)) {
+                            b_s = 0;
+                            b_ph ^= 1;
+                        }
+                        const uint32_t b16 = sB16 + bs * bbuf16;
                         const PlaneTab* pt = plane_tab + zi0;
-                        for (int j = 0; j < n_img_planes; ++j, ++a_it, pt += zstep) {
-                            const uint32_t s = a_it % p.na;
-                            mbar_wait(&full_a[s], (a_it / p.na) & 1);
+                        PlaneRegs cur = load_plane_regs(pt);
+                        for (int j = 0; j < n_img_planes; ++j) {
+                            // prefetch the next plane's MMA blocks before blocking on this plane's data
+                            const PlaneTab* ptn = pt + zstep;
+                            PlaneRegs nxt = cur;
+                            if (j + 1 < n_img_planes) nxt = load_plane_regs(ptn);
+                            const uint32_t s = a_s;
+                            mbar_wait(&full_a[s], a_ph);
                             tc_fence_after();
+                            if (++a_s == static_cast<uint32_t>(na)) {
+                                a_s = 0;
+                                a_ph ^= 1;
+                            }
                             const uint32_t a16 = sA16 + s * (kAStageBytes >> 4) + pbase;
                             int st0 = 0;
                             if (bi == 0) {
@@ -382,12 +422,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                                 st0 = 1;
                             }
                             switch (kind) {
-                                case kK3Full: issue_plane<kK3Full>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
-                                case kK3Lone: issue_plane<kK3Lone>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
-                                case kS2Full: issue_plane<kS2Full>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
-                                default: issue_plane<kS2Lone>(st0, a16, b16, b_lbo, bstep16, tacc, *pt); break;
+                                case kK3Full: issue_plane<kK3Full>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
+                                case kK3Lone: issue_plane<kK3Lone>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
+                                case kS2Full: issue_plane<kS2Full>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
+                                default: issue_plane<kS2Lone>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
                             }
                             umma_commit(&empty_a[s]);
+                            cur = nxt;
+                            pt = ptn;
                         }
                         umma_commit(&empty_b[bs]);
                     }
@@ -431,60 +473,98 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 }
                 const uint32_t tbase = tmem + set * 256 + (static_cast<uint32_t>(lg * 32) << 16);
                 if (e.out_ncdhw == nullptr) {
-                    int item = 0;
-                    for (int q = 0; q < p.TZ; ++q) {
-                        const int oz = z0 + q;
-                        if (oz >= p.out_z) break;
+                    // Work items of this warp: (plane q, round of kR chunks).  Software pipelined: the TMEM and
+                    // residual loads of the next item are in flight while the current one is converted and stored.
+                    constexpr int kR = 3;
+                    const int nq = min(p.TZ, p.out_z - z0);
+                    const int rounds = (c8 + kR - 1) / kR;
+                    auto load_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
                         const uint32_t taddr = tbase + q * p.Cpad;
-                        // 5 chunks (40 channels) per round: TMEM loads, residual loads, then math + stores
-                        for (int c0 = 0; c0 < c8; c0 += 5, ++item) {
-                            if (kHalves == 2 && (item & 1) != half) continue;
-                            uint32_t r[5][8];
 #pragma unroll
-                            for (int j = 0; j < 5; ++j)
-                                if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
-                            uint4 res[5];
-                            if (valid && has_res) {
+                        for (int j = 0; j < kR; ++j)
+                            if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
+                        if (valid && has_res) {
 #pragma unroll
-                                for (int j = 0; j < 5; ++j)
-                                    if (c0 + j < c8 && c0 + j < e.split_c8)
-                                        res[j] = __ldg(reinterpret_cast<const uint4*>(e.residual.data) +
-                                                       vox_index(e.residual, n, c0 + j, oz, oy, ox));
-                            }
-                            tmem_ld_wait();
-                            if (valid) {
+                            for (int j = 0; j < kR; ++j)
+                                if (c0 + j < c8 && c0 + j < e.split_c8)
+                                    res[j] = __ldg(reinterpret_cast<const uint4*>(e.residual.data) +
+                                                   vox_index(e.residual, n, c0 + j, z0 + q, oy, ox));
+                        }
+                    };
+                    auto finish_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
+                        if (!valid) return;
+                        const int oz = z0 + q;
 #pragma unroll
-                                for (int j = 0; j < 5; ++j) {
-                                    const int cc = c0 + j;
-                                    if (cc >= c8) continue;
-                                    float v[8];
+                        for (int j = 0; j < kR; ++j) {
+                            const int cc = c0 + j;
+                            if (cc >= c8) continue;
+                            float v[8];
+                            {
+                                // per-channel parameters: 6 x 128-bit broadcast loads per chunk
+                                const float4* ps = reinterpret_cast<const float4*>(s_scale + cc * 8);
+                                const float4* ph = reinterpret_cast<const float4*>(s_shift + cc * 8);
+                                const float4* pl = reinterpret_cast<const float4*>(s_slope + cc * 8);
+                                const float4 s0 = ps[0], s1 = ps[1], h0 = ph[0], h1 = ph[1], l0 = pl[0], l1 = pl[1];
+                                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                                const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const int c = cc * 8 + i;
-                                        float tv = fmaf(__uint_as_float(r[j][i]), s_scale[c], s_shift[c]);
-                                        v[i] = tv > 0.f ? tv : tv * s_slope[c];
-                                    }
-                                    const bool to0 = cc < e.split_c8;
-                                    if (to0 && has_res) {
-                                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
-#pragma unroll
-                                        for (int i = 0; i < 4; ++i) {
-                                            float2 f = __bfloat1622float2(h[i]);
-                                            v[2 * i] += f.x;
-                                            v[2 * i + 1] += f.y;
-                                        }
-                                    }
-                                    uint4 o;
-                                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                                    if (to0)
-                                        reinterpret_cast<uint4*>(e.dst0.data)[vox_index(e.dst0, n, cc, oz, oy, ox)] = o;
-                                    else
-                                        reinterpret_cast<uint4*>(e.dst1.data)[vox_index(e.dst1, n, cc - e.split_c8, oz, oy, ox)] = o;
+                                for (int k = 0; k < 8; ++k) {
+                                    float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                                    v[k] = tv > 0.f ? tv : tv * sl[k];
                                 }
                             }
+                            const bool to0 = cc < e.split_c8;
+                            if (to0 && has_res) {
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float2 f = __bfloat1622float2(h[k]);
+                                    v[2 * k] += f.x;
+                                    v[2 * k + 1] += f.y;
+                                }
+                            }
+                            uint4 o;
+                            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                            if (to0)
+                                reinterpret_cast<uint4*>(e.dst0.data)[vox_index(e.dst0, n, cc, oz, oy, ox)] = o;
+                            else
+                                reinterpret_cast<uint4*>(e.dst1.data)[vox_index(e.dst1, n, cc - e.split_c8, oz, oy, ox)] = o;
                         }
+                    };
+                    // item cursor (q, rr): this warp takes every kHalves-th item of the (q-major) item list
+                    auto advance = [&](int& q, int& rr) {
+                        rr += kHalves;
+                        while (rr >= rounds) {
+                            rr -= rounds;
+                            ++q;
+                        }
+                    };
+                    uint32_t rA[kR][8], rB[kR][8];
+                    uint4 resA[kR], resB[kR];
+                    int q = 0, rr = kHalves == 2 ? half : 0;
+                    while (rr >= rounds) {
+                        rr -= rounds;
+                        ++q;
+                    }
+                    if (q < nq) load_item(q, rr * kR, rA, resA);
+                    while (q < nq) {
+                        tmem_ld_wait();
+                        int q2 = q, rr2 = rr;
+                        advance(q2, rr2);
+                        if (q2 < nq) load_item(q2, rr2 * kR, rB, resB);
+                        finish_item(q, rr * kR, rA, resA);
+                        q = q2;
+                        rr = rr2;
+                        if (q >= nq) break;
+                        tmem_ld_wait();
+                        advance(q2, rr2);
+                        if (q2 < nq) load_item(q2, rr2 * kR, rA, resA);
+                        finish_item(q, rr * kR, rB, resB);
+                        q = q2;
+                        rr = rr2;
                     }
                 } else {
                     // final layer: affine (+bias), optional channel softmax, fp32 NCDHW store (cout <= 16)
