@@ -41,6 +41,7 @@ constexpr int kHX = 10, kHY = 18;                 // halo extent of a 8 x 16 til
 constexpr int kChunkBytes = kHX * kHY * 16;       // 2880: one 8-channel chunk of one halo plane
 constexpr int kAStageBytes = 2 * kChunkBytes;     // 5760
 constexpr int kMaxA = 12;                         // A ring depth (upper bound)
+constexpr int kMaxB = 16;                         // B image slots (ring of 1-2, or ALL images when they fit: resident)
 constexpr int kMaxZin = 28;                       // input planes a tile may walk (DOWN: 2*TZ+2, TZ <= 12)
 constexpr int kMaxBlk = 4;                        // MMAs (column blocks) per step and plane
 
@@ -61,6 +62,7 @@ struct TcParams {
     int maxp;         // planes per MMA
     int n_pass, n_bimg;  // passes and B images per pass
     int na, nbuf;     // A ring depth, B ring depth
+    int resident;     // 1: every weight image has its own slot and is loaded once per CTA (nbuf = n_pass * n_bimg)
     int batch;
     int chunk_base;   // in.c8_off
     int c8_total;     // in.c8_total
@@ -235,9 +237,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nbuf * p.bbuf_bytes);
     uint64_t* full_a = bars;                 // [kMaxA]
     uint64_t* empty_a = bars + kMaxA;        // [kMaxA]
-    uint64_t* full_b = bars + 2 * kMaxA;     // [2]
-    uint64_t* empty_b = full_b + 2;          // [2]
-    uint64_t* acc_full = empty_b + 2;        // [2]
+    uint64_t* full_b = bars + 2 * kMaxA;     // [kMaxB]
+    uint64_t* empty_b = full_b + kMaxB;      // [kMaxB]
+    uint64_t* acc_full = empty_b + kMaxB;    // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(
@@ -255,9 +257,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_init(&full_a[i], 1);
             mbar_init(&empty_a[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxB; ++i) {
             mbar_init(&full_b[i], 1);
             mbar_init(&empty_b[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], kEpiWarps * 32);
         }
@@ -328,7 +332,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         // =============================================================== B producer
         if (elect_one()) {
             uint32_t b_it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // resident mode: every image has its own slot, loaded once; otherwise a ring re-streamed per unit
+            const int n_rounds = p.resident ? 1 : (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                                      static_cast<int>(gridDim.x);
+            for (int round = 0; round < n_rounds; ++round) {
                 for (int pass = 0; pass < p.n_pass; ++pass) {
                     for (int bi = 0; bi < p.n_bimg; ++bi, ++b_it) {
                         const int g = bi % p.G;
@@ -350,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (elect_one()) {
             // everything the loop needs lives in registers: no divisions, no parameter re-loads per MMA
             const int mode = p.mode, na = p.na, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G, n_pass = p.n_pass;
-            const bool lone_last = p.lone_last != 0;
+            const bool lone_last = p.lone_last != 0, resident = p.resident != 0;
             uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, unit = 0;
             const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
             const uint32_t bbuf16 = static_cast<uint32_t>(p.bbuf_bytes) >> 4;
@@ -380,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         const int kind = (mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
                         const uint32_t pbase = parity_base(mode, pp);
                         const uint32_t bs = b_s;
-                        mbar_wait(&full_b[bs], b_ph);
+                        mbar_wait(&full_b[bs], resident ? 0u : b_ph);   // resident images complete phase 0 once
                         tc_fence_after();
                         if (++b_s == static_cast<uint32_t>(nbuf)) {
                             b_s = 0;
@@ -431,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             cur = nxt;
                             pt = ptn;
                         }
-                        umma_commit(&empty_b[bs]);
+                        if (!resident) umma_commit(&empty_b[bs]);
                     }
                     umma_commit(&acc_full[set]);
                 }
@@ -813,9 +820,16 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     }
     // ---- shared memory: weight image ring (double-buffered when it fits) + A plane ring
     p.bbuf_bytes = (g.bimg_stride + 127) & ~127;
-    const size_t misc = (2 * kMaxA + 8) * 8 + 16 + sizeof(PlaneTab) * kMaxZin + 3 * static_cast<size_t>(g.Cpad) * 4 + 256;
+    const size_t misc = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + sizeof(PlaneTab) * kMaxZin +
+                        3 * static_cast<size_t>(g.Cpad) * 4 + 256;
     const size_t budget = variant == 2 ? 224 * 1024 : 112 * 1024;
-    p.nbuf = (misc + 2 * static_cast<size_t>(p.bbuf_bytes) + 4 * kAStageBytes <= budget) ? 2 : 1;
+    // weights stay resident (one slot per image, loaded once per CTA) when the whole packed operand fits next to
+    // at least 8 A stages; otherwise the images stream through a ring (double-buffered when possible)
+    const int n_images = g.n_pass * g.n_bimg;
+    p.resident = (n_images <= kMaxB &&
+                  misc + static_cast<size_t>(n_images) * p.bbuf_bytes + 8 * kAStageBytes <= budget) ? 1 : 0;
+    p.nbuf = p.resident ? n_images
+                        : ((misc + 2 * static_cast<size_t>(p.bbuf_bytes) + 4 * kAStageBytes <= budget) ? 2 : 1);
     B200SEG_CHECK_ARG(misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + 3 * kAStageBytes <= budget,
                       "conv3d_tc: weight image of %d bytes does not fit shared memory", p.bbuf_bytes);
     long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / kAStageBytes);
