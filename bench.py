@@ -207,6 +207,7 @@ def run_gpu_arm(args) -> None:
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200SEG_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     import b200seg
@@ -305,7 +306,7 @@ def run_gpu_arm(args) -> None:
         "config": {"workload": WORKLOAD, "patch_batch": PATCH_BATCH, "volumes_per_step": world,
                    "partition": "one volume per GPU (cohort), no data-path collective",
                    "l2": "working set per step (>= 9 GB of activations, 100 MB volume) is far larger than the 126 MB L2"},
-        "e2e": {"value": world * vox / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * vol_bytes,
+        "e2e": {"value": world * vox / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": vol_bytes,
                 "d2h_bytes_per_step": vol_bytes, "ms_per_step": e2e_ms,
                 "api": "PatchPredict.predict(model, device, [subject]) with a pinned host volume; returns host probabilities"},
         "gpu_launches": gpu_launches,

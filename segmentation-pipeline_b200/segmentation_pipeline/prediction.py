@@ -188,17 +188,32 @@ class PatchPredict(Predictor):
         device = _require_cuda(device)
         label_attributes = {} if label_attributes is None else label_attributes
         out_subjects = []
+        volumes_on_device = []
         for subject in subjects:
             volume = subject["X"]["data"]
+            volume_dev = volume.to(device, non_blocking=True)   # one H2D per subject (async when pinned)
+            volumes_on_device.append(volume_dev)
             with torch.no_grad():
-                probs, labels = self.predict_volume(model, volume.to(device, non_blocking=True))
-            image = _tio.make_label_map(probs.cpu(), **copy.deepcopy(label_attributes))
+                probs, labels = self.predict_volume(model, volume_dev)
+            # D2H through pinned memory (the caching host allocator recycles the block once the caller drops it)
+            probs_host = torch.empty(probs.shape, dtype=probs.dtype, pin_memory=True)
+            probs_host.copy_(probs, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            image = _tio.make_label_map(probs_host, **copy.deepcopy(label_attributes))
             if labels is not None:
                 image[LABELS_KEY] = labels
             subject.add_image(image, "y_pred")
             out_subjects.append(_tio.enforce_consistent_affine(subject, "X"))
-        batch = collate_subjects(subjects, image_names=self.image_names, device=device)
-        batch["y_pred"] = torch.stack([subject["y_pred"]["data"] for subject in out_subjects])
+        # batch[name]: (S, C, W, H, D) on the device, as collate_subjects returns (utils/utils.py:75-85); the 'X'
+        # volumes are already there, so they are stacked on the device instead of being uploaded a second time
+        batch = {}
+        for name in self.image_names:
+            if name == "X":
+                batch[name] = volumes_on_device[0][None] if len(subjects) == 1 else torch.stack(volumes_on_device)
+            else:
+                batch.update(collate_subjects(subjects, image_names=[name], device=device))
+        preds = [subject["y_pred"]["data"] for subject in out_subjects]
+        batch["y_pred"] = preds[0][None] if len(preds) == 1 else torch.stack(preds)
         return out_subjects, batch
 
 
