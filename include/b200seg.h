@@ -151,6 +151,13 @@ int b200seg_finalize(const float* out, int32_t c, int32_t pw, int32_t ph, int32_
                      const int32_t* ch, const int32_t* cd, const int32_t border[3], float* probs,
                      int64_t* labels_i64, uint8_t* labels_u8, void* stream);
 
+/* Same, for an arbitrary sub-region of the accumulator: output voxel (i,j,k) of extent[] reads out[:, offset+ijk].
+ * Used by the z-slab multi-GPU mode, where each rank finalises only the planes it owns (count pointers are
+ * passed pre-offset to the rank's first plane). */
+int b200seg_finalize_region(const float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const int32_t* cw,
+                            const int32_t* ch, const int32_t* cd, const int32_t offset[3], const int32_t extent[3],
+                            float* probs, int64_t* labels_i64, uint8_t* labels_u8, void* stream);
+
 /* torch.argmax(data, dim=0, keepdim=True) on fp32 [C][V] -> int64 [V] and/or uint8 [V]. */
 int b200seg_argmax(const float* probs, int32_t c, int64_t voxels, int64_t* labels_i64, uint8_t* labels_u8,
                    void* stream);

@@ -56,6 +56,8 @@ _SIGNATURES = {
                                        c_int32, POINTER(c_int32), c_int32, c_void_p]),
     "b200seg_finalize": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                    POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200seg_finalize_region": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                          POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200seg_argmax": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200seg_confusion": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
 }
@@ -264,6 +266,26 @@ def finalize(out: torch.Tensor, counts, border: Sequence[int], probs: Optional[t
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_finalize(_ptr(out), c, pw, ph, pd, _ptr(cw), _ptr(ch), _ptr(cd), _i32(border),
                                            _ptr(probs), _ptr(labels_i64), _ptr(labels_u8), _stream()), "finalize")
+
+
+def finalize_region(out: torch.Tensor, counts, offset: Sequence[int], extent: Sequence[int],
+                    probs: Optional[torch.Tensor], labels_i64: Optional[torch.Tensor],
+                    labels_u8: Optional[torch.Tensor], count_offset: int = 0) -> None:
+    """finalize() for the sub-region [offset, offset + extent) of the accumulator; ``count_offset`` is the global
+    padded coordinate of the accumulator's first plane along axis 0 (z-slab mode)."""
+    _require_cuda(out, probs, labels_i64, labels_u8)
+    c, pw, ph, pd = out.shape
+    cw = ch = cd = None
+    cw_ptr = c_void_p(0)
+    if counts is not None:
+        cw, ch, cd = counts
+        for t in (cw, ch, cd):
+            assert t.dtype == torch.int32 and t.is_cuda
+        cw_ptr = c_void_p(cw.data_ptr() + 4 * int(count_offset))
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_finalize_region(_ptr(out), c, pw, ph, pd, cw_ptr, _ptr(ch), _ptr(cd), _i32(offset),
+                                                  _i32(extent), _ptr(probs), _ptr(labels_i64), _ptr(labels_u8),
+                                                  _stream()), "finalize_region")
 
 
 def argmax(probs: torch.Tensor, labels_i64: Optional[torch.Tensor] = None,

@@ -652,12 +652,24 @@ int b200seg_overlap_crop(float* out, int32_t c, int32_t pw, int32_t ph, int32_t 
 int b200seg_finalize(const float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const int32_t* cw,
                      const int32_t* ch, const int32_t* cd, const int32_t border[3], float* probs,
                      int64_t* labels_i64, uint8_t* labels_u8, void* stream) {
+    B200SEG_CHECK_ARG(pw > 0 && ph > 0 && pd > 0, "finalize: bad arguments");
+    const int32_t extent[3] = {pw - 2 * border[0], ph - 2 * border[1], pd - 2 * border[2]};
+    return b200seg_finalize_region(out, c, pw, ph, pd, cw, ch, cd, border, extent, probs, labels_i64, labels_u8, stream);
+}
+
+int b200seg_finalize_region(const float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const int32_t* cw,
+                            const int32_t* ch, const int32_t* cd, const int32_t offset[3], const int32_t extent[3],
+                            float* probs, int64_t* labels_i64, uint8_t* labels_u8, void* stream) {
     B200SEG_CHECK_ARG(out && c > 0 && pw > 0 && ph > 0 && pd > 0, "finalize: bad arguments");
     B200SEG_CHECK_ARG((cw == nullptr) == (ch == nullptr) && (cw == nullptr) == (cd == nullptr),
                       "finalize: give all three count arrays or none");
     B200SEG_CHECK_ARG(labels_u8 == nullptr || c <= 256, "finalize: uint8 labels need <= 256 classes");
-    const int W = pw - 2 * border[0], H = ph - 2 * border[1], D = pd - 2 * border[2];
-    B200SEG_CHECK_ARG(W > 0 && H > 0 && D > 0, "finalize: border larger than the volume");
+    const int32_t* border = offset;
+    const int W = extent[0], H = extent[1], D = extent[2];
+    B200SEG_CHECK_ARG(W > 0 && H > 0 && D > 0, "finalize: empty region");
+    B200SEG_CHECK_ARG(offset[0] >= 0 && offset[1] >= 0 && offset[2] >= 0 && offset[0] + W <= pw && offset[1] + H <= ph &&
+                          offset[2] + D <= pd,
+                      "finalize: region exceeds the accumulator");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     bool vec = (D % 4 == 0) && (pd % 4 == 0) && (border[2] % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                (probs == nullptr || (reinterpret_cast<uintptr_t>(probs) & 15) == 0) &&
