@@ -228,3 +228,24 @@ def test_segmentation_evaluator_matches_reference_fixture():
     np.testing.assert_array_equal(res["summary_stats"].data.numpy(), z["summary_stats"])
     vol = LabelMapEvaluator("pred")(subjects)["subject_stats"][["volume"]].to_numpy(dtype=np.float64)
     np.testing.assert_array_equal(vol, z["volumes"])
+
+
+def test_slab_mode_single_rank_equals_patch_predict():
+    """z-slab driver with the CUDA ops on one rank == PatchPredict.predict_volume, bit for bit."""
+    from segmentation_pipeline.distributed import CudaSlabOps, slab_predict
+    from segmentation_pipeline.grid import PatchGrid
+    from segmentation_pipeline.models import set_precision
+    from segmentation_pipeline.prediction import PatchPredict
+    meta, sd, model = _small_model()
+    vol = torch.randn(2, 40, 36, 28, generator=torch.Generator().manual_seed(23)).cuda()
+    set_precision("bf16")
+    try:
+        with torch.no_grad():
+            predictor = PatchPredict(patch_batch_size=5, patch_size=(16, 16, 16), patch_overlap=(8, 8, 4),
+                                     padding_mode="edge")
+            probs, labels = predictor.predict_volume(model, vol)
+            grid = PatchGrid(vol.shape[1:], (16, 16, 16), (8, 8, 4), "edge")
+            labels2, probs2 = slab_predict(vol, grid, CudaSlabOps(model, 5), gather_probs=True)
+    finally:
+        set_precision("auto")
+    assert torch.equal(labels, labels2) and torch.equal(probs, probs2)
