@@ -108,6 +108,17 @@ int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpacked, int64_
 /* Bytes of the packed operand image the engine expects for (mode, cin chunks, cout). */
 int64_t b200seg_conv3d_tc_wbytes(int32_t mode, int32_t cin_chunks, int32_t cout);
 
+/* ------------------------------------------------------------------------------------------------ normalisation
+ * nn.InstanceNorm3d (normalization_class of Block3d, components.py:53) in place on a blocked view, fused with the
+ * block's activation (slope: ReLU 0, LeakyReLU negative_slope, none 1) and the `res_conv(x_in) + x` add
+ * (residual.data == NULL when unused).  Statistics: biased variance over the spatial extent per (sample, channel),
+ * two-pass (mean, then squared deviations), warp-shuffle + fixed-order partial sums (deterministic).
+ * gamma / beta: fp32 device arrays of x.c entries or NULL (affine=False).  scratch: device memory of at least
+ * b200seg_instnorm_scratch_bytes(x) bytes. */
+int64_t b200seg_instnorm_scratch_bytes(b200seg_view x);
+int b200seg_instnorm(b200seg_view x, const float* gamma, const float* beta, float eps, float slope,
+                     b200seg_view residual, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ resampling
  * nn.AvgPool3d(2, 2, count_include_pad=False) (modular_unet.py:40-41, nested_residual_unet.py:67) and
  * nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True) (modular_unet.py:38-39, :68), writing

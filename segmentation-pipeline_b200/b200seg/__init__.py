@@ -44,6 +44,8 @@ _SIGNATURES = {
                                         POINTER(Epilogue), c_void_p]),
     "b200seg_conv3d_tc": (c_int32, [c_int32, View, c_void_p, c_int64, c_int32, POINTER(Epilogue), c_void_p]),
     "b200seg_conv3d_tc_wbytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "b200seg_instnorm_scratch_bytes": (c_int64, [View]),
+    "b200seg_instnorm": (c_int32, [View, c_void_p, c_void_p, c_float, c_float, View, c_void_p, c_int64, c_void_p]),
     "b200seg_avgpool2": (c_int32, [View, View, c_void_p]),
     "b200seg_upsample_trilinear2": (c_int32, [View, View, c_void_p]),
     "b200seg_copy_view": (c_int32, [View, View, c_void_p]),
@@ -183,6 +185,17 @@ def conv3d_tc(mode: int, inp: View, wpacked: torch.Tensor, cout: int, epi: Epilo
 
 def conv3d_tc_wbytes(mode: int, cin_chunks: int, cout: int) -> int:
     return int(load_library().b200seg_conv3d_tc_wbytes(mode, cin_chunks, cout))
+
+
+def instnorm(x: View, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float, slope: float,
+             residual: View = NULL_VIEW) -> None:
+    """In-place InstanceNorm3d + activation (+ residual) on a blocked view (three streaming launches)."""
+    lib = load_library()
+    need = int(lib.b200seg_instnorm_scratch_bytes(x))
+    scratch = torch.empty(need // 4, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+    _LAUNCHES[0] += 3
+    _check(lib.b200seg_instnorm(x, _ptr(gamma), _ptr(beta), float(eps), float(slope), residual, _ptr(scratch), need,
+                                _stream()), "instnorm")
 
 
 def avgpool2(inp: View, out: View) -> None:

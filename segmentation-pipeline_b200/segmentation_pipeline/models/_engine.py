@@ -150,6 +150,14 @@ class CompiledPlan:
             call.dst0, call.dst1, call.split, call.residual = d0, d1, split, res
             self.calls.append(call)
 
+    def _norm_params(self, op):
+        cache = self.__dict__.setdefault("_norm_cache", {})
+        hit = cache.get(id(op))
+        if hit is None:
+            hit = (None if op.gamma is None else self._dev(op.gamma), None if op.beta is None else self._dev(op.beta))
+            cache[id(op)] = hit
+        return hit
+
     def _new_call(self, op: ConvOp, tc: bool, geom) -> _ConvCall:
         call = _ConvCall()
         call.tc, call.mode, call.src = tc, op.mode, op.src
@@ -222,6 +230,9 @@ class CompiledPlan:
                 lib.upsample_trilinear2(view(call.src), view(call.dst))
             elif isinstance(call, SoftmaxOp):
                 lib.softmax_ncdhw(out, call.sm_channels, call.diag_bias)
+            elif isinstance(call, _plan.InstNormOp):
+                gamma, beta = self._norm_params(call)
+                lib.instnorm(view(call.ref), gamma, beta, call.eps, call.slope, view(call.residual))
             else:  # pragma: no cover
                 raise RuntimeError(f"unknown op {call}")
             if TRACE is not None:

@@ -85,6 +85,18 @@ class SoftmaxOp:
 
 
 @dataclass
+class InstNormOp:
+    """nn.InstanceNorm3d in place on ``ref`` + activation (+ residual): cannot be folded into the conv epilogue
+    because its statistics depend on the whole conv output."""
+    ref: Ref
+    gamma: Optional[np.ndarray]
+    beta: Optional[np.ndarray]
+    eps: float
+    slope: float
+    residual: Optional[Ref] = None
+
+
+@dataclass
 class Plan:
     in_channels: int
     out_channels: int
@@ -129,7 +141,7 @@ def _norm_affine(norm: Optional[nn.Module], cout: int):
     """(scale, shift) of an eval-mode normalisation layer."""
     if norm is None or isinstance(norm, nn.Identity):
         return np.ones(cout, np.float64), np.zeros(cout, np.float64)
-    if isinstance(norm, nn.BatchNorm3d):
+    if isinstance(norm, (nn.BatchNorm3d, nn.InstanceNorm3d)):
         if norm.running_mean is None:
             raise UnsupportedModule("BatchNorm3d without running statistics")
         var = norm.running_var.detach().double().cpu().numpy()
@@ -139,6 +151,18 @@ def _norm_affine(norm: Optional[nn.Module], cout: int):
         scale = gamma / np.sqrt(var + norm.eps)
         return scale, beta - mean * scale
     raise UnsupportedModule(f"normalisation {type(norm).__name__} is not lowered yet (BatchNorm3d eval / none are)")
+
+
+def _instance_norm_params(norm: Optional[nn.Module], cout: int):
+    """-> (gamma, beta, eps) when ``norm`` is an InstanceNorm3d that normalises with per-sample statistics
+    (the default: track_running_stats=False, or training statistics are not available), else None."""
+    if not isinstance(norm, nn.InstanceNorm3d):
+        return None
+    if norm.track_running_stats and norm.running_mean is not None:
+        return None     # eval mode uses the running statistics: folds like BatchNorm
+    gamma = None if norm.weight is None else norm.weight.detach().float().cpu().numpy()
+    beta = None if norm.bias is None else norm.bias.detach().float().cpu().numpy()
+    return gamma, beta, float(norm.eps)
 
 
 def _act_slope(act: Optional[nn.Module], cout: int) -> np.ndarray:
@@ -181,10 +205,24 @@ def _lower_block(plan: Plan, level: int, name: str, src: Ref, segments, convs, n
     cur, cur_segments = src, segments
     for i, conv in enumerate(convs):
         w, b = _conv_weight_bias(conv)
-        scale, shift, slope = _epilogue_arrays(cout, b, norms[i], acts[i])
         last = i == n - 1
         dst = out if last else Ref(plan.add_buffer(f"{name}.t{i}", cout, level), 0, cout)
-        if i == 0 and res_conv is not None and not last and cout % 8 == 0:
+        inst = _instance_norm_params(norms[i], cout)
+        if inst is not None:
+            # statistics need the whole conv output: raw conv (+bias) first, then the in-place norm kernel, which
+            # also applies the activation and, on the last conv, the residual add
+            scale, shift, slope = _epilogue_arrays(cout, b, None, None)
+        else:
+            scale, shift, slope = _epilogue_arrays(cout, b, norms[i], acts[i])
+        if inst is not None:
+            if i == 0 and res_conv is not None:
+                plan.ops.append(ConvOp(K3, cur, cur_segments, rw, r_scale, r_shift, r_slope, dst0=res_ref,
+                                       name=f"{name}.res_conv"))
+            plan.ops.append(ConvOp(K3, cur, cur_segments, w, scale, shift, slope, dst0=dst, name=f"{name}.conv{i}"))
+            gamma, beta, eps = inst
+            plan.ops.append(InstNormOp(dst, gamma, beta, eps, float(_act_slope(acts[i], 1)[0]),
+                                       residual=res_ref if (last and res_conv is not None) else None))
+        elif i == 0 and res_conv is not None and not last and cout % 8 == 0:
             # conv0 and res_conv read the same tensor: one contraction with N = 2*Cout, two destinations
             op = ConvOp(K3, cur, cur_segments, torch.cat([w, rw], 0), np.concatenate([scale, r_scale]),
                         np.concatenate([shift, r_shift]), np.concatenate([slope, r_slope]), dst0=dst, dst1=res_ref,

@@ -69,6 +69,24 @@ def test_avgpool_and_trilinear_match_torch(lib):
     assert rel_err(got.cpu(), ref) <= 2e-6
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 1e-2)])
+def test_instance_norm_fused(lib, dtype, tol):
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 11, 9, 10, 12, generator=g) * 3 + 5      # large mean: the two-pass variance matters
+    res = torch.randn(2, 11, 9, 10, 12, generator=g)
+    gamma, beta = torch.rand(11, generator=g) + 0.5, torch.randn(11, generator=g)
+    xr = x.to(dtype).float()
+    ref = F.leaky_relu(F.instance_norm(xr, weight=gamma, bias=beta, eps=1e-5), 0.1) + res.to(dtype).float()
+    buf, rbuf = to_blocked(lib, x, dtype), to_blocked(lib, res, dtype)
+    lib.instnorm(buf.view(11), dev(gamma), dev(beta), 1e-5, 0.1, rbuf.view(11))
+    assert rel_err(from_blocked(lib, buf, 11), ref) <= tol
+    assert buf.tensor[:, 1, ..., 3:].abs().max().item() == 0      # padding channels stay zero
+    # affine=False, no residual, ReLU
+    buf = to_blocked(lib, x, dtype)
+    lib.instnorm(buf.view(11), None, None, 1e-5, 0.0)
+    assert rel_err(from_blocked(lib, buf, 11), F.relu(F.instance_norm(xr, eps=1e-5))) <= tol
+
+
 def test_softmax_and_stochastic_matrix(lib):
     from oracle import unet
     x = torch.randn(2, 5, 3, 4, 5)

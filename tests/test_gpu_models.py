@@ -42,7 +42,7 @@ def build_model(meta):
 
 
 FP32_CASES = ["models_modular_blur", "models_modular_default", "models_modular_leaky_logits", "models_nested",
-              "models_nested_10class"]
+              "models_nested_10class", "models_modular_ws_instnorm"]
 
 
 @pytest.mark.parametrize("name", FP32_CASES)
@@ -63,7 +63,7 @@ def test_fp32_network_matches_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name", ["models_modular_blur", "models_modular_default", "models_modular_leaky_logits",
-                                  "models_nested", "models_nested_10class"])
+                                  "models_nested", "models_nested_10class", "models_modular_ws_instnorm"])
 def test_bf16_network_within_tolerance(name):
     from segmentation_pipeline.models import set_precision
     meta, sd, x, y = load_case(name)
@@ -99,12 +99,11 @@ def test_autocast_selects_bf16_path():
 
 def test_unsupported_and_training_mode_raise():
     from torch import nn
-    meta, sd, x, y = load_case("models_modular_ws_instnorm")
-    model = build_model(meta)
-    model.load_state_dict(sd)
+    from segmentation_pipeline import models as M
+    model = M.ModularUNet(1, 2, [8, 8], 2, block_params={"activation_class": nn.Tanh, "activation_params": {}})
     model.eval().cuda()
     with pytest.raises(NotImplementedError):
-        model(x.cuda())           # InstanceNorm3d is not lowered: loud error, no silent ATen path
+        model(torch.zeros(1, 1, 8, 8, 8).cuda())     # Tanh is not lowered: loud error, no silent ATen path
     meta, sd, x, y = load_case("models_modular_default")
     model = build_model(meta).cuda().train()
     with pytest.raises(NotImplementedError):
