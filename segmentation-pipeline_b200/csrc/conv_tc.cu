@@ -190,38 +190,70 @@ __device__ __forceinline__ PlaneRegs load_plane_regs(const PlaneTab* pt) {
     return r;
 }
 
-template <int KIND>
-__device__ __forceinline__ void issue_plane(int st0, uint32_t a16, uint32_t b16, uint32_t b_lbo, uint32_t bstep16,
+// Steps [ST0, n) of one plane.  The B descriptor low word is (b16 + brow + st*bstep16) | LBO<<16; the sum stays below
+// 2^14, so the step offset can be added AFTER the OR -- one value per block, then uniform adds per MMA.
+template <int KIND, int ST0>
+__device__ __forceinline__ void issue_plane(uint32_t a16, uint32_t b16, uint32_t b_lbo, uint32_t bstep16,
                                             uint32_t tacc, const PlaneRegs& pr) {
     const int nb = pr.nb;
     const MmaBlk k0 = pr.k0;
     const uint32_t d0 = tacc + k0.dcol;
+    const uint32_t bl0 = (b16 + k0.brow) | b_lbo;
     if (nb == 1) {
-        uint32_t bsum = b16 + k0.brow;
 #pragma unroll
-        for (int st = 0; st < Steps<KIND>::n; ++st) {
-            if (st >= st0)
-                umma_bf16(d0, kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(st)),
-                          kBDescHi | static_cast<uint64_t>(bsum | b_lbo), k0.idesc, 1u);
-            bsum += bstep16;
-        }
+        for (int st = ST0; st < Steps<KIND>::n; ++st)
+            umma_bf16(d0, kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(st)),
+                      kBDescHi | static_cast<uint64_t>(bl0 + st * bstep16), k0.idesc, 1u);
     } else {
         const MmaBlk k1 = pr.k1;
         const MmaBlk k2 = nb > 2 ? pr.k2 : pr.k1;
         const uint32_t d1 = tacc + k1.dcol, d2 = tacc + k2.dcol;
-        uint32_t bs0 = b16 + k0.brow, bs1 = b16 + k1.brow, bs2 = b16 + k2.brow;
+        const uint32_t bl1 = (b16 + k1.brow) | b_lbo, bl2 = (b16 + k2.brow) | b_lbo;
 #pragma unroll
-        for (int st = 0; st < Steps<KIND>::n; ++st) {
-            if (st >= st0) {
-                const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(st));
-                umma_bf16(d0, adesc, kBDescHi | static_cast<uint64_t>(bs0 | b_lbo), k0.idesc, 1u);
-                umma_bf16(d1, adesc, kBDescHi | static_cast<uint64_t>(bs1 | b_lbo), k1.idesc, 1u);
-                if (nb > 2) umma_bf16(d2, adesc, kBDescHi | static_cast<uint64_t>(bs2 | b_lbo), k2.idesc, 1u);
-            }
-            bs0 += bstep16;
-            bs1 += bstep16;
-            bs2 += bstep16;
+        for (int st = ST0; st < Steps<KIND>::n; ++st) {
+            const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(st));
+            umma_bf16(d0, adesc, kBDescHi | static_cast<uint64_t>(bl0 + st * bstep16), k0.idesc, 1u);
+            umma_bf16(d1, adesc, kBDescHi | static_cast<uint64_t>(bl1 + st * bstep16), k1.idesc, 1u);
+            if (nb > 2) umma_bf16(d2, adesc, kBDescHi | static_cast<uint64_t>(bl2 + st * bstep16), k2.idesc, 1u);
         }
+    }
+}
+
+// All planes of one weight image: wait for the plane's halo, issue its steps, release the stage.  The next plane's
+// MMA blocks are fetched from shared memory before blocking on the current plane's data.
+template <int KIND>
+__device__ __forceinline__ void run_image(bool first_image, int n_planes, int zstep, const PlaneTab* pt,
+                                          uint64_t* full_a, uint64_t* empty_a, uint32_t& a_s, uint32_t& a_ph, int na,
+                                          uint32_t sA16, uint32_t pbase, uint32_t b16, uint32_t b_lbo,
+                                          uint32_t bstep16, uint32_t tacc) {
+    PlaneRegs cur = load_plane_regs(pt);
+    for (int j = 0; j < n_planes; ++j) {
+        const PlaneTab* ptn = pt + zstep;
+        PlaneRegs nxt = cur;
+        if (j + 1 < n_planes) nxt = load_plane_regs(ptn);
+        const uint32_t s = a_s;
+        mbar_wait(&full_a[s], a_ph);
+        tc_fence_after();
+        if (++a_s == static_cast<uint32_t>(na)) {
+            a_s = 0;
+            a_ph ^= 1;
+        }
+        const uint32_t a16 = sA16 + s * (kAStageBytes >> 4) + pbase;
+        if (first_image) {
+            // first step of the pass: first-touch split (planes seen for the first time overwrite)
+            const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(0));
+            const int nb = pt->nblk[1];
+            for (int b = 0; b < nb; ++b) {
+                const MmaBlk k = pt->blk[1][b];
+                umma_bf16(tacc + k.dcol, adesc, kBDescHi | static_cast<uint64_t>((b16 + k.brow) | b_lbo), k.idesc, k.acc);
+            }
+            issue_plane<KIND, 1>(a16, b16, b_lbo, bstep16, tacc, cur);
+        } else {
+            issue_plane<KIND, 0>(a16, b16, b_lbo, bstep16, tacc, cur);
+        }
+        umma_commit(&empty_a[s]);
+        cur = nxt;
+        pt = ptn;
     }
 }
 
@@ -395,48 +427,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         }
                         const uint32_t b16 = sB16 + bs * bbuf16;
                         const PlaneTab* pt = plane_tab + zi0;
-                        PlaneRegs cur = load_plane_regs(pt);
-                        for (int j = 0; j < n_img_planes; ++j) {
-                            // prefetch the next plane's MMA blocks before blocking on this plane's data
-                            const PlaneTab* ptn = pt + zstep;
-                            PlaneRegs nxt = cur;
-                            if (j + 1 < n_img_planes) nxt = load_plane_regs(ptn);
-                            const uint32_t s = a_s;
-                            mbar_wait(&full_a[s], a_ph);
-                            tc_fence_after();
-                            if (++a_s == static_cast<uint32_t>(na)) {
-                                a_s = 0;
-                                a_ph ^= 1;
-                            }
-                            const uint32_t a16 = sA16 + s * (kAStageBytes >> 4) + pbase;
-                            int st0 = 0;
-                            if (bi == 0) {
-                                // first step of the pass: first-touch split (planes seen for the first time overwrite)
-                                uint32_t d0;
-                                switch (kind) {
-                                    case kK3Full: d0 = Steps<kK3Full>::delta(0); break;
-                                    case kK3Lone: d0 = Steps<kK3Lone>::delta(0); break;
-                                    case kS2Full: d0 = Steps<kS2Full>::delta(0); break;
-                                    default: d0 = Steps<kS2Lone>::delta(0); break;
-                                }
-                                const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + d0);
-                                const int nb = pt->nblk[1];
-                                for (int b = 0; b < nb; ++b) {
-                                    const MmaBlk k = pt->blk[1][b];
-                                    umma_bf16(tacc + k.dcol, adesc, kBDescHi | static_cast<uint64_t>((b16 + k.brow) | b_lbo),
-                                              k.idesc, k.acc);
-                                }
-                                st0 = 1;
-                            }
-                            switch (kind) {
-                                case kK3Full: issue_plane<kK3Full>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
-                                case kK3Lone: issue_plane<kK3Lone>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
-                                case kS2Full: issue_plane<kS2Full>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
-                                default: issue_plane<kS2Lone>(st0, a16, b16, b_lbo, bstep16, tacc, cur); break;
-                            }
-                            umma_commit(&empty_a[s]);
-                            cur = nxt;
-                            pt = ptn;
+                        const bool first_image = bi == 0;
+                        switch (kind) {
+                            case kK3Full:
+                                run_image<kK3Full>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                break;
+                            case kK3Lone:
+                                run_image<kK3Lone>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                break;
+                            case kS2Full:
+                                run_image<kS2Full>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                break;
+                            default:
+                                run_image<kS2Lone>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                break;
                         }
                         if (!resident) umma_commit(&empty_b[bs]);
                     }
