@@ -460,8 +460,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int m = lg * 32 + lane;       // accumulator row
         const int my = m >> 3, mx = m & 7;
         const DEpilogue& e = p.epi;
-        const int c8 = p.Cpad / 8;
+        const int Cpad = p.Cpad, c8 = p.Cpad / 8, split_c8 = e.split_c8;
         const bool has_res = e.residual.data != nullptr;
+        // destination geometry hoisted into registers (dst0 / dst1 / residual share the output's spatial extent)
+        const int o_x = e.dst0.x;
+        const long long o_plane = static_cast<long long>(e.dst0.y) * e.dst0.x;
+        const long long o_cs = e.dst0.chunk_stride;
+        uint4* const d0_base = reinterpret_cast<uint4*>(e.dst0.data) + e.dst0.c8_off * o_cs;
+        const long long d0_ss = e.dst0.sample_stride;
+        uint4* const d1_base = reinterpret_cast<uint4*>(e.dst1.data) + (e.dst1.c8_off - split_c8) * o_cs;
+        const long long d1_ss = e.dst1.sample_stride;
+        const uint4* const r_base = reinterpret_cast<const uint4*>(e.residual.data) + e.residual.c8_off * o_cs;
+        const long long r_ss = e.residual.sample_stride;
         uint32_t unit = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             int t = tile;
@@ -493,22 +503,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     constexpr int kR = 3;
                     const int nq = min(p.TZ, p.out_z - z0);
                     const int rounds = (c8 + kR - 1) / kR;
+                    // per-unit base pointers (16-byte vectors): element (chunk cc, plane q) = base[cc * cs + q * plane]
+                    const long long spatial = static_cast<long long>(z0) * o_plane + oy * o_x + ox;
+                    uint4* const p0 = d0_base + n * d0_ss + spatial;
+                    uint4* const p1 = d1_base + n * d1_ss + spatial;          // already offset by -split_c8 chunks
+                    const uint4* const pr = r_base + n * r_ss + spatial;
                     auto load_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
-                        const uint32_t taddr = tbase + q * p.Cpad;
+                        const uint32_t taddr = tbase + q * Cpad;
 #pragma unroll
                         for (int j = 0; j < kR; ++j)
                             if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
                         if (valid && has_res) {
 #pragma unroll
                             for (int j = 0; j < kR; ++j)
-                                if (c0 + j < c8 && c0 + j < e.split_c8)
-                                    res[j] = __ldg(reinterpret_cast<const uint4*>(e.residual.data) +
-                                                   vox_index(e.residual, n, c0 + j, z0 + q, oy, ox));
+                                if (c0 + j < c8 && c0 + j < split_c8)
+                                    res[j] = __ldg(pr + (c0 + j) * o_cs + static_cast<long long>(q) * o_plane);
                         }
                     };
                     auto finish_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
                         if (!valid) return;
-                        const int oz = z0 + q;
+                        const long long qoff = static_cast<long long>(q) * o_plane;
 #pragma unroll
                         for (int j = 0; j < kR; ++j) {
                             const int cc = c0 + j;
@@ -529,7 +543,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                                     v[k] = tv > 0.f ? tv : tv * sl[k];
                                 }
                             }
-                            const bool to0 = cc < e.split_c8;
+                            const bool to0 = cc < split_c8;
                             if (to0 && has_res) {
                                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
 #pragma unroll
@@ -543,10 +557,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-                            if (to0)
-                                reinterpret_cast<uint4*>(e.dst0.data)[vox_index(e.dst0, n, cc, oz, oy, ox)] = o;
-                            else
-                                reinterpret_cast<uint4*>(e.dst1.data)[vox_index(e.dst1, n, cc - e.split_c8, oz, oy, ox)] = o;
+                            (to0 ? p0 : p1)[cc * o_cs + qoff] = o;
                         }
                     };
                     // item cursor (q, rr): this warp takes every kHalves-th item of the (q-major) item list
