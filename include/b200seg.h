@@ -70,6 +70,8 @@ typedef struct b200seg_epilogue {
     b200seg_view residual;   /* data == NULL when unused; added to dst0 channels only */
     float* out_ncdhw;        /* softmax / final output, fp32 [N][cout][Z][Y][X]; NULL when unused */
     int32_t softmax;         /* 1: softmax over channels before writing out_ncdhw; 0: raw values */
+    int32_t slope01;         /* 1: the caller guarantees 0 <= slope[c] <= 1 (ReLU / LeakyReLU / none), which lets the
+                                tensor-core epilogue use max(v, v*slope); 0: general v > 0 ? v : v*slope */
 } b200seg_epilogue;
 
 /* ------------------------------------------------------------------------------------------------ misc */

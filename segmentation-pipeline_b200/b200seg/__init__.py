@@ -29,7 +29,8 @@ class View(Structure):
 class Epilogue(Structure):
     """Mirror of ``b200seg_epilogue``."""
     _fields_ = [("scale", c_void_p), ("shift", c_void_p), ("slope", c_void_p), ("dst0", View), ("dst1", View),
-                ("split", c_int32), ("residual", View), ("out_ncdhw", c_void_p), ("softmax", c_int32)]
+                ("split", c_int32), ("residual", View), ("out_ncdhw", c_void_p), ("softmax", c_int32),
+                ("slope01", c_int32)]
 
 
 _lib = None
@@ -161,10 +162,12 @@ def unpack_ncdhw(src: View, dst: torch.Tensor) -> None:
 
 def make_epilogue(scale: torch.Tensor, shift: torch.Tensor, slope: torch.Tensor, dst0: View = NULL_VIEW,
                   dst1: View = NULL_VIEW, split: int = 0, residual: View = NULL_VIEW,
-                  out_ncdhw: Optional[torch.Tensor] = None, softmax: bool = False) -> Epilogue:
+                  out_ncdhw: Optional[torch.Tensor] = None, softmax: bool = False,
+                  slope01: bool = False) -> Epilogue:
+    """``slope01``: the caller guarantees every slope is in [0, 1] (enables the cheaper max(v, v*slope) form)."""
     _require_cuda(scale, shift, slope, out_ncdhw)
     return Epilogue(scale.data_ptr(), shift.data_ptr(), slope.data_ptr(), dst0, dst1, split, residual,
-                    0 if out_ncdhw is None else out_ncdhw.data_ptr(), 1 if softmax else 0)
+                    0 if out_ncdhw is None else out_ncdhw.data_ptr(), 1 if softmax else 0, 1 if slope01 else 0)
 
 
 def conv3d_direct(inp: View, weight: torch.Tensor, cout: int, ksize: int, stride: int, pad: int, transposed: bool,

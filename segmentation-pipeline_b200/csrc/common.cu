@@ -31,6 +31,7 @@ int make_depilogue(const b200seg_epilogue* e, int cout, int n, int z, int y, int
     d.slope = e->slope;
     d.cout = cout;
     d.softmax = e->softmax;
+    d.slope01 = e->slope01;
     d.out_ncdhw = e->out_ncdhw;
     d.dst0 = null_dview();
     d.dst1 = null_dview();

@@ -139,6 +139,7 @@ struct DEpilogue {
     int split_c8;     // chunks routed to dst0
     float* out_ncdhw;
     int softmax;
+    int slope01;
     int cout;
 };
 

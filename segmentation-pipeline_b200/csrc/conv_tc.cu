@@ -461,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int my = m >> 3, mx = m & 7;
         const DEpilogue& e = p.epi;
         const int Cpad = p.Cpad, c8 = p.Cpad / 8, split_c8 = e.split_c8;
-        const bool has_res = e.residual.data != nullptr;
+        const bool has_res = e.residual.data != nullptr, slope01 = e.slope01 != 0;
         // destination geometry hoisted into registers (dst0 / dst1 / residual share the output's spatial extent)
         const int o_x = e.dst0.x;
         const long long o_plane = static_cast<long long>(e.dst0.y) * e.dst0.x;
@@ -537,10 +537,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                                 const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                                 const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                                 const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                                if (slope01) {
+                                    // 0 <= slope <= 1:  v > 0 ? v : v*slope  ==  max(v, v*slope)
 #pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
-                                    v[k] = tv > 0.f ? tv : tv * sl[k];
+                                    for (int k = 0; k < 8; ++k) {
+                                        float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                                        v[k] = fmaxf(tv, tv * sl[k]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) {
+                                        float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                                        v[k] = tv > 0.f ? tv : tv * sl[k];
+                                    }
                                 }
                             }
                             const bool to0 = cc < split_c8;

@@ -79,7 +79,7 @@ def lower(module: nn.Module) -> Plan:
 class _ConvCall:
     """One kernel launch of a ConvOp (a ConvOp wider than the engine's N limit becomes several)."""
     __slots__ = ("tc", "mode", "src", "weight", "cout", "scale", "shift", "slope", "dst0", "dst1", "split",
-                 "residual", "final", "softmax", "ksize", "stride", "pad", "transposed", "name")
+                 "residual", "final", "softmax", "ksize", "stride", "pad", "transposed", "name", "slope01")
 
 
 class CompiledPlan:
@@ -163,6 +163,7 @@ class CompiledPlan:
         call.tc, call.mode, call.src = tc, op.mode, op.src
         call.ksize, call.stride, call.pad, call.transposed = geom
         call.final, call.softmax, call.name = op.final, op.softmax, op.name
+        call.slope01 = bool(((op.slope >= 0.0) & (op.slope <= 1.0)).all())   # ReLU / LeakyReLU / none
         return call
 
     # ------------------------------------------------------------------ workspaces
@@ -217,7 +218,8 @@ class CompiledPlan:
                 TRACE.append((call, (n, z, y, x), ev))
             if isinstance(call, _ConvCall):
                 epi = lib.make_epilogue(call.scale, call.shift, call.slope, view(call.dst0), view(call.dst1),
-                                        call.split, view(call.residual), out if call.final else None, call.softmax)
+                                        call.split, view(call.residual), out if call.final else None, call.softmax,
+                                        call.slope01)
                 if call.tc:
                     lib.conv3d_tc(call.mode, view(call.src), call.weight, call.cout, epi)
                 else:
