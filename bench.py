@@ -156,11 +156,13 @@ def cpu_reference_sample(threads: int, n_patches: int = 1):
 def cpu_finalize_seconds(state) -> float:
     """divide + crop + argmax of the full padded volume on the CPU (the reference's get_output_tensor +
     CustomArgMax), measured once."""
-    from oracle import evalstats, grid as ogrid
+    out = torch.from_numpy(state["out"])
+    cnt = torch.from_numpy(np.maximum(state["cnt"], 1))
     t0 = time.perf_counter()
-    cnt = np.maximum(state["cnt"], 1)
-    probs = ogrid.finalize(state["out"], cnt, OVERLAP, True)
-    evalstats.argmax_labels(probs)
+    probs = torch.true_divide(out, cnt)                       # GridAggregator.get_output_tensor
+    b = OVERLAP // 2
+    probs = probs[:, b:-b, b:-b, b:-b]                        # torchio Crop of the padded border
+    torch.argmax(probs, dim=0, keepdim=True)                  # CustomArgMax (custom_label_transforms.py:267)
     return time.perf_counter() - t0
 
 

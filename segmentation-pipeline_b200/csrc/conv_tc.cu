@@ -274,10 +274,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint64_t* acc_full = empty_b + kMaxB;    // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(
-        (reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~static_cast<uintptr_t>(15));   // kMaxZin entries, 16-byte aligned
-    float* s_scale = reinterpret_cast<float*>(
-        (reinterpret_cast<uintptr_t>(plane_tab + kMaxZin) + 15) & ~static_cast<uintptr_t>(15));   // float4 reads
+    // 16-byte aligned tables; offsets are computed on the byte OFFSET (smem is 1024-byte aligned) so that the
+    // pointers keep their shared-memory address space (LDS, not generic loads)
+    const uint32_t bars_off = static_cast<uint32_t>(p.na * kAStageBytes + p.nbuf * p.bbuf_bytes);
+    const uint32_t tab_off = (bars_off + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 8 + 15u) & ~15u;
+    PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(smem + tab_off);                  // kMaxZin entries
+    float* s_scale = reinterpret_cast<float*>(smem + tab_off + sizeof(PlaneTab) * kMaxZin);   // float4 reads
     float* s_shift = s_scale + p.Cpad;
     float* s_slope = s_shift + p.Cpad;
 
