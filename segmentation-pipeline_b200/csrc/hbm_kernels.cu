@@ -179,21 +179,17 @@ struct LocBatch {
     int loc[64][6];
 };
 
+// grid: x = (j, k) plane of the patch, y = i, z = (patch, chunk) -- no 64-bit divisions per thread
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 grid_extract_kernel(const float* __restrict__ vol, int C, int W, int H, int D, LocBatch lb, int b0, int bw, int bh,
-                    int bd, int pad_mode, float pad_value, DView dst, long long total) {
-    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
-    if (t >= total) return;
+                    int bd, int pad_mode, float pad_value, DView dst) {
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= dst.y * dst.x) return;
     const int c8 = (dst.c + 7) / 8;
-    int k = static_cast<int>(t % dst.x);
-    long long r = t / dst.x;
-    int j = static_cast<int>(r % dst.y);
-    r /= dst.y;
-    int i = static_cast<int>(r % dst.z);
-    r /= dst.z;
-    int cc = static_cast<int>(r % c8);
-    int b = static_cast<int>(r / c8);
+    const int j = t / dst.x, k = t - j * dst.x;
+    const int i = blockIdx.y;
+    const int b = blockIdx.z / c8, cc = blockIdx.z - b * c8;
     int si = lb.loc[b][0] + i - bw, sj = lb.loc[b][1] + j - bh, sk = lb.loc[b][2] + k - bd;
     bool inside = si >= 0 && si < W && sj >= 0 && sj < H && sk >= 0 && sk < D;
     if (pad_mode == 1) {
@@ -216,42 +212,66 @@ grid_extract_kernel(const float* __restrict__ vol, int C, int W, int H, int D, L
 // =========================================================================================== overlap-add
 // Owner-computes gather: thread (c, i, j, k4) of the batch bounding box sums, in batch order, every patch of
 // the batch that covers its voxels.  VEC = 4 uses 128-bit accesses (needs k extents/offsets multiple of 4).
+// grid: x = (j, k/VEC) plane of the bounding box, y = i, z = channel.  Each block first selects, with two warp
+// ballots, the patches that can touch its (i, j-range) at all, then every thread walks only those (in order).
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 overlap_add_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
-                   LocBatch lb, int p0, int p1, int p2, int bi0, int bj0, int bk0, int bw, int bh, int bd,
-                   long long total) {
-    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
-    if (t >= total) return;
+                   LocBatch lb, int p0, int p1, int p2, int bi0, int bj0, int bk0, int bw, int bh, int bd) {
+    __shared__ unsigned int cand[2];
     const int bdv = bd / VEC;
-    int kk = static_cast<int>(t % bdv) * VEC + bk0;
-    long long r = t / bdv;
-    int j = static_cast<int>(r % bh) + bj0;
-    r /= bh;
-    int i = static_cast<int>(r % bw) + bi0;
-    int c = static_cast<int>(r / bw);
+    const int i = blockIdx.y + bi0;
+    const int c = blockIdx.z;
+    const int t0 = blockIdx.x * kThreads;
+    {
+        // j range covered by this block
+        const int tl = min(t0 + kThreads - 1, bh * bdv - 1);
+        const int jlo = t0 / bdv + bj0, jhi = tl / bdv + bj0;
+        if (threadIdx.x < 64) {
+            const int b = threadIdx.x;
+            const bool hit = b < lb.count && i >= lb.loc[b][0] && i < lb.loc[b][3] && jhi >= lb.loc[b][1] &&
+                             jlo < lb.loc[b][4];
+            const unsigned int m = __ballot_sync(0xffffffffu, hit);
+            if ((threadIdx.x & 31) == 0) cand[threadIdx.x >> 5] = m;
+        }
+        __syncthreads();
+    }
+    const int t = t0 + threadIdx.x;
+    if (t >= bh * bdv) return;
+    const int jj = t / bdv;
+    const int kk = (t - jj * bdv) * VEC + bk0;
+    const int j = jj + bj0;
     float* o = out + ((static_cast<long long>(c) * PW + i) * PH + j) * PD + kk;
     float acc[VEC];
-    if constexpr (VEC == 4) {
-        float4 v = *reinterpret_cast<const float4*>(o);
-        acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[VEC - 1] = v.w;
-    } else {
-        acc[0] = *o;
-    }
-    bool touched = false;
+    bool touched = false, loaded = false;
     const long long pvox = 1LL * p0 * p1 * p2;
-    for (int b = 0; b < lb.count; ++b) {
-        int i0 = lb.loc[b][0], j0 = lb.loc[b][1], k0 = lb.loc[b][2];
-        if (i < i0 || i >= lb.loc[b][3] || j < j0 || j >= lb.loc[b][4] || kk < k0 || kk >= lb.loc[b][5]) continue;
-        const float* p = patches + (static_cast<long long>(b) * C + c) * pvox +
-                         (static_cast<long long>(i - i0) * p1 + (j - j0)) * p2 + (kk - k0);
-        if constexpr (VEC == 4) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(p));
-            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[VEC - 1] += v.w;
-        } else {
-            acc[0] += __ldg(p);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        unsigned int m = cand[half];
+        while (m) {
+            const int b = (__ffs(m) - 1) + half * 32;
+            m &= m - 1;
+            const int i0 = lb.loc[b][0], j0 = lb.loc[b][1], k0 = lb.loc[b][2];
+            if (j < j0 || j >= lb.loc[b][4] || kk < k0 || kk >= lb.loc[b][5]) continue;
+            if (!loaded) {
+                if constexpr (VEC == 4) {
+                    float4 v = *reinterpret_cast<const float4*>(o);
+                    acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[VEC - 1] = v.w;
+                } else {
+                    acc[0] = *o;
+                }
+                loaded = true;
+            }
+            const float* p = patches + (static_cast<long long>(b) * C + c) * pvox +
+                             (static_cast<long long>(i - i0) * p1 + (j - j0)) * p2 + (kk - k0);
+            if constexpr (VEC == 4) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(p));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[VEC - 1] += v.w;
+            } else {
+                acc[0] += __ldg(p);
+            }
+            touched = true;
         }
-        touched = true;
     }
     if (!touched) return;
     if constexpr (VEC == 4) {
@@ -375,14 +395,28 @@ confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long lo
         uint4 tr = __ldg(reinterpret_cast<const uint4*>(targ) + v);
         const L* pp = reinterpret_cast<const L*>(&pr);
         const L* tp = reinterpret_cast<const L*>(&tr);
+        // run-length accumulation: label maps are piecewise constant, so consecutive voxels mostly hit the same bin
+        // and one shared-memory update covers the whole run
+        int cur = -1;
+        unsigned int run = 0;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             long long p = static_cast<long long>(pp[q]), tt = static_cast<long long>(tp[q]);
-            if (p >= 0 && p < nc && tt >= 0 && tt < nc) {
-                int bin = static_cast<int>(tt) * nc + static_cast<int>(p);
-                if (shared_cols) atomicAdd(mine + bin * 32, 1u);
-                else mine[bin * 32] += 1u;
+            const int bin = (p >= 0 && p < nc && tt >= 0 && tt < nc) ? static_cast<int>(tt) * nc + static_cast<int>(p) : -1;
+            if (bin == cur) {
+                ++run;
+            } else {
+                if (cur >= 0) {
+                    if (shared_cols) atomicAdd(mine + cur * 32, run);
+                    else mine[cur * 32] += run;
+                }
+                cur = bin;
+                run = 1;
             }
+        }
+        if (cur >= 0) {
+            if (shared_cols) atomicAdd(mine + cur * 32, run);
+            else mine[cur * 32] += run;
         }
     }
     // tail (voxels not a multiple of PER): first thread of the grid
@@ -564,9 +598,10 @@ int b200seg_grid_extract(const float* volume, int32_t c, int32_t w, int32_t h, i
                                   "grid_extract: location %d outside the volume", b0 + b);
             }
         }
-        long long total = 1LL * lb.count * ((c + 7) / 8) * dd.chunk_stride;
-        DISPATCH_DTYPE(dst.dtype, (grid_extract_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(
-                                      volume, c, w, h, d, lb, b0, bw, bh, bd, pad_mode, pad_value, dd, total)));
+        dim3 grid(blocks_for(1LL * dst.y * dst.x), static_cast<unsigned>(dst.z),
+                  static_cast<unsigned>(lb.count * ((c + 7) / 8)));
+        DISPATCH_DTYPE(dst.dtype, (grid_extract_kernel<T><<<grid, kThreads, 0, s>>>(
+                                      volume, c, w, h, d, lb, b0, bw, bh, bd, pad_mode, pad_value, dd)));
         rc = check_launch("grid_extract");
         if (rc) return rc;
     }
@@ -601,13 +636,13 @@ int b200seg_overlap_add(float* out, int32_t c, int32_t pw, int32_t ph, int32_t p
         const int bw = bb[3] - bb[0], bh = bb[4] - bb[1], bd = bb[5] - bb[2];
         const float* pp = patches + 1LL * b0 * c * p0 * p1 * p2;
         if (vec) {
-            long long total = 1LL * c * bw * bh * (bd / 4);
-            overlap_add_kernel<4><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0],
-                                                                        bb[1], bb[2], bw, bh, bd, total);
+            dim3 grid(blocks_for(1LL * bh * (bd / 4)), static_cast<unsigned>(bw), static_cast<unsigned>(c));
+            overlap_add_kernel<4><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0], bb[1], bb[2],
+                                                            bw, bh, bd);
         } else {
-            long long total = 1LL * c * bw * bh * bd;
-            overlap_add_kernel<1><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0],
-                                                                        bb[1], bb[2], bw, bh, bd, total);
+            dim3 grid(blocks_for(1LL * bh * bd), static_cast<unsigned>(bw), static_cast<unsigned>(c));
+            overlap_add_kernel<1><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0], bb[1], bb[2],
+                                                            bw, bh, bd);
         }
         int rc = check_launch("overlap_add");
         if (rc) return rc;

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Achieved HBM bandwidth of the streaming kernels of the path (extraction, overlap-add, finalize+argmax, argmax,
+confusion) at config-2 / config-3 scale.  CUDA events, 3 warm-ups, best of 10; inputs are far larger than L2 or an
+L2 flush (256 MB memset) runs between iterations.  Prints one line per kernel: algorithmic bytes, time, GB/s and
+the fraction of the measured copy bandwidth (MEASURED_PEAKS.json)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "segmentation-pipeline_b200")]
+
+import torch  # noqa: E402
+
+import b200seg  # noqa: E402
+from segmentation_pipeline.grid import PatchGrid  # noqa: E402
+
+
+def timed(fn, flush, reps=10):
+    best = 1e9
+    for i in range(3 + reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            best = min(best, s.elapsed_time(e))
+    return best
+
+
+def main():
+    peak = 6554.9
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = json.load(open(p)).get("hbm_gbs", peak)
+    dev = "cuda"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+
+    # ---- config 2 geometry: 2 x 256 x 256 x 192, patch 96, overlap 48, edge padding, 48 patches per batch
+    vol = torch.randn(2, 256, 256, 192, device=dev)
+    grid = PatchGrid(vol.shape[1:], 96, 48, "edge")
+    locs = grid.locations[:48]
+    buf = b200seg.Blocked(48, 1, 96, 96, 96, torch.bfloat16, dev)
+    t = timed(lambda: b200seg.grid_extract(vol, locs, grid.border, 1, 0.0, buf.view(2)), flush)
+    nbytes = 48 * 96 ** 3 * 16 + 48 * 2 * 96 ** 3 * 4       # bf16 chunk written (16 B/voxel) + fp32 gathered
+    rows.append(("grid_extract (48 patches, bf16 blocked out)", nbytes, t))
+
+    patches = torch.rand(48, 2, 96, 96, 96, device=dev)
+    out = torch.zeros((2, *grid.padded_shape), device=dev)
+    t = timed(lambda: b200seg.overlap_add(out, patches, locs), flush)
+    # bounding box of the first 48 locations
+    bb = [min(l[i] for l in locs) for i in range(3)] + [max(l[i + 3] for l in locs) for i in range(3)]
+    box = (bb[3] - bb[0]) * (bb[4] - bb[1]) * (bb[5] - bb[2])
+    nbytes = patches.numel() * 4 + 2 * 2 * box * 4          # every patch read once + accumulator read & written
+    rows.append(("overlap_add (48 patches, fp32)", nbytes, t))
+
+    counts = [torch.tensor(c, dtype=torch.int32, device=dev) for c in grid.axis_counts()]
+    labels = torch.empty(vol.shape[1:], dtype=torch.uint8, device=dev)
+    probs = torch.empty_like(vol)
+    t = timed(lambda: b200seg.finalize(out, counts, grid.border, None, None, labels), flush)
+    v = vol[0].numel()
+    rows.append(("finalize -> uint8 labels (config 2)", 2 * v * 4 + v, t))
+    t = timed(lambda: b200seg.finalize(out, counts, grid.border, probs, None, labels), flush)
+    rows.append(("finalize -> probs + labels (config 2)", 2 * v * 4 + 2 * v * 4 + v, t))
+
+    # ---- config 3 scale: 10 classes, 224^3
+    p10 = torch.rand(10, 224, 224, 224, device=dev)
+    lab64 = torch.empty((224, 224, 224), dtype=torch.int64, device=dev)
+    lab8 = torch.empty((224, 224, 224), dtype=torch.uint8, device=dev)
+    v3 = 224 ** 3
+    t = timed(lambda: b200seg.argmax(p10, None, lab8), flush)
+    rows.append(("argmax 10 x 224^3 -> uint8", 10 * v3 * 4 + v3, t))
+    t = timed(lambda: b200seg.argmax(p10, lab64, None), flush)
+    rows.append(("argmax 10 x 224^3 -> int64 (reference dtype)", 10 * v3 * 4 + 8 * v3, t))
+
+    # ---- confusion: cohort of 64 config-3 label maps in one buffer (uint8) and one map in int64
+    a = torch.randint(0, 10, (64 * v3 // 4,), dtype=torch.uint8, device=dev)    # 16 volumes worth, 180 MB each side
+    b = torch.randint(0, 10, (64 * v3 // 4,), dtype=torch.uint8, device=dev)
+    cm = torch.zeros((10, 10), dtype=torch.int64, device=dev)
+    t = timed(lambda: b200seg.confusion(a, b, 10, cm), flush)
+    rows.append(("confusion 10 classes, uint8, 180 M voxels", 2 * a.numel(), t))
+    a2 = torch.randint(0, 2, (256 * 256 * 192,), dtype=torch.uint8, device=dev)
+    b2 = torch.randint(0, 2, (256 * 256 * 192,), dtype=torch.uint8, device=dev)
+    cm2 = torch.zeros((2, 2), dtype=torch.int64, device=dev)
+    t = timed(lambda: b200seg.confusion(a2, b2, 2, cm2), flush)
+    rows.append(("confusion 2 classes, uint8, config 2 (12.6 M voxels)", 2 * a2.numel(), t))
+    # piecewise-constant label maps (what a segmentation looks like): blocks of 8^3 voxels share a label
+    coarse = torch.randint(0, 10, (1, 1, 28, 28, 28), device=dev).float()
+    sm_a = torch.nn.functional.interpolate(coarse, scale_factor=8, mode="nearest")[0, 0].to(torch.uint8).contiguous()
+    sm_b = torch.roll(sm_a, shifts=(3, 2, 1), dims=(0, 1, 2)).contiguous()
+    t = timed(lambda: b200seg.confusion(sm_a, sm_b, 10, cm), flush)
+    rows.append(("confusion 10 classes, uint8, 224^3 piecewise-constant", 2 * sm_a.numel(), t))
+    a64, b64 = a[: v3].long(), b[: v3].long()
+    t = timed(lambda: b200seg.confusion(a64, b64, 10, cm), flush)
+    rows.append(("confusion 10 classes, int64, 224^3", 2 * 8 * v3, t))
+
+    print(f"{'kernel':52s} {'MB':>9s} {'ms':>8s} {'GB/s':>8s} {'of measured copy peak':>22s}")
+    for name, nbytes, ms in rows:
+        gbs = nbytes / ms / 1e6
+        print(f"{name:52s} {nbytes / 1e6:9.1f} {ms:8.3f} {gbs:8.0f} {gbs / peak:21.1%}")
+
+
+if __name__ == "__main__":
+    main()
