@@ -257,7 +257,135 @@ __device__ __forceinline__ void run_image(bool first_image, int n_planes, int zs
     }
 }
 
-template <int kSets>
+// ------------------------------------------------------------------------------------------------ epilogue
+// One epilogue warp owns 32 accumulator rows (TMEM lanes) and, per output plane, NCH consecutive 8-channel chunks
+// starting at chunk `cbeg`.  The chunk count is a template parameter so that the per-chunk code is straight-line:
+// one tcgen05.ld, six 128-bit parameter loads at immediate offsets, 8 x (FFMA, FMUL, FMNMX), 4 packs, one 16-byte
+// store.  A plane's chunks form one item (NCH <= 3) or two (4 -> 2+2, 5 -> 3+2); the TMEM / residual loads of the
+// next item are in flight while the current one is converted and stored (two register buffers).
+struct EpiArgs {
+    uint32_t tbase;        // TMEM address of (lane quarter, accumulator set, column 0)
+    int Cpad;              // TMEM columns per plane
+    int nq;                // planes of this unit that exist in the output
+    bool valid;            // this lane's (y, x) lies inside the output
+    bool slope01;
+    uint4* p0;             // dst0 at (chunk 0, plane 0, this lane's voxel)
+    uint4* p1;             // dst1, pre-offset by -split_c8 chunks
+    const uint4* pr;       // residual
+    uint32_t cs;           // chunk stride in 16-byte vectors
+    uint32_t plane;        // plane stride in 16-byte vectors
+    int split_c8;          // chunks below go to dst0 (and receive the residual), the others to dst1
+    const float* s_par;    // shared: per chunk 8 scales, 8 shifts, 8 slopes
+};
+
+template <int S, bool RES>
+__device__ __forceinline__ void epi_load(const EpiArgs& a, int q, int cc0, uint32_t (&r)[3][8], uint4 (&res)[3]) {
+    const uint32_t taddr = a.tbase + q * a.Cpad + cc0 * 8;
+#pragma unroll
+    for (int j = 0; j < S; ++j) tmem_ld8(taddr + j * 8, r[j]);
+    if (RES) {
+        if (a.valid) {
+            const uint4* prq = a.pr + static_cast<size_t>(static_cast<uint32_t>(q) * a.plane);
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (cc0 + j < a.split_c8) res[j] = __ldg(prq + static_cast<size_t>((cc0 + j) * a.cs));
+        }
+    }
+}
+
+template <int S, bool RES>
+__device__ __forceinline__ void epi_finish(const EpiArgs& a, int q, int cc0, const uint32_t (&r)[3][8],
+                                           const uint4 (&res)[3]) {
+    if (!a.valid) return;
+    const size_t qoff = static_cast<size_t>(static_cast<uint32_t>(q) * a.plane);
+    const float4* par = reinterpret_cast<const float4*>(a.s_par + cc0 * 24);
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const int cc = cc0 + j;
+        const float4 s0 = par[6 * j], s1 = par[6 * j + 1], h0 = par[6 * j + 2], h1 = par[6 * j + 3],
+                     l0 = par[6 * j + 4], l1 = par[6 * j + 5];
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        float v[8];
+        if (a.slope01) {
+            // 0 <= slope <= 1:  v > 0 ? v : v*slope  ==  max(v, v*slope)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                v[k] = fmaxf(tv, tv * sl[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                v[k] = tv > 0.f ? tv : tv * sl[k];
+            }
+        }
+        const bool to0 = cc < a.split_c8;
+        if (RES) {
+            if (to0) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(h[k]);
+                    v[2 * k] += f.x;
+                    v[2 * k + 1] += f.y;
+                }
+            }
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        (to0 ? a.p0 : a.p1)[qoff + static_cast<size_t>(cc * a.cs)] = o;
+    }
+}
+
+// planes q0, q0 + qstep, ... of one accumulator set; chunks [cbeg, cbeg + NCH)
+template <int NCH, bool RES>
+__device__ __forceinline__ void epi_planes(const EpiArgs& a, int cbeg, int q0, int qstep) {
+    constexpr int S0 = NCH <= 3 ? NCH : (NCH + 1) / 2;
+    constexpr int S1 = NCH - S0;
+    uint32_t rA[3][8], rB[3][8];
+    uint4 resA[3], resB[3];
+    int q = q0;
+    if (q >= a.nq) return;
+    epi_load<S0, RES>(a, q, cbeg, rA, resA);
+    if (S1 > 0) {
+        constexpr int S1c = S1 > 0 ? S1 : 1;
+        for (;;) {
+            tmem_ld_wait();
+            epi_load<S1c, RES>(a, q, cbeg + S0, rB, resB);
+            epi_finish<S0, RES>(a, q, cbeg, rA, resA);
+            const int qn = q + qstep;
+            tmem_ld_wait();
+            if (qn < a.nq) epi_load<S0, RES>(a, qn, cbeg, rA, resA);
+            epi_finish<S1c, RES>(a, q, cbeg + S0, rB, resB);
+            if (qn >= a.nq) break;
+            q = qn;
+        }
+    } else {
+        for (;;) {
+            tmem_ld_wait();
+            int qn = q + qstep;
+            if (qn < a.nq) epi_load<S0, RES>(a, qn, cbeg, rB, resB);
+            epi_finish<S0, RES>(a, q, cbeg, rA, resA);
+            if (qn >= a.nq) break;
+            q = qn;
+            qn = q + qstep;
+            tmem_ld_wait();
+            if (qn < a.nq) epi_load<S0, RES>(a, qn, cbeg, rA, resA);
+            epi_finish<S0, RES>(a, q, cbeg, rB, resB);
+            if (qn >= a.nq) break;
+            q = qn;
+        }
+    }
+}
+
+// kEpi selects the epilogue: 0 = any chunk count (run-time item cursor); 1 / 2 = 10 chunks without / with residual;
+// 3 / 4 = 5 chunks without / with residual.
+template <int kSets, int kEpi>
 __global__ void __launch_bounds__(kSets == 2 ? 384 : 224, kSets == 2 ? 1 : 2)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr int kEpiWarp0 = kSets == 2 ? 4 : 3;
@@ -279,9 +407,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const uint32_t bars_off = static_cast<uint32_t>(p.na * kAStageBytes + p.nbuf * p.bbuf_bytes);
     const uint32_t tab_off = (bars_off + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 8 + 15u) & ~15u;
     PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(smem + tab_off);                  // kMaxZin entries
-    float* s_scale = reinterpret_cast<float*>(smem + tab_off + sizeof(PlaneTab) * kMaxZin);   // float4 reads
-    float* s_shift = s_scale + p.Cpad;
-    float* s_slope = s_shift + p.Cpad;
+    // epilogue parameters, per 8-channel chunk: 8 scales, 8 shifts, 8 slopes (float4 reads)
+    float* s_par = reinterpret_cast<float*>(smem + tab_off + sizeof(PlaneTab) * kMaxZin);
 
     const int warp = threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -304,9 +431,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     for (int zi = threadIdx.x; zi < p.zin_count; zi += blockDim.x) build_plane_tab(p, zi, plane_tab[zi]);
     for (int c = threadIdx.x; c < p.Cpad; c += blockDim.x) {
-        s_scale[c] = p.epi.scale[c];
-        s_shift[c] = p.epi.shift[c];
-        s_slope[c] = p.epi.slope[c];
+        float* par = s_par + (c >> 3) * 24 + (c & 7);
+        par[0] = p.epi.scale[c];
+        par[8] = p.epi.shift[c];
+        par[16] = p.epi.slope[c];
     }
     tc_fence_before();
     __syncthreads();
@@ -500,108 +628,133 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 }
                 const uint32_t tbase = tmem + set * 256 + (static_cast<uint32_t>(lg * 32) << 16);
                 if (e.out_ncdhw == nullptr) {
-                    // Work items of this warp: (plane q, round of kR chunks).  Software pipelined: the TMEM and
-                    // residual loads of the next item are in flight while the current one is converted and stored.
-                    constexpr int kR = 3;
-                    const int nq = min(p.TZ, p.out_z - z0);
-                    const int rounds = (c8 + kR - 1) / kR;
-                    // per-unit base pointers (16-byte vectors): element (chunk cc, plane q) = base[cc * cs + q * plane]
-                    const long long spatial = static_cast<long long>(z0) * o_plane + oy * o_x + ox;
-                    uint4* const p0 = d0_base + n * d0_ss + spatial;
-                    uint4* const p1 = d1_base + n * d1_ss + spatial;          // already offset by -split_c8 chunks
-                    const uint4* const pr = r_base + n * r_ss + spatial;
-                    auto load_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
-                        const uint32_t taddr = tbase + q * Cpad;
-#pragma unroll
-                        for (int j = 0; j < kR; ++j)
-                            if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
-                        if (valid && has_res) {
-#pragma unroll
+                    if constexpr (kEpi != 0) {
+                        // specialised epilogues: 10 chunks (the two warps of a lane quarter take 5 chunks each of
+                        // every plane) or 5 chunks (they take alternate planes), with or without a residual
+                        constexpr bool kRes = kEpi == 2 || kEpi == 4;
+                        constexpr bool kByPlane = kEpi >= 3;
+                        EpiArgs a;
+                        a.tbase = tbase;
+                        a.Cpad = Cpad;
+                        a.nq = min(p.TZ, p.out_z - z0);
+                        a.valid = valid;
+                        a.slope01 = slope01;
+                        const long long spatial = static_cast<long long>(z0) * o_plane + oy * o_x + ox;
+                        a.p0 = d0_base + n * d0_ss + spatial;
+                        a.p1 = d1_base + n * d1_ss + spatial;          // already offset by -split_c8 chunks
+                        a.pr = r_base + n * r_ss + spatial;
+                        a.cs = static_cast<uint32_t>(o_cs);
+                        a.plane = static_cast<uint32_t>(o_plane);
+                        a.split_c8 = split_c8;
+                        a.s_par = s_par;
+                        for (int h = kHalves == 2 ? half : 0; h < 2; h += kHalves) {
+                            if (kByPlane) epi_planes<5, kRes>(a, 0, h, 2);
+                            else epi_planes<5, kRes>(a, 5 * h, 0, 1);
+                        }
+                    } else {
+                        // Work items of this warp: (plane q, round of kR chunks).  Software pipelined: the TMEM and
+                        // residual loads of the next item are in flight while the current one is converted and stored.
+                        constexpr int kR = 3;
+                        const int nq = min(p.TZ, p.out_z - z0);
+                        const int rounds = (c8 + kR - 1) / kR;
+                        // per-unit base pointers (16-byte vectors): element (chunk cc, plane q) = base[cc * cs + q * plane]
+                        const long long spatial = static_cast<long long>(z0) * o_plane + oy * o_x + ox;
+                        uint4* const p0 = d0_base + n * d0_ss + spatial;
+                        uint4* const p1 = d1_base + n * d1_ss + spatial;          // already offset by -split_c8 chunks
+                        const uint4* const pr = r_base + n * r_ss + spatial;
+                        auto load_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
+                            const uint32_t taddr = tbase + q * Cpad;
+    #pragma unroll
                             for (int j = 0; j < kR; ++j)
-                                if (c0 + j < c8 && c0 + j < split_c8)
-                                    res[j] = __ldg(pr + (c0 + j) * o_cs + static_cast<long long>(q) * o_plane);
-                        }
-                    };
-                    auto finish_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
-                        if (!valid) return;
-                        const long long qoff = static_cast<long long>(q) * o_plane;
-#pragma unroll
-                        for (int j = 0; j < kR; ++j) {
-                            const int cc = c0 + j;
-                            if (cc >= c8) continue;
-                            float v[8];
-                            {
-                                // per-channel parameters: 6 x 128-bit broadcast loads per chunk
-                                const float4* ps = reinterpret_cast<const float4*>(s_scale + cc * 8);
-                                const float4* ph = reinterpret_cast<const float4*>(s_shift + cc * 8);
-                                const float4* pl = reinterpret_cast<const float4*>(s_slope + cc * 8);
-                                const float4 s0 = ps[0], s1 = ps[1], h0 = ph[0], h1 = ph[1], l0 = pl[0], l1 = pl[1];
-                                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                                const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-                                if (slope01) {
-                                    // 0 <= slope <= 1:  v > 0 ? v : v*slope  ==  max(v, v*slope)
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) {
-                                        float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
-                                        v[k] = fmaxf(tv, tv * sl[k]);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) {
-                                        float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
-                                        v[k] = tv > 0.f ? tv : tv * sl[k];
+                                if (c0 + j < c8) tmem_ld8(taddr + (c0 + j) * 8, r[j]);
+                            if (valid && has_res) {
+    #pragma unroll
+                                for (int j = 0; j < kR; ++j)
+                                    if (c0 + j < c8 && c0 + j < split_c8)
+                                        res[j] = __ldg(pr + (c0 + j) * o_cs + static_cast<long long>(q) * o_plane);
+                            }
+                        };
+                        auto finish_item = [&](int q, int c0, uint32_t (&r)[kR][8], uint4 (&res)[kR]) {
+                            if (!valid) return;
+                            const long long qoff = static_cast<long long>(q) * o_plane;
+    #pragma unroll
+                            for (int j = 0; j < kR; ++j) {
+                                const int cc = c0 + j;
+                                if (cc >= c8) continue;
+                                float v[8];
+                                {
+                                    // per-channel parameters: 6 x 128-bit broadcast loads per chunk
+                                    const float4* ps = reinterpret_cast<const float4*>(s_par + cc * 24);
+                                    const float4* ph = ps + 2;
+                                    const float4* pl = ps + 4;
+                                    const float4 s0 = ps[0], s1 = ps[1], h0 = ph[0], h1 = ph[1], l0 = pl[0], l1 = pl[1];
+                                    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                                    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                                    const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                                    if (slope01) {
+                                        // 0 <= slope <= 1:  v > 0 ? v : v*slope  ==  max(v, v*slope)
+    #pragma unroll
+                                        for (int k = 0; k < 8; ++k) {
+                                            float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                                            v[k] = fmaxf(tv, tv * sl[k]);
+                                        }
+                                    } else {
+    #pragma unroll
+                                        for (int k = 0; k < 8; ++k) {
+                                            float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
+                                            v[k] = tv > 0.f ? tv : tv * sl[k];
+                                        }
                                     }
                                 }
-                            }
-                            const bool to0 = cc < split_c8;
-                            if (to0 && has_res) {
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    float2 f = __bfloat1622float2(h[k]);
-                                    v[2 * k] += f.x;
-                                    v[2 * k + 1] += f.y;
+                                const bool to0 = cc < split_c8;
+                                if (to0 && has_res) {
+                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
+    #pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        float2 f = __bfloat1622float2(h[k]);
+                                        v[2 * k] += f.x;
+                                        v[2 * k + 1] += f.y;
+                                    }
                                 }
+                                uint4 o;
+                                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+    #pragma unroll
+                                for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                                (to0 ? p0 : p1)[cc * o_cs + qoff] = o;
                             }
-                            uint4 o;
-                            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-                            (to0 ? p0 : p1)[cc * o_cs + qoff] = o;
-                        }
-                    };
-                    // item cursor (q, rr): this warp takes every kHalves-th item of the (q-major) item list
-                    auto advance = [&](int& q, int& rr) {
-                        rr += kHalves;
+                        };
+                        // item cursor (q, rr): this warp takes every kHalves-th item of the (q-major) item list
+                        auto advance = [&](int& q, int& rr) {
+                            rr += kHalves;
+                            while (rr >= rounds) {
+                                rr -= rounds;
+                                ++q;
+                            }
+                        };
+                        uint32_t rA[kR][8], rB[kR][8];
+                        uint4 resA[kR], resB[kR];
+                        int q = 0, rr = kHalves == 2 ? half : 0;
                         while (rr >= rounds) {
                             rr -= rounds;
                             ++q;
                         }
-                    };
-                    uint32_t rA[kR][8], rB[kR][8];
-                    uint4 resA[kR], resB[kR];
-                    int q = 0, rr = kHalves == 2 ? half : 0;
-                    while (rr >= rounds) {
-                        rr -= rounds;
-                        ++q;
-                    }
-                    if (q < nq) load_item(q, rr * kR, rA, resA);
-                    while (q < nq) {
-                        tmem_ld_wait();
-                        int q2 = q, rr2 = rr;
-                        advance(q2, rr2);
-                        if (q2 < nq) load_item(q2, rr2 * kR, rB, resB);
-                        finish_item(q, rr * kR, rA, resA);
-                        q = q2;
-                        rr = rr2;
-                        if (q >= nq) break;
-                        tmem_ld_wait();
-                        advance(q2, rr2);
-                        if (q2 < nq) load_item(q2, rr2 * kR, rA, resA);
-                        finish_item(q, rr * kR, rB, resB);
-                        q = q2;
-                        rr = rr2;
+                        if (q < nq) load_item(q, rr * kR, rA, resA);
+                        while (q < nq) {
+                            tmem_ld_wait();
+                            int q2 = q, rr2 = rr;
+                            advance(q2, rr2);
+                            if (q2 < nq) load_item(q2, rr2 * kR, rB, resB);
+                            finish_item(q, rr * kR, rA, resA);
+                            q = q2;
+                            rr = rr2;
+                            if (q >= nq) break;
+                            tmem_ld_wait();
+                            advance(q2, rr2);
+                            if (q2 < nq) load_item(q2, rr2 * kR, rA, resA);
+                            finish_item(q, rr * kR, rB, resB);
+                            q = q2;
+                            rr = rr2;
+                        }
                     }
                 } else {
                     // final layer: affine (+bias), optional channel softmax, fp32 NCDHW store (cout <= 16)
@@ -617,14 +770,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             float v[16];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float tv = fmaf(__uint_as_float(r0[j]), s_scale[j], s_shift[j]);
-                                v[j] = tv > 0.f ? tv : tv * s_slope[j];
+                                float tv = fmaf(__uint_as_float(r0[j]), s_par[j], s_par[8 + j]);
+                                v[j] = tv > 0.f ? tv : tv * s_par[16 + j];
                             }
                             if (c8 > 1) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    float tv = fmaf(__uint_as_float(r1[j]), s_scale[8 + j], s_shift[8 + j]);
-                                    v[8 + j] = tv > 0.f ? tv : tv * s_slope[8 + j];
+                                    float tv = fmaf(__uint_as_float(r1[j]), s_par[24 + j], s_par[32 + j]);
+                                    v[8 + j] = tv > 0.f ? tv : tv * s_par[40 + j];
                                 }
                             }
                             const long long vox = 1LL * p.out_z * p.out_y * p.out_x;
@@ -757,6 +910,11 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     DEpilogue de;
     rc = make_depilogue(epi, cout, in.n, oz, oy, ox, B200SEG_BF16, &de);
     if (rc) return rc;
+    // the epilogue indexes (chunk, plane) inside one sample with 32-bit arithmetic on 16-byte vectors
+    B200SEG_CHECK_ARG(epi->out_ncdhw != nullptr ||
+                          static_cast<long long>(de.dst0.chunk_stride) * 16 < (1LL << 32),
+                      "conv3d_tc: output sample too large (chunk stride %lld voxels)",
+                      static_cast<long long>(de.dst0.chunk_stride));
 
     int dev = 0, sms = 148;
     B200SEG_CHECK_CUDA(cudaGetDevice(&dev));
@@ -871,14 +1029,21 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     const long long max_ctas = 1LL * sms * (variant == 2 ? 1 : 2);
     dim3 grid(static_cast<unsigned>(n_tiles < max_ctas ? n_tiles : max_ctas));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static const bool generic_epilogue = [] {
+        const char* v = getenv("B200SEG_TC_GENERIC_EPILOGUE");   // test hook: force the run-time epilogue
+        return v && v[0] == '1';
+    }();
+    void (*kernel)(const TcMaps, const TcParams) = nullptr;
     if (variant == 2) {
-        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                static_cast<int>(smem)));
-        conv_tc_kernel<2><<<grid, 384, smem, s>>>(maps, p);
+        const bool res = de.residual.data != nullptr;
+        const int c8 = p.Cpad / 8;
+        if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<2, 0>;
+        else if (c8 == 10) kernel = res ? conv_tc_kernel<2, 2> : conv_tc_kernel<2, 1>;
+        else kernel = res ? conv_tc_kernel<2, 4> : conv_tc_kernel<2, 3>;
     } else {
-        B200SEG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                static_cast<int>(smem)));
-        conv_tc_kernel<1><<<grid, 224, smem, s>>>(maps, p);
+        kernel = conv_tc_kernel<1, 0>;
     }
+    B200SEG_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<grid, variant == 2 ? 384 : 224, smem, s>>>(maps, p);
     return check_launch("conv3d_tc");
 }
