@@ -63,6 +63,7 @@ struct TcParams {
     int n_pass, n_bimg;  // passes and B images per pass
     int na, nbuf;     // A ring depth, B ring depth
     int resident;     // 1: every weight image has its own slot and is loaded once per CTA (nbuf = n_pass * n_bimg)
+    int dual;         // 1: two MMA issuers, one per accumulator set, each with half of the A ring (resident weights only)
     int batch;
     int chunk_base;   // in.c8_off
     int c8_total;     // in.c8_total
@@ -443,54 +444,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int n_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.batch;
     const int n_img_planes = p.mode == B200SEG_TC_DOWN ? p.TZ + 1 : p.zin_count;
 
-    if (warp == 0) {
-        // =============================================================== A producer
-        if (elect_one()) {
-            const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : 2;
-            for (int i = 0; i < nmap; ++i) prefetch_tmap(&maps.m[i]);
-            uint32_t a_it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int tx = t % p.tiles_x; t /= p.tiles_x;
-                const int ty = t % p.tiles_y; t /= p.tiles_y;
-                const int tz = t % p.tiles_z;
-                const int n = t / p.tiles_z;
-                const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
-                const int chunk0 = n * p.c8_total + p.chunk_base;
-                for (int pass = 0; pass < p.n_pass; ++pass) {
-                    for (int bi = 0; bi < p.n_bimg; ++bi) {
-                        const int g = bi % p.G;
-                        const bool lone = p.lone_last && g == p.G - 1;
-                        const uint32_t plane_bytes = lone ? kChunkBytes : kAStageBytes;
-                        int zi0 = 0, zstep = 1, pp = 0;
-                        if (p.mode == B200SEG_TC_DOWN) {
-                            zi0 = bi / (4 * p.G);
-                            zstep = 2;
-                            pp = (bi / p.G) % 4;
-                        }
-                        for (int j = 0; j < n_img_planes; ++j, ++a_it) {
-                            const int zi = zi0 + j * zstep;
-                            const uint32_t s = a_it % p.na, ph = (a_it / p.na) & 1;
-                            mbar_wait(&empty_a[s], ph ^ 1);
-                            mbar_arrive_expect_tx(&full_a[s], plane_bytes);
-                            uint8_t* dst = sA + s * kAStageBytes;
-                            if (p.mode == B200SEG_TC_K3) {
-                                tma_load_4d(dst, &maps.m[lone ? 1 : 0], &full_a[s], (x0 - 1) * 8, y0 - 1,
-                                            z0 - 1 + zi, chunk0 + 2 * g);
-                            } else if (p.mode == B200SEG_TC_UP) {
-                                // tile origin is in low-res input coordinates; z0 counts OUTPUT planes (even)
-                                tma_load_4d(dst, &maps.m[lone ? 1 : 0], &full_a[s], (x0 - 1) * 8, y0 - 1,
-                                            z0 / 2 - 1 + zi, chunk0 + 2 * g);
-                            } else {
-                                tma_load_5d(dst, &maps.m[(lone ? 4 : 0) + pp], &full_a[s], 0, x0 - 1, y0 - 1,
-                                            2 * z0 - 1 + zi, chunk0 + 2 * g);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 2) {
+    // Dual-issuer mode (p.dual, resident weights only): issuer r (warp 1 / warp 3) owns accumulator set r, the units u
+    // with (u & 1) == r and half r of the A ring, which is fed by its own producer (warp 0 / warp 2 once it has loaded the
+    // weights).  A single thread issuing MMAs spends ~100 instructions per plane and is the bottleneck of every layer
+    // whose MMAs are short (N <= 128); two issuers on different accumulators double that rate and keep the results
+    // deterministic (each accumulator still sees its MMAs in one fixed order).
+    const int dual = kSets == 2 ? p.dual : 0;
+    const int ring_n = dual ? p.na / 2 : p.na;
+    if (warp == 2) {
         // =============================================================== B producer
         if (elect_one()) {
             uint32_t b_it = 0;
@@ -514,19 +475,77 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // =============================================================== MMA issuer
+        __syncwarp();
+    }
+    if (warp == 0 || (warp == 2 && dual)) {
+        // =============================================================== A producer (ring r)
+        const int r = warp >> 1;
+        if (elect_one()) {
+            const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : 2;
+            for (int i = 0; i < nmap; ++i) prefetch_tmap(&maps.m[i]);
+            uint64_t* const full_r = full_a + r * ring_n;
+            uint64_t* const empty_r = empty_a + r * ring_n;
+            uint8_t* const sA_r = sA + r * ring_n * kAStageBytes;
+            uint32_t s = 0, ph = 0, unit = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; t /= p.tiles_y;
+                const int tz = t % p.tiles_z;
+                const int n = t / p.tiles_z;
+                const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
+                const int chunk0 = n * p.c8_total + p.chunk_base;
+                for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
+                    if (dual && static_cast<int>(unit & 1) != r) continue;
+                    for (int bi = 0; bi < p.n_bimg; ++bi) {
+                        const int g = bi % p.G;
+                        const bool lone = p.lone_last && g == p.G - 1;
+                        const uint32_t plane_bytes = lone ? kChunkBytes : kAStageBytes;
+                        const int cc = chunk0 + 2 * g;
+                        int zc, zstep = 1;          // z coordinate of the first plane, step between planes
+                        const CUtensorMap* map = &maps.m[lone ? 1 : 0];
+                        if (p.mode == B200SEG_TC_K3) {
+                            zc = z0 - 1;
+                        } else if (p.mode == B200SEG_TC_UP) {
+                            zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
+                        } else {
+                            zc = 2 * z0 - 1 + bi / (4 * p.G);
+                            zstep = 2;
+                            map = &maps.m[(lone ? 4 : 0) + (bi / p.G) % 4];
+                        }
+                        for (int j = 0; j < n_img_planes; ++j, zc += zstep) {
+                            mbar_wait(&empty_r[s], ph ^ 1);
+                            mbar_arrive_expect_tx(&full_r[s], plane_bytes);
+                            uint8_t* dst = sA_r + s * kAStageBytes;
+                            if (p.mode == B200SEG_TC_DOWN) tma_load_5d(dst, map, &full_r[s], 0, x0 - 1, y0 - 1, zc, cc);
+                            else tma_load_4d(dst, map, &full_r[s], (x0 - 1) * 8, y0 - 1, zc, cc);
+                            if (++s == static_cast<uint32_t>(ring_n)) {
+                                s = 0;
+                                ph ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 || (warp == 3 && dual)) {
+        // =============================================================== MMA issuer r (accumulator set r in dual mode)
+        const int r = warp >> 1;
         if (elect_one()) {
             // everything the loop needs lives in registers: no divisions, no parameter re-loads per MMA
-            const int mode = p.mode, na = p.na, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G, n_pass = p.n_pass;
+            const int mode = p.mode, na = ring_n, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G, n_pass = p.n_pass;
             const bool lone_last = p.lone_last != 0, resident = p.resident != 0;
             uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, unit = 0;
-            const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+            uint64_t* const full_r = full_a + r * ring_n;
+            uint64_t* const empty_r = empty_a + r * ring_n;
+            const uint32_t sA16 = smem_u32(sA + r * ring_n * kAStageBytes) >> 4, sB16 = smem_u32(sB) >> 4;
             const uint32_t bbuf16 = static_cast<uint32_t>(p.bbuf_bytes) >> 4;
             const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
             const uint32_t bstep16 = 2 * p.NB;                          // one step of a B image, in 16-byte units
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int pass = 0; pass < n_pass; ++pass, ++unit) {
+                    if (dual && static_cast<int>(unit & 1) != r) continue;
+                    if (resident) b_s = pass * n_bimg;     // image slot = (pass, image), also when units are skipped
                     const uint32_t set = kSets == 2 ? (unit & 1) : 0;
                     mbar_wait(&acc_empty[set], ((kSets == 2 ? (unit >> 1) : unit) & 1) ^ 1);
                     tc_fence_after();
@@ -560,19 +579,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         const bool first_image = bi == 0;
                         switch (kind) {
                             case kK3Full:
-                                run_image<kK3Full>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                run_image<kK3Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
                                                    pbase, b16, b_lbo, bstep16, tacc);
                                 break;
                             case kK3Lone:
-                                run_image<kK3Lone>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                run_image<kK3Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
                                                    pbase, b16, b_lbo, bstep16, tacc);
                                 break;
                             case kS2Full:
-                                run_image<kS2Full>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                run_image<kS2Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
                                                    pbase, b16, b_lbo, bstep16, tacc);
                                 break;
                             default:
-                                run_image<kS2Lone>(first_image, n_img_planes, zstep, pt, full_a, empty_a, a_s, a_ph, na, sA16,
+                                run_image<kS2Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
                                                    pbase, b16, b_lbo, bstep16, tacc);
                                 break;
                         }
@@ -612,8 +631,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
             for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
                 const uint32_t set = kSets == 2 ? (unit & 1) : 0;
-                mbar_wait(&acc_full[set], (kSets == 2 ? (unit >> 1) : unit) & 1);
-                tc_fence_after();
                 int oy, ox;
                 bool valid;
                 if (p.mode == B200SEG_TC_UP) {
@@ -626,6 +643,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     ox = x0 + mx;
                     valid = oy < p.out_y && ox < p.out_x;
                 }
+                if (has_res && valid) {
+                    // The residual does not depend on the accumulators: pull this warp's share of it into L2 while the
+                    // MMAs of the unit are still running, so that the loads in the item loop see L2 latency, not DRAM.
+                    const int nq = min(p.TZ, p.out_z - z0);
+                    const uint4* pr = r_base + n * r_ss + static_cast<long long>(z0) * o_plane + oy * o_x + ox;
+                    for (int q = half; q < nq; q += kHalves)
+                        for (int cc = 0; cc < split_c8; ++cc) prefetch_l2(pr + cc * o_cs + q * o_plane);
+                }
+                mbar_wait(&acc_full[set], (kSets == 2 ? (unit >> 1) : unit) & 1);
+                tc_fence_after();
                 const uint32_t tbase = tmem + set * 256 + (static_cast<uint32_t>(lg * 32) << 16);
                 if (e.out_ncdhw == nullptr) {
                     if constexpr (kEpi != 0) {
@@ -1023,7 +1050,13 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / kAStageBytes);
     if (na > kMaxA) na = kMaxA;
     p.na = static_cast<int>(na);
-    const size_t smem = misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * kAStageBytes;
+    // two MMA issuers (one per accumulator set, half of the A ring each) when the weights are resident
+    static const bool single_issuer = [] {
+        const char* v = getenv("B200SEG_TC_SINGLE_ISSUER");   // test / profiling hook
+        return v && v[0] == '1';
+    }();
+    p.dual = (variant == 2 && p.resident && p.na >= 8 && !single_issuer) ? 1 : 0;
+    const size_t smem =misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * kAStageBytes;
     // ---- launch (persistent)
     const long long n_tiles = 1LL * p.tiles_x * p.tiles_y * p.tiles_z * in.n;
     const long long max_ctas = 1LL * sms * (variant == 2 ? 1 : 2);
@@ -1041,7 +1074,11 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
         else if (c8 == 10) kernel = res ? conv_tc_kernel<2, 2> : conv_tc_kernel<2, 1>;
         else kernel = res ? conv_tc_kernel<2, 4> : conv_tc_kernel<2, 3>;
     } else {
-        kernel = conv_tc_kernel<1, 0>;
+        const bool res = de.residual.data != nullptr;
+        const int c8 = p.Cpad / 8;
+        if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<1, 0>;
+        else if (c8 == 10) kernel = res ? conv_tc_kernel<1, 2> : conv_tc_kernel<1, 1>;
+        else kernel = res ? conv_tc_kernel<1, 4> : conv_tc_kernel<1, 3>;
     }
     B200SEG_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kernel<<<grid, variant == 2 ? 384 : 224, smem, s>>>(maps, p);

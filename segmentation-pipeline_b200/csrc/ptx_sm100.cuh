@@ -72,6 +72,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* gptr) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
+}
 // 4-D tiled load: coordinates are (c0 innermost .. c3 outermost), signed; out-of-bounds -> zero fill.
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
