@@ -63,7 +63,7 @@ struct TcParams {
     int n_pass, n_bimg;  // passes and B images per pass
     int na, nbuf;     // A ring depth, B ring depth
     int resident;     // 1: every weight image has its own slot and is loaded once per CTA (nbuf = n_pass * n_bimg)
-    int dual;         // 1: two MMA issuers, one per accumulator set, each with half of the A ring (resident weights only)
+    int dual;         // 1: two MMA issuers, one per accumulator set, each with half of the A ring
     int batch;
     int chunk_base;   // in.c8_off
     int c8_total;     // in.c8_total
@@ -421,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
         for (int i = 0; i < kMaxB; ++i) {
             mbar_init(&full_b[i], 1);
-            mbar_init(&empty_b[i], 1);
+            mbar_init(&empty_b[i], (kSets == 2 && p.dual) ? 2 : 1);   // a streamed image is released by both issuers
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -444,87 +444,176 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int n_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.batch;
     const int n_img_planes = p.mode == B200SEG_TC_DOWN ? p.TZ + 1 : p.zin_count;
 
-    // Dual-issuer mode (p.dual, resident weights only): issuer r (warp 1 / warp 3) owns accumulator set r, the units u
-    // with (u & 1) == r and half r of the A ring, which is fed by its own producer (warp 0 / warp 2 once it has loaded the
-    // weights).  A single thread issuing MMAs spends ~100 instructions per plane and is the bottleneck of every layer
-    // whose MMAs are short (N <= 128); two issuers on different accumulators double that rate and keep the results
-    // deterministic (each accumulator still sees its MMAs in one fixed order).
+    // Unit walk.  A unit is (tile, pass); the CTA owns tiles bid, bid + G, ...  Units are numbered q = 0, 1, ...; unit q
+    // uses accumulator set q & 1 with barrier phase (q >> 1) & 1.
+    //   single issuer: q = tile_it * n_pass + pass.
+    //   dual issuers : q = 2 * (k * n_pass + pass) + r  is (tile 2k + r, pass): issuer r (warp 1 / warp 3) owns set r, the
+    //                  odd/even tiles and half r of the A ring (fed by warp 0 / warp 2); both issuers walk the same
+    //                  (pass, image) sequence, so a streamed weight image is shared and released by both.
+    // A single thread issuing MMAs spends ~100 instructions per plane and is the bottleneck of every layer whose MMAs are
+    // short; two issuers on different accumulators double that rate and keep the results deterministic (each accumulator
+    // still sees its MMAs in one fixed order).
     const int dual = kSets == 2 ? p.dual : 0;
     const int ring_n = dual ? p.na / 2 : p.na;
-    if (warp == 2) {
-        // =============================================================== B producer
+    const int bid = static_cast<int>(blockIdx.x), grid_n = static_cast<int>(gridDim.x);
+    const int my_tiles = (n_tiles - bid + grid_n - 1) / grid_n;
+    const int n_seq = dual ? ((my_tiles + 1) / 2) * 2 * p.n_pass : my_tiles * p.n_pass;
+    auto unit_of = [&](int q, int& tile, int& pass) -> bool {
+        int tile_it;
+        if (dual) {
+            const int group = q >> 1, k = group / p.n_pass;
+            pass = group - k * p.n_pass;
+            tile_it = 2 * k + (q & 1);
+        } else {
+            tile_it = q / p.n_pass;
+            pass = q - tile_it * p.n_pass;
+        }
+        tile = bid + tile_it * grid_n;
+        return tile_it < my_tiles;
+    };
+    const int n_img_round = p.n_pass * p.n_bimg;
+    // one A-plane load request (coordinates of the halo box of input plane zc, chunk pair cc)
+    auto image_loads = [&](int tile, int bi, int& x0, int& y0, int& zc, int& zstep, int& cc, uint32_t& bytes,
+                           const CUtensorMap*& map) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int tz = t % p.tiles_z;
+        const int n = t / p.tiles_z;
+        x0 = tx * 8;
+        y0 = ty * 16;
+        const int z0 = tz * p.TZ;
+        const int g = bi % p.G;
+        const bool lone = p.lone_last && g == p.G - 1;
+        bytes = lone ? kChunkBytes : kAStageBytes;
+        cc = n * p.c8_total + p.chunk_base + 2 * g;
+        zstep = 1;
+        map = &maps.m[lone ? 1 : 0];
+        if (p.mode == B200SEG_TC_K3) {
+            zc = z0 - 1;
+        } else if (p.mode == B200SEG_TC_UP) {
+            zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
+        } else {
+            zc = 2 * z0 - 1 + bi / (4 * p.G);
+            zstep = 2;
+            map = &maps.m[(lone ? 4 : 0) + (bi / p.G) % 4];
+        }
+    };
+    auto issue_a = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, uint32_t bytes, int x0, int y0, int zc, int cc) {
+        mbar_arrive_expect_tx(bar, bytes);
+        if (p.mode == B200SEG_TC_DOWN) tma_load_5d(dst, map, bar, 0, x0 - 1, y0 - 1, zc, cc);
+        else tma_load_4d(dst, map, bar, (x0 - 1) * 8, y0 - 1, zc, cc);
+    };
+    auto issue_b = [&](int idx, uint32_t slot) {
+        const int g = (idx % p.n_bimg) % p.G;
+        const bool lone = p.lone_last && g == p.G - 1;
+        const uint32_t bytes = (lone ? p.steps_lone : p.steps_full) * 2 * p.NB * 16;
+        mbar_arrive_expect_tx(&full_b[slot], bytes);
+        bulk_load(sB + slot * p.bbuf_bytes, p.wpacked + static_cast<size_t>(idx) * p.bimg_stride, bytes, &full_b[slot]);
+    };
+    if (warp == 0) {
+        // =============================================================== A producer (ring 0)
         if (elect_one()) {
-            uint32_t b_it = 0;
-            // resident mode: every image has its own slot, loaded once; otherwise a ring re-streamed per unit
-            const int n_rounds = p.resident ? 1 : (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                                      static_cast<int>(gridDim.x);
-            for (int round = 0; round < n_rounds; ++round) {
-                for (int pass = 0; pass < p.n_pass; ++pass) {
-                    for (int bi = 0; bi < p.n_bimg; ++bi, ++b_it) {
-                        const int g = bi % p.G;
-                        const bool lone = p.lone_last && g == p.G - 1;
-                        const int nsteps = lone ? p.steps_lone : p.steps_full;
-                        const uint32_t bytes = nsteps * 2 * p.NB * 16;
-                        const uint32_t s = b_it % p.nbuf, ph = (b_it / p.nbuf) & 1;
-                        mbar_wait(&empty_b[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&full_b[s], bytes);
-                        bulk_load(sB + s * p.bbuf_bytes,
-                                  p.wpacked + static_cast<size_t>(pass * p.n_bimg + bi) * p.bimg_stride, bytes,
-                                  &full_b[s]);
+            const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : 2;
+            for (int i = 0; i < nmap; ++i) prefetch_tmap(&maps.m[i]);
+            uint32_t s = 0, ph = 0;
+            for (int q = 0; q < n_seq; q += dual ? 2 : 1) {
+                int tile, pass;
+                unit_of(q, tile, pass);          // ring 0 units always exist
+                for (int bi = 0; bi < p.n_bimg; ++bi) {
+                    int x0, y0, zc, zstep, cc;
+                    uint32_t bytes;
+                    const CUtensorMap* map;
+                    image_loads(tile, bi, x0, y0, zc, zstep, cc, bytes, map);
+                    for (int j = 0; j < n_img_planes; ++j, zc += zstep) {
+                        mbar_wait(&empty_a[s], ph ^ 1);
+                        issue_a(sA + s * kAStageBytes, map, &full_a[s], bytes, x0, y0, zc, cc);
+                        if (++s == static_cast<uint32_t>(ring_n)) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
             }
         }
-        __syncwarp();
-    }
-    if (warp == 0 || (warp == 2 && dual)) {
-        // =============================================================== A producer (ring r)
-        const int r = warp >> 1;
+    } else if (warp == 2) {
         if (elect_one()) {
-            const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : 2;
-            for (int i = 0; i < nmap; ++i) prefetch_tmap(&maps.m[i]);
-            uint64_t* const full_r = full_a + r * ring_n;
-            uint64_t* const empty_r = empty_a + r * ring_n;
-            uint8_t* const sA_r = sA + r * ring_n * kAStageBytes;
-            uint32_t s = 0, ph = 0, unit = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int tx = t % p.tiles_x; t /= p.tiles_x;
-                const int ty = t % p.tiles_y; t /= p.tiles_y;
-                const int tz = t % p.tiles_z;
-                const int n = t / p.tiles_z;
-                const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
-                const int chunk0 = n * p.c8_total + p.chunk_base;
-                for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
-                    if (dual && static_cast<int>(unit & 1) != r) continue;
-                    for (int bi = 0; bi < p.n_bimg; ++bi) {
-                        const int g = bi % p.G;
-                        const bool lone = p.lone_last && g == p.G - 1;
-                        const uint32_t plane_bytes = lone ? kChunkBytes : kAStageBytes;
-                        const int cc = chunk0 + 2 * g;
-                        int zc, zstep = 1;          // z coordinate of the first plane, step between planes
-                        const CUtensorMap* map = &maps.m[lone ? 1 : 0];
-                        if (p.mode == B200SEG_TC_K3) {
-                            zc = z0 - 1;
-                        } else if (p.mode == B200SEG_TC_UP) {
-                            zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
-                        } else {
-                            zc = 2 * z0 - 1 + bi / (4 * p.G);
-                            zstep = 2;
-                            map = &maps.m[(lone ? 4 : 0) + (bi / p.G) % 4];
-                        }
-                        for (int j = 0; j < n_img_planes; ++j, zc += zstep) {
-                            mbar_wait(&empty_r[s], ph ^ 1);
-                            mbar_arrive_expect_tx(&full_r[s], plane_bytes);
-                            uint8_t* dst = sA_r + s * kAStageBytes;
-                            if (p.mode == B200SEG_TC_DOWN) tma_load_5d(dst, map, &full_r[s], 0, x0 - 1, y0 - 1, zc, cc);
-                            else tma_load_4d(dst, map, &full_r[s], (x0 - 1) * 8, y0 - 1, zc, cc);
-                            if (++s == static_cast<uint32_t>(ring_n)) {
-                                s = 0;
-                                ph ^= 1;
-                            }
+            if (!dual) {
+                // =========================================================== B producer (blocking)
+                // resident mode: every image has its own slot, loaded once; otherwise a ring re-streamed per unit
+                const int total = p.resident ? n_img_round : n_seq * p.n_bimg;
+                uint32_t s = 0, ph = 0;
+                int idx = 0;
+                for (int it = 0; it < total; ++it) {
+                    mbar_wait(&empty_b[s], ph ^ 1);
+                    issue_b(idx, s);
+                    if (++idx == n_img_round) idx = 0;
+                    if (++s == static_cast<uint32_t>(p.nbuf)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            } else {
+                // =========================================================== B producer + A producer of ring 1
+                // One thread serves two queues, so it must never block on either: both are polled (test_wait).  Blocking
+                // on a full A ring while issuer 1 waits for a weight image that only this thread can load would deadlock.
+                const int b_total = p.resident ? n_img_round : (n_seq / 2) * p.n_bimg;
+                int b_next = 0, b_idx = 0;
+                uint32_t b_s = 0, b_ph = 0;
+                uint64_t* const full_r = full_a + ring_n;
+                uint64_t* const empty_r = empty_a + ring_n;
+                uint8_t* const sA_r = sA + ring_n * kAStageBytes;
+                uint32_t s = 0, ph = 0;
+                int q = 1, bi = 0, j = 0, tile = 0, pass = 0;
+                int x0 = 0, y0 = 0, zc = 0, zstep = 1, cc = 0;
+                uint32_t bytes = 0;
+                const CUtensorMap* map = nullptr;
+                bool a_done = true;
+                // position the A cursor on the first existing unit of ring 1
+                auto seek = [&]() {
+                    a_done = true;
+                    for (; q < n_seq; q += 2) {
+                        if (unit_of(q, tile, pass)) {
+                            a_done = false;
+                            bi = 0;
+                            j = 0;
+                            image_loads(tile, 0, x0, y0, zc, zstep, cc, bytes, map);
+                            break;
                         }
                     }
+                };
+                seek();
+                while (!a_done || b_next < b_total) {
+                    bool progress = false;
+                    if (b_next < b_total && (p.resident || mbar_test(&empty_b[b_s], b_ph ^ 1))) {
+                        issue_b(b_idx, b_s);
+                        ++b_next;
+                        if (++b_idx == n_img_round) b_idx = 0;
+                        if (++b_s == static_cast<uint32_t>(p.nbuf)) {
+                            b_s = 0;
+                            b_ph ^= 1;
+                        }
+                        progress = true;
+                    }
+                    if (!a_done && mbar_test(&empty_r[s], ph ^ 1)) {
+                        issue_a(sA_r + s * kAStageBytes, map, &full_r[s], bytes, x0, y0, zc, cc);
+                        if (++s == static_cast<uint32_t>(ring_n)) {
+                            s = 0;
+                            ph ^= 1;
+                        }
+                        zc += zstep;
+                        if (++j == n_img_planes) {
+                            j = 0;
+                            if (++bi == p.n_bimg) {
+                                q += 2;
+                                seek();
+                            } else {
+                                image_loads(tile, bi, x0, y0, zc, zstep, cc, bytes, map);
+                            }
+                        }
+                        progress = true;
+                    }
+                    if (!progress) __nanosleep(40);
                 }
             }
         }
@@ -533,21 +622,36 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int r = warp >> 1;
         if (elect_one()) {
             // everything the loop needs lives in registers: no divisions, no parameter re-loads per MMA
-            const int mode = p.mode, na = ring_n, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G, n_pass = p.n_pass;
+            const int mode = p.mode, na = ring_n, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G;
             const bool lone_last = p.lone_last != 0, resident = p.resident != 0;
-            uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0, unit = 0;
+            uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;
             uint64_t* const full_r = full_a + r * ring_n;
             uint64_t* const empty_r = empty_a + r * ring_n;
             const uint32_t sA16 = smem_u32(sA + r * ring_n * kAStageBytes) >> 4, sB16 = smem_u32(sB) >> 4;
             const uint32_t bbuf16 = static_cast<uint32_t>(p.bbuf_bytes) >> 4;
             const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
             const uint32_t bstep16 = 2 * p.NB;                          // one step of a B image, in 16-byte units
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int pass = 0; pass < n_pass; ++pass, ++unit) {
-                    if (dual && static_cast<int>(unit & 1) != r) continue;
-                    if (resident) b_s = pass * n_bimg;     // image slot = (pass, image), also when units are skipped
-                    const uint32_t set = kSets == 2 ? (unit & 1) : 0;
-                    mbar_wait(&acc_empty[set], ((kSets == 2 ? (unit >> 1) : unit) & 1) ^ 1);
+            for (int q = dual ? r : 0; q < n_seq; q += dual ? 2 : 1) {
+                int tile, pass;
+                if (!unit_of(q, tile, pass)) {
+                    // the partner issuer has a tile in this round, this one has none: release the streamed weight
+                    // images it would have consumed, so that the shared ring keeps turning
+                    if (!resident) {
+                        for (int bi = 0; bi < n_bimg; ++bi) {
+                            mbar_wait(&full_b[b_s], b_ph);
+                            mbar_arrive(&empty_b[b_s]);
+                            if (++b_s == static_cast<uint32_t>(nbuf)) {
+                                b_s = 0;
+                                b_ph ^= 1;
+                            }
+                        }
+                    }
+                    continue;
+                }
+                {
+                    if (resident) b_s = pass * n_bimg;     // image slot = (pass, image)
+                    const uint32_t set = kSets == 2 ? (q & 1) : 0;
+                    mbar_wait(&acc_empty[set], ((kSets == 2 ? (q >> 1) : q) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tacc = tmem + set * 256;
                     int g = 0, gq = 0;   // bi = gq * G + g
@@ -621,15 +725,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const long long d1_ss = e.dst1.sample_stride;
         const uint4* const r_base = reinterpret_cast<const uint4*>(e.residual.data) + e.residual.c8_off * o_cs;
         const long long r_ss = e.residual.sample_stride;
-        uint32_t unit = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int q = 0; q < n_seq; ++q) {
+            int tile, pass;
+            if (!unit_of(q, tile, pass)) continue;
             int t = tile;
             const int tx = t % p.tiles_x; t /= p.tiles_x;
             const int ty = t % p.tiles_y; t /= p.tiles_y;
             const int tz = t % p.tiles_z;
             const int n = t / p.tiles_z;
             const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
-            for (int pass = 0; pass < p.n_pass; ++pass, ++unit) {
+            {
+                const uint32_t unit = static_cast<uint32_t>(q);
                 const uint32_t set = kSets == 2 ? (unit & 1) : 0;
                 int oy, ox;
                 bool valid;
@@ -1050,13 +1156,23 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / kAStageBytes);
     if (na > kMaxA) na = kMaxA;
     p.na = static_cast<int>(na);
-    // two MMA issuers (one per accumulator set, half of the A ring each) when the weights are resident
-    static const bool single_issuer = [] {
-        const char* v = getenv("B200SEG_TC_SINGLE_ISSUER");   // test / profiling hook
-        return v && v[0] == '1';
+    // two MMA issuers (one per accumulator set, half of the A ring each) when every CTA has at least two tiles
+    // Measured on config 2 (profiles/r01_issuer_modes.log): dual issue helps every layer except the transposed convolution
+    // with 40 output channels, whose units are epilogue-heavy and lose more to the lock-step on the shared weight ring.
+    // B200SEG_TC_ISSUERS (test / profiling hook): 1 = single issuer everywhere, 2 = dual only with resident weights,
+    // 3 = dual wherever possible, unset = the default rule.
+    static const int issuers = [] {
+        const char* v = getenv("B200SEG_TC_ISSUERS");
+        return (v && v[0] >= '1' && v[0] <= '3') ? v[0] - '0' : 0;
     }();
-    p.dual = (variant == 2 && p.resident && p.na >= 8 && !single_issuer) ? 1 : 0;
-    const size_t smem =misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * kAStageBytes;
+    const long long tiles_all = 1LL * p.tiles_x * p.tiles_y * p.tiles_z * in.n;
+    const bool dual_ok = variant == 2 && p.na >= 8 && tiles_all >= 2LL * sms;
+    const bool dual_rule = issuers == 1 ? false
+                         : issuers == 2 ? p.resident != 0
+                         : issuers == 3 ? true
+                                        : (mode != B200SEG_TC_UP || p.resident || g.Cpad >= 80);
+    p.dual = (dual_ok && dual_rule) ? 1 : 0;
+    const size_t smem = misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * kAStageBytes;
     // ---- launch (persistent)
     const long long n_tiles = 1LL * p.tiles_x * p.tiles_y * p.tiles_z * in.n;
     const long long max_ctas = 1LL * sms * (variant == 2 ? 1 : 2);
