@@ -101,10 +101,13 @@ int b200seg_conv3d_direct(b200seg_view in, const float* weight, int32_t cout, in
  *   B200SEG_TC_K3   : kernel 3, stride 1, padding 1            (nn.Conv3d of Block3d / out_conv)
  *   B200SEG_TC_DOWN : kernel 4, stride 2, padding 1            (BlurConv3d with the blur folded, :111-121)
  *   B200SEG_TC_UP   : transposed kernel 4, stride 2, padding 1 (BlurConvTranspose3d folded, :144-154)
+ *   B200SEG_TC_K3T  : kernel 3, stride 1, padding 1 for a FINAL layer with cout <= 4 (out_conv, modular_unet.py:81-84):
+ *                     same arithmetic as K3 but the nine in-plane taps are accumulator columns summed in the epilogue,
+ *                     so one MMA per chunk pair and plane replaces nine; needs epi.out_ncdhw; own weight packing.
  * wpacked is the bf16 operand image produced by pack_tc_weight (segmentation_pipeline/models/_plan.py), laid out
  * exactly as the kernel stages it in shared memory; wpacked_bytes is checked against the geometry.
  * cout <= 80 per call (the host splits wider layers). */
-enum { B200SEG_TC_K3 = 0, B200SEG_TC_DOWN = 1, B200SEG_TC_UP = 2 };
+enum { B200SEG_TC_K3 = 0, B200SEG_TC_DOWN = 1, B200SEG_TC_UP = 2, B200SEG_TC_K3T = 3 };
 int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpacked, int64_t wpacked_bytes, int32_t cout,
                       const b200seg_epilogue* epi, void* stream);
 /* Bytes of the packed operand image the engine expects for (mode, cin chunks, cout). */

@@ -68,6 +68,9 @@ struct TcParams {
     int chunk_base;   // in.c8_off
     int c8_total;     // in.c8_total
     int tiles_x, tiles_y, tiles_z;
+    int tile_sx, tile_sy;      // tile pitch in voxels: 8 x 16, or 6 x 14 in K3T mode (the tile computes a 1-voxel border it does not own)
+    int tcout;                 // K3T: real output channels (Cpad holds 9 * tcout columns per plane)
+    int tpitch;                // K3T: floats per row of the epilogue's shared-memory exchange buffer
     int out_z, out_y, out_x;   // extent the tile grid covers (K3/DOWN: output; UP: low-res input y/x, output z)
     int zin_count;    // input planes a tile walks (zi range)
     const uint8_t* wpacked;
@@ -79,7 +82,7 @@ __host__ __device__ __forceinline__ uint32_t pad16(uint32_t n) { return (n + 15u
 // ------------------------------------------------------------------------------------------------ step tables
 // A-descriptor low word of step `st`, relative to the stage base and the parity base:
 //   (halo offset in 16-byte units) | (LBO in 16-byte units) << 16.        These are compile-time constants.
-enum StepKind { kK3Full = 0, kK3Lone = 1, kS2Full = 2, kS2Lone = 3 };
+enum StepKind { kK3Full = 0, kK3Lone = 1, kS2Full = 2, kS2Lone = 3, kT1Full = 4, kT1Lone = 5 };
 
 template <int KIND> struct Steps;
 template <> struct Steps<kK3Full> {
@@ -107,10 +110,20 @@ template <> struct Steps<kS2Lone> {
     static constexpr int n = 2;
     __device__ static constexpr uint32_t delta(int st) { return static_cast<uint32_t>(st * kHX) | (1u << 16); }
 };
+// K3T ("taps in N", tiny Cout): ONE step per chunk group, no tap shift -- row m of the MMA is halo voxel m.  The lone
+// chunk is paired with its x-neighbour (LBO = 16 B) against zero weights.
+template <> struct Steps<kT1Full> {
+    static constexpr int n = 1;
+    __device__ static constexpr uint32_t delta(int) { return static_cast<uint32_t>(kChunkBytes >> 4) << 16; }
+};
+template <> struct Steps<kT1Lone> {
+    static constexpr int n = 1;
+    __device__ static constexpr uint32_t delta(int) { return 1u << 16; }
+};
 
 // Parity base (16-byte units) of the stride-2 modes: DOWN parity 1 -> halo offset 0, parity 0 -> 1; UP: parity.
 __device__ __forceinline__ uint32_t parity_base(int mode, int pp) {
-    if (mode == B200SEG_TC_K3) return 0;
+    if (mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T) return 0;
     const int py = pp >> 1, px = pp & 1;
     const int sy0 = (mode == B200SEG_TC_DOWN) ? (1 - py) : py;
     const int sx0 = (mode == B200SEG_TC_DOWN) ? (1 - px) : px;
@@ -119,7 +132,7 @@ __device__ __forceinline__ uint32_t parity_base(int mode, int pp) {
 
 // planes touched by input plane zi: [lo, hi], B row block of plane lo, first plane that is touched for the first time
 __device__ __forceinline__ void plane_window(int mode, int TZ, int zi, int& lo, int& hi, int& jlo, int& ft) {
-    if (mode == B200SEG_TC_K3) {
+    if (mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T) {
         lo = max(zi - 2, 0);
         hi = min(zi, TZ - 1);
         jlo = 2 - zi + lo;
@@ -308,19 +321,29 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& a, int q, int cc0, con
         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        // affine in packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two exact fp32 operations per instruction)
+        f32x2 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            t[k] = fma2(pack2(__uint_as_float(r[j][2 * k]), __uint_as_float(r[j][2 * k + 1])),
+                        pack2(sc[2 * k], sc[2 * k + 1]), pack2(sh[2 * k], sh[2 * k + 1]));
         float v[8];
         if (a.slope01) {
             // 0 <= slope <= 1:  v > 0 ? v : v*slope  ==  max(v, v*slope)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
-                v[k] = fmaxf(tv, tv * sl[k]);
+            for (int k = 0; k < 4; ++k) {
+                const f32x2 u = mul2(t[k], pack2(sl[2 * k], sl[2 * k + 1]));
+                float t0, t1, u0, u1;
+                unpack2(t[k], t0, t1);
+                unpack2(u, u0, u1);
+                t[k] = pack2(fmaxf(t0, u0), fmaxf(t1, u1));
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float tv = fmaf(__uint_as_float(r[j][k]), sc[k], sh[k]);
-                v[k] = tv > 0.f ? tv : tv * sl[k];
+            for (int k = 0; k < 4; ++k) {
+                float t0, t1;
+                unpack2(t[k], t0, t1);
+                t[k] = pack2(t0 > 0.f ? t0 : t0 * sl[2 * k], t1 > 0.f ? t1 : t1 * sl[2 * k + 1]);
             }
         }
         const bool to0 = cc < a.split_c8;
@@ -330,11 +353,12 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& a, int q, int cc0, con
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float2 f = __bfloat1622float2(h[k]);
-                    v[2 * k] += f.x;
-                    v[2 * k + 1] += f.y;
+                    t[k] = add2(t[k], pack2(f.x, f.y));
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpack2(t[k], v[2 * k], v[2 * k + 1]);
         uint4 o;
         __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
@@ -410,6 +434,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(smem + tab_off);                  // kMaxZin entries
     // epilogue parameters, per 8-channel chunk: 8 scales, 8 shifts, 8 slopes (float4 reads)
     float* s_par = reinterpret_cast<float*>(smem + tab_off + sizeof(PlaneTab) * kMaxZin);
+    // K3T: per half of the epilogue warps, a 128-row exchange buffer for the tap products of one plane
+    float* t_xbuf = s_par + 3 * p.Cpad;
 
     const int warp = threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -431,7 +457,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     for (int zi = threadIdx.x; zi < p.zin_count; zi += blockDim.x) build_plane_tab(p, zi, plane_tab[zi]);
-    for (int c = threadIdx.x; c < p.Cpad; c += blockDim.x) {
+    const int n_par = p.mode == B200SEG_TC_K3T ? 8 : p.Cpad;   // K3T: Cpad counts tap columns, not channels
+    for (int c = threadIdx.x; c < n_par; c += blockDim.x) {
         float* par = s_par + (c >> 3) * 24 + (c & 7);
         par[0] = p.epi.scale[c];
         par[8] = p.epi.shift[c];
@@ -480,8 +507,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int tz = t % p.tiles_z;
         const int n = t / p.tiles_z;
-        x0 = tx * 8;
-        y0 = ty * 16;
+        x0 = tx * p.tile_sx;
+        y0 = ty * p.tile_sy;
         const int z0 = tz * p.TZ;
         const int g = bi % p.G;
         const bool lone = p.lone_last && g == p.G - 1;
@@ -489,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         cc = n * p.c8_total + p.chunk_base + 2 * g;
         zstep = 1;
         map = &maps.m[lone ? 1 : 0];
-        if (p.mode == B200SEG_TC_K3) {
+        if (p.mode == B200SEG_TC_K3 || p.mode == B200SEG_TC_K3T) {
             zc = z0 - 1;
         } else if (p.mode == B200SEG_TC_UP) {
             zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
@@ -669,7 +696,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             g = 0;
                             ++gq;
                         }
-                        const int kind = (mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
+                        const int kind = (mode == B200SEG_TC_K3 ? 0 : (mode == B200SEG_TC_K3T ? 4 : 2)) + (lone ? 1 : 0);
                         const uint32_t pbase = parity_base(mode, pp);
                         const uint32_t bs = b_s;
                         mbar_wait(&full_b[bs], resident ? 0u : b_ph);   // resident images complete phase 0 once
@@ -694,8 +721,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                                 run_image<kS2Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
                                                    pbase, b16, b_lbo, bstep16, tacc);
                                 break;
-                            default:
+                            case kS2Lone:
                                 run_image<kS2Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
+                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                break;
+                            case kT1Full:
+                                run_image<kT1Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
+                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                break;
+                            default:
+                                run_image<kT1Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
                                                    pbase, b16, b_lbo, bstep16, tacc);
                                 break;
                         }
@@ -733,7 +768,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             const int ty = t % p.tiles_y; t /= p.tiles_y;
             const int tz = t % p.tiles_z;
             const int n = t / p.tiles_z;
-            const int x0 = tx * 8, y0 = ty * 16, z0 = tz * p.TZ;
+            const int x0 = tx * p.tile_sx, y0 = ty * p.tile_sy, z0 = tz * p.TZ;
             {
                 const uint32_t unit = static_cast<uint32_t>(q);
                 const uint32_t set = kSets == 2 ? (unit & 1) : 0;
@@ -760,7 +795,118 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 mbar_wait(&acc_full[set], (kSets == 2 ? (unit >> 1) : unit) & 1);
                 tc_fence_after();
                 const uint32_t tbase = tmem + set * 256 + (static_cast<uint32_t>(lg * 32) << 16);
-                if (e.out_ncdhw == nullptr) {
+                if (kEpi == 0 && p.mode == B200SEG_TC_K3T) {
+                    // Final layer with tiny Cout: accumulator row m holds, for halo voxel m of the tile, the products of
+                    // all nine in-plane taps (column (dy*3+dx)*cout + co).  The rows go through shared memory; every
+                    // interior voxel sums the nine columns of its nine neighbours, then bias / softmax / fp32 store.
+                    const int tcout = p.tcout, pitch = p.tpitch, ncol = 9 * p.tcout, nld = p.Cpad >> 3;
+                    float* const xbuf = t_xbuf + half * (128 * pitch);
+                    const int yT = y0 - 1 + my, xT = x0 - 1 + mx;
+                    const bool mine = my >= 1 && my <= 14 && mx >= 1 && mx <= 6 && yT < p.out_y && xT < p.out_x;
+                    const int nq = min(p.TZ, p.out_z - z0);
+                    const long long vox = 1LL * p.out_z * p.out_y * p.out_x;
+                    if (tcout == 2 && e.softmax) {
+                        // the shipped heads (2 classes + softmax): straight-line code, 64-bit shared-memory accesses at
+                        // immediate offsets (row pitch 26 floats), two-class softmax with one exponential
+                        constexpr int kP = 26;
+                        float2* const row2 = reinterpret_cast<float2*>(xbuf + m * kP);
+                        const float* const nb = xbuf + (m - 9) * kP;       // neighbour (dy, dx) = (0, 0)
+                        const float sc0 = s_par[0], sc1 = s_par[1], sh0 = s_par[8], sh1 = s_par[9];
+                        const float sl0 = s_par[16], sl1 = s_par[17];
+                        float* dst = e.out_ncdhw + static_cast<long long>(n) * 2 * vox +
+                                     (static_cast<long long>(z0) * p.out_y + yT) * p.out_x + xT;
+                        const long long plane = static_cast<long long>(p.out_y) * p.out_x;
+                        for (int q = half; q < nq; q += kHalves) {
+                            uint32_t r[3][8];
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) tmem_ld8(tbase + q * 24 + j * 8, r[j]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int t = 0; t < 9; ++t)
+                                row2[t] = make_float2(__uint_as_float(r[(2 * t) >> 3][(2 * t) & 7]),
+                                                      __uint_as_float(r[(2 * t + 1) >> 3][(2 * t + 1) & 7]));
+                            if (half == 0) named_bar_sync<1>(128); else named_bar_sync<2>(128);
+                            if (mine) {
+                                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                    for (int dx = 0; dx < 3; ++dx) {
+                                        const float2 t2 = *reinterpret_cast<const float2*>(
+                                            nb + (dy * 8 + dx) * kP + (dy * 3 + dx) * 2);
+                                        a0 += t2.x;
+                                        a1 += t2.y;
+                                    }
+                                float v0 = fmaf(a0, sc0, sh0), v1 = fmaf(a1, sc1, sh1);
+                                v0 = v0 > 0.f ? v0 : v0 * sl0;
+                                v1 = v1 > 0.f ? v1 : v1 * sl1;
+                                // softmax of two logits: the larger one contributes exp(0) = 1 exactly
+                                const float ex = expf(-fabsf(v0 - v1)), sum = 1.f + ex;
+                                const float hi = 1.f / sum, lo = ex / sum;
+                                const bool first = v0 >= v1;
+                                float* d = dst + q * plane;
+                                d[0] = first ? hi : lo;
+                                d[vox] = first ? lo : hi;
+                            }
+                            if (half == 0) named_bar_sync<1>(128); else named_bar_sync<2>(128);
+                        }
+                    } else
+                    for (int q = half; q < nq; q += kHalves) {
+                        uint32_t r[5][8];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (j < nld) tmem_ld8(tbase + q * p.Cpad + j * 8, r[j]);
+                        tmem_ld_wait();
+                        float* const row = xbuf + m * pitch;
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (j < nld) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    if (j * 8 + k < ncol) row[j * 8 + k] = __uint_as_float(r[j][k]);
+                            }
+                        if (half == 0) named_bar_sync<1>(128); else named_bar_sync<2>(128);
+                        if (mine) {
+                            float v[4];
+#pragma unroll
+                            for (int co = 0; co < 4; ++co) {
+                                if (co < tcout) {
+                                    float acc = 0.f;
+#pragma unroll
+                                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                        for (int dx = 0; dx < 3; ++dx)
+                                            acc += xbuf[((my + dy - 1) * 8 + (mx + dx - 1)) * pitch + (dy * 3 + dx) * tcout + co];
+                                    const float tv = fmaf(acc, s_par[co], s_par[8 + co]);
+                                    v[co] = tv > 0.f ? tv : tv * s_par[16 + co];
+                                }
+                            }
+                            float* dst = e.out_ncdhw + static_cast<long long>(n) * tcout * vox +
+                                         (static_cast<long long>(z0 + q) * p.out_y + yT) * p.out_x + xT;
+                            if (e.softmax) {
+                                float mx_ = -INFINITY, sum = 0.f;
+#pragma unroll
+                                for (int co = 0; co < 4; ++co)
+                                    if (co < tcout) mx_ = fmaxf(mx_, v[co]);
+#pragma unroll
+                                for (int co = 0; co < 4; ++co)
+                                    if (co < tcout) {
+                                        v[co] = expf(v[co] - mx_);
+                                        sum += v[co];
+                                    }
+#pragma unroll
+                                for (int co = 0; co < 4; ++co)
+                                    if (co < tcout) dst[co * vox] = v[co] / sum;
+                            } else {
+#pragma unroll
+                                for (int co = 0; co < 4; ++co)
+                                    if (co < tcout) dst[co * vox] = v[co];
+                            }
+                        }
+                        // the buffer is rewritten by the next plane of this half
+                        if (half == 0) named_bar_sync<1>(128); else named_bar_sync<2>(128);
+                    }
+                } else if (kEpi != 0 || e.out_ncdhw == nullptr) {
                     if constexpr (kEpi != 0) {
                         // specialised epilogues: 10 chunks (the two warps of a lane quarter take 5 chunks each of
                         // every plane) or 5 chunks (they take alternate planes), with or without a residual
@@ -971,14 +1117,16 @@ struct TcGeom {
 };
 
 static int tc_geometry(int mode, int cin_chunks, int cout, TcGeom* g) {
-    B200SEG_CHECK_ARG(mode >= 0 && mode <= 2, "conv3d_tc: bad mode %d", mode);
+    B200SEG_CHECK_ARG(mode >= 0 && mode <= 3, "conv3d_tc: bad mode %d", mode);
     B200SEG_CHECK_ARG(cout >= 1 && cout <= 80, "conv3d_tc: cout %d not in [1,80] (split wider layers)", cout);
+    B200SEG_CHECK_ARG(mode != B200SEG_TC_K3T || cout <= 4, "conv3d_tc K3T: cout %d not in [1,4]", cout);
     B200SEG_CHECK_ARG(cin_chunks >= 1, "conv3d_tc: no input chunks");
-    g->Cpad = (cout + 7) / 8 * 8;
-    g->blocks = mode == B200SEG_TC_K3 ? 3 : (mode == B200SEG_TC_DOWN ? 2 : 4);
+    // K3T: the 9 in-plane taps are columns of the accumulator (9 * cout per plane), summed in the epilogue
+    g->Cpad = mode == B200SEG_TC_K3T ? (9 * cout + 7) / 8 * 8 : (cout + 7) / 8 * 8;
+    g->blocks = (mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T) ? 3 : (mode == B200SEG_TC_DOWN ? 2 : 4);
     g->NB = g->blocks * g->Cpad + 16;
-    g->steps_full = mode == B200SEG_TC_K3 ? 9 : 4;
-    g->steps_lone = mode == B200SEG_TC_K3 ? 5 : 2;
+    g->steps_full = mode == B200SEG_TC_K3 ? 9 : (mode == B200SEG_TC_K3T ? 1 : 4);
+    g->steps_lone = mode == B200SEG_TC_K3 ? 5 : (mode == B200SEG_TC_K3T ? 1 : 2);
     g->G = (cin_chunks + 1) / 2;
     g->lone_last = cin_chunks & 1;
     g->n_pass = mode == B200SEG_TC_UP ? 4 : 1;
@@ -1031,7 +1179,7 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
                       static_cast<long long>(wpacked_bytes), static_cast<long long>(need));
     // ---- output extent
     int oz, oy, ox;
-    if (mode == B200SEG_TC_K3) {
+    if (mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T) {
         oz = in.z; oy = in.y; ox = in.x;
     } else if (mode == B200SEG_TC_DOWN) {
         B200SEG_CHECK_ARG(in.z % 2 == 0 && in.y % 2 == 0 && in.x % 2 == 0, "conv3d_tc DOWN: input extent must be even");
@@ -1039,7 +1187,9 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     } else {
         oz = in.z * 2; oy = in.y * 2; ox = in.x * 2;
     }
-    B200SEG_CHECK_ARG(epi->out_ncdhw == nullptr || mode == B200SEG_TC_K3, "conv3d_tc: out_ncdhw only in K3 mode");
+    B200SEG_CHECK_ARG(epi->out_ncdhw == nullptr || mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T,
+                      "conv3d_tc: out_ncdhw only in K3 / K3T mode");
+    B200SEG_CHECK_ARG(mode != B200SEG_TC_K3T || epi->out_ncdhw != nullptr, "conv3d_tc K3T: needs out_ncdhw (final layer)");
     DEpilogue de;
     rc = make_depilogue(epi, cout, in.n, oz, oy, ox, B200SEG_BF16, &de);
     if (rc) return rc;
@@ -1088,8 +1238,9 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     if (mode == B200SEG_TC_UP && (TZ & 1)) ++TZ;
     {
         // small grids: thinner z tiles until every CTA slot has work (or TZ bottoms out)
-        const int plane_tiles = (mode == B200SEG_TC_UP ? ((in.x + 7) / 8) * ((in.y + 15) / 16)
-                                                       : ((ox + 7) / 8) * ((oy + 15) / 16)) * in.n;
+        const int plane_tiles = (mode == B200SEG_TC_UP    ? ((in.x + 7) / 8) * ((in.y + 15) / 16)
+                                 : mode == B200SEG_TC_K3T ? ((ox + 5) / 6) * ((oy + 13) / 14)
+                                                          : ((ox + 7) / 8) * ((oy + 15) / 16)) * in.n;
         const int tz_min = mode == B200SEG_TC_UP ? 2 : 1;
         while (TZ > tz_min && plane_tiles * ((oz + TZ - 1) / TZ) < 4 * sms) {
             TZ = (TZ + 1) / 2;
@@ -1104,12 +1255,27 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
         p.out_y = in.y;  // validity is tested in low-res coordinates
         p.out_x = in.x;
         p.zin_count = TZ / 2 + 2;
+    } else if (mode == B200SEG_TC_K3T) {
+        // a tile computes the tap products of its 16 x 8 halo-anchored voxels and owns the 14 x 6 interior
+        p.tile_sx = 6;
+        p.tile_sy = 14;
+        p.tiles_x = (ox + 5) / 6;
+        p.tiles_y = (oy + 13) / 14;
+        p.out_y = oy;
+        p.out_x = ox;
+        p.zin_count = TZ + 2;
+        p.tcout = cout;
+        p.tpitch = 9 * cout + 8;
     } else {
         p.tiles_x = (ox + 7) / 8;
         p.tiles_y = (oy + 15) / 16;
         p.out_y = oy;
         p.out_x = ox;
         p.zin_count = mode == B200SEG_TC_K3 ? TZ + 2 : 2 * TZ + 2;
+    }
+    if (mode != B200SEG_TC_K3T) {
+        p.tile_sx = 8;
+        p.tile_sy = 16;
     }
     p.out_z = oz;
     B200SEG_CHECK_ARG(p.zin_count <= kMaxZin, "conv3d_tc: tile walks %d input planes (max %d)", p.zin_count, kMaxZin);
@@ -1142,7 +1308,8 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     // ---- shared memory: weight image ring (double-buffered when it fits) + A plane ring
     p.bbuf_bytes = (g.bimg_stride + 127) & ~127;
     const size_t misc = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + sizeof(PlaneTab) * kMaxZin +
-                        3 * static_cast<size_t>(g.Cpad) * 4 + 256;
+                        3 * static_cast<size_t>(g.Cpad) * 4 + 256 +
+                        (mode == B200SEG_TC_K3T ? 2 * 128 * static_cast<size_t>(p.tpitch) * 4 : 0);
     const size_t budget = variant == 2 ? 224 * 1024 : 112 * 1024;
     // weights stay resident (one slot per image, loaded once per CTA) when the whole packed operand fits next to
     // at least 8 A stages; otherwise the images stream through a ring (double-buffered when possible)

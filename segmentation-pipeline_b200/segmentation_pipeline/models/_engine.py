@@ -23,6 +23,9 @@ TRACE = None    # set to a list to record (call, extent, (start, end) CUDA event
 TC_MAX_COUT = 80
 
 
+_NO_K3T = os.environ.get("B200SEG_TC_NO_K3T", "0") == "1"     # profiling hook: final layer through the plain K3 mode
+
+
 def set_precision(mode: str) -> None:
     if mode not in ("auto", "fp32", "bf16"):
         raise ValueError("precision must be 'auto', 'fp32' or 'bf16'")
@@ -141,7 +144,9 @@ class CompiledPlan:
         for lo, hi, d0, d1, split, res in pieces:
             call = self._new_call(op, True, geom)
             phys = _plan.physical_weight(op.weight, op.mode == UP, op.segments, n_chunks, lo, hi)
-            call.weight = _plan.pack_tc_weight(op.mode, phys, n_chunks, hi - lo).to(self.device)
+            if op.final and op.mode == K3 and hi - lo <= _plan.K3T_MAX_COUT and not _NO_K3T:
+                call.mode = _plan.K3T      # tiny-Cout final layer: taps as accumulator columns (see conv_tc.cu)
+            call.weight = _plan.pack_tc_weight(call.mode, phys, n_chunks, hi - lo).to(self.device)
             call.cout = hi - lo
             cpad = c8(hi - lo) * 8
             call.scale, call.shift, call.slope = (self._dev(self._padded(a[lo:hi], cpad)) for a in

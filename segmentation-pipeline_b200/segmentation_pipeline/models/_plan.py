@@ -27,6 +27,8 @@ import torch.nn.functional as F
 from torch import nn
 
 K3, DOWN, UP = 0, 1, 2          # tensor-core engine modes (B200SEG_TC_*)
+K3T = 3                         # K3 for a final layer with cout <= 4: the nine in-plane taps are accumulator columns
+K3T_MAX_COUT = 4
 HX, HY = 10, 18                 # halo extent of the engine's 8 x 16 tile
 
 
@@ -511,11 +513,11 @@ def pack_direct_weight(op: ConvOp, n_chunks: int) -> torch.Tensor:
 
 def tc_geometry(mode: int, cin_chunks: int, cout: int) -> dict:
     """Mirror of tc_geometry() in csrc/conv_tc.cu."""
-    cpad = c8(cout) * 8
-    blocks = {K3: 3, DOWN: 2, UP: 4}[mode]
+    cpad = c8(9 * cout if mode == K3T else cout) * 8
+    blocks = {K3: 3, DOWN: 2, UP: 4, K3T: 3}[mode]
     nb = blocks * cpad + 16
-    steps_full = 9 if mode == K3 else 4
-    steps_lone = 5 if mode == K3 else 2
+    steps_full = {K3: 9, K3T: 1}.get(mode, 4)
+    steps_lone = {K3: 5, K3T: 1}.get(mode, 2)
     groups = (cin_chunks + 1) // 2
     return dict(cpad=cpad, blocks=blocks, nb=nb, steps_full=steps_full, steps_lone=steps_lone, groups=groups,
                 lone_last=cin_chunks % 2, n_pass=4 if mode == UP else 1,
@@ -525,6 +527,9 @@ def tc_geometry(mode: int, cin_chunks: int, cout: int) -> dict:
 def step_units(mode: int, lone: bool, pp: int, st: int):
     """The two K-halves of MMA step ``st``: each is (sy, sx, chunk_in_group) or None (zero weights).
     (sy, sx) is the halo offset the A operand starts at -- must agree with step_desc() in csrc/conv_tc.cu."""
+    if mode == K3T:
+        # one step, A rows are the halo voxels themselves (offset 0); a lone chunk is paired with zero weights
+        return [(0, 0, 0), None] if lone else [(0, 0, 0), (0, 0, 1)]
     if mode == K3:
         if not lone:
             return [(st // 3, st % 3, 0), (st // 3, st % 3, 1)]
@@ -554,7 +559,7 @@ def tap_of(mode: int, pp: int, sy: int, sx: int):
 
 def block_tz(mode: int, j: int, zpar: int) -> int:
     """Kernel tap along z served by row block ``j`` of a B image."""
-    if mode == K3:
+    if mode in (K3, K3T):
         return 2 - j
     if mode == DOWN:
         return (3 if zpar else 2) - 2 * j
@@ -582,8 +587,18 @@ def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) ->
                     if unit is None:
                         continue
                     sy, sx, ck = unit
-                    ty, tx = tap_of(mode, pp, sy, sx)
                     chunk = 2 * grp + ck
+                    if mode == K3T:
+                        # rows of block j: column (dy*3+dx)*cout + co = weight of tap (2-j, dy, dx), channel co
+                        for j in range(g["blocks"]):
+                            tz = block_tz(mode, j, zpar)
+                            for dy in range(3):
+                                for dx in range(3):
+                                    r0 = j * cpad + (dy * 3 + dx) * cout
+                                    img[ps, bi, st, half, r0:r0 + cout, :] = \
+                                        phys[tz, dy, dx, chunk * 8:(chunk + 1) * 8, :cout].t()
+                        continue
+                    ty, tx = tap_of(mode, pp, sy, sx)
                     for j in range(g["blocks"]):
                         tz = block_tz(mode, j, zpar)
                         # (8 cin, Cpad) -> rows = cout, 8 contiguous input channels

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-K3, DOWN, UP = 0, 1, 2
+K3, DOWN, UP, K3T = 0, 1, 2, 3
 HX, HY = 10, 18
 CHUNK_BYTES = HX * HY * 16
 STAGE_BYTES = 2 * CHUNK_BYTES
@@ -23,7 +23,9 @@ def pad16(n):
 
 
 def step_desc(mode, lone, pp, st):
-    """(byte offset, LBO bytes) -- transcription of step_desc() in conv_tc.cu."""
+    """(byte offset, LBO bytes) -- transcription of Steps<KIND>::delta() in conv_tc.cu."""
+    if mode == K3T:
+        return 0, (16 if lone else CHUNK_BYTES)
     if mode == K3:
         if not lone:
             return ((st // 3) * HX + (st % 3)) * 16, CHUNK_BYTES
@@ -42,7 +44,7 @@ def step_desc(mode, lone, pp, st):
 
 def plane_window(mode, TZ, zi):
     """(lo, hi, jlo, ft) -- transcription of plane_window() in conv_tc.cu."""
-    if mode == K3:
+    if mode in (K3, K3T):
         lo, hi = max(zi - 2, 0), min(zi, TZ - 1)
         return lo, hi, 2 - zi + lo, (zi if zi < TZ else TZ)
     if mode == DOWN:
@@ -63,18 +65,19 @@ def _operand(mem, start_byte, rows, lbo, sbo):
 
 def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
     """x_blocked: float array [N][C8][Z][Y][X][8] (values already bf16-representable);
-    wpacked: float array [pass][image][step][2][NB][8].  Returns raw accumulators [N][Cpad][oz][oy][ox]."""
+    wpacked: float array [pass][image][step][2][NB][8].  Returns raw accumulators [N][Cpad][oz][oy][ox]
+    (K3T: the tap-summed outputs [N][cout][oz][oy][ox])."""
     N, C8, Z, Y, X, _ = x_blocked.shape
-    cpad = (cout + 7) // 8 * 8
-    blocks = {K3: 3, DOWN: 2, UP: 4}[mode]
+    cpad = ((9 * cout if mode == K3T else cout) + 7) // 8 * 8
+    blocks = {K3: 3, DOWN: 2, UP: 4, K3T: 3}[mode]
     NB = blocks * cpad + 16
-    steps_full, steps_lone = (9, 5) if mode == K3 else (4, 2)
+    steps_full, steps_lone = {K3: (9, 5), K3T: (1, 1)}.get(mode, (4, 2))
     G = (C8 + 1) // 2
     lone_last = C8 % 2
     n_pass = 4 if mode == UP else 1
     n_bimg = 8 * G if mode == DOWN else G
     assert wpacked.shape == (n_pass, n_bimg, steps_full, 2, NB, 8), wpacked.shape
-    if mode == K3:
+    if mode in (K3, K3T):
         oz, oy, ox = Z, Y, X
     elif mode == DOWN:
         oz, oy, ox = Z // 2, Y // 2, X // 2
@@ -97,8 +100,12 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
         tiles_x, tiles_y, lim_y, lim_x, zin = -(-X // 8), -(-Y // 16), Y, X, TZ // 2 + 2
     else:
         tiles_x, tiles_y, lim_y, lim_x = -(-ox // 8), -(-oy // 16), oy, ox
-        zin = TZ + 2 if mode == K3 else 2 * TZ + 2
-    out = np.full((N, cpad, oz, oy, ox), np.nan, dtype=np.float64)
+        zin = TZ + 2 if mode in (K3, K3T) else 2 * TZ + 2
+    sx, sy = 8, 16
+    if mode == K3T:      # tiles own the 14 x 6 interior of the 16 x 8 voxels they compute tap products for
+        sx, sy = 6, 14
+        tiles_x, tiles_y = -(-ox // 6), -(-oy // 14)
+    out = np.full((N, cout if mode == K3T else cpad, oz, oy, ox), np.nan, dtype=np.float64)
 
     def load_box(n, chunk, nch, cx, cy, cz, pp):
         """TMA box load -> flat stage array (elements); bytes not written stay NaN."""
@@ -123,7 +130,7 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
         for tz in range(tiles_z):
             for ty in range(tiles_y):
                 for tx in range(tiles_x):
-                    x0, y0, z0 = tx * 8, ty * 16, tz * TZ
+                    x0, y0, z0 = tx * sx, ty * sy, tz * TZ
                     tmem = np.full((128, TZ * cpad + 16), np.nan)
                     for ps in range(n_pass):
                         for bi in range(n_bimg):
@@ -139,7 +146,7 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
                                 pp = ps
                             for zi in range(zi_start, zin, zi_step):
                                 nch = 1 if lone else 2
-                                if mode == K3:
+                                if mode in (K3, K3T):
                                     stage = load_box(n, 2 * g, nch, x0 - 1, y0 - 1, z0 - 1 + zi, 0)
                                 elif mode == UP:
                                     stage = load_box(n, 2 * g, nch, x0 - 1, y0 - 1, z0 // 2 - 1 + zi, 0)
@@ -163,6 +170,25 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
                                         tmem[:, cols] = prod if overwrite else tmem[:, cols] + prod
                                         q += npl
                         # epilogue of this pass
+                        if mode == K3T:
+                            # row m = halo voxel (y0-1+my, x0-1+mx); interior voxels sum the nine tap columns of
+                            # their nine neighbours (fixed dy, dx order, like the kernel)
+                            for m in range(128):
+                                my, mx = m >> 3, m & 7
+                                yy, xx = y0 - 1 + my, x0 - 1 + mx
+                                if not (1 <= my <= 14 and 1 <= mx <= 6 and yy < lim_y and xx < lim_x):
+                                    continue
+                                for q in range(TZ):
+                                    if z0 + q >= oz:
+                                        break
+                                    for co in range(cout):
+                                        acc = 0.0
+                                        for dy in range(3):
+                                            for dx in range(3):
+                                                acc += tmem[(my + dy - 1) * 8 + (mx + dx - 1),
+                                                            q * cpad + (dy * 3 + dx) * cout + co]
+                                        out[n, co, z0 + q, yy, xx] = acc
+                            continue
                         for m in range(128):
                             my, mx = m >> 3, m & 7
                             if mode == UP:

@@ -298,6 +298,35 @@ def test_conv_tc_softmax_head(lib):
         assert torch.allclose(out.sum(1).cpu(), torch.ones(2, 7, 18, 9), atol=1e-5)
 
 
+@pytest.mark.parametrize("cin,cout,ext,softmax", [(40, 2, (2, 7, 30, 14), True),     # out_conv: 3 x 3 tiles of 14 x 6
+                                                  (40, 2, (1, 96, 96, 96), True),   # bench shape, dual issuers
+                                                  (8, 1, (1, 3, 15, 7), False),     # lone chunk, one class, logits
+                                                  (24, 4, (2, 13, 17, 9), True),    # widest tap block, ragged tiles
+                                                  (16, 3, (1, 5, 14, 6), False)])
+def test_conv_tc_taps_in_n_head(lib, cin, cout, ext, softmax):
+    """B200SEG_TC_K3T (final layer with cout <= 4: nine in-plane taps as accumulator columns, summed in the
+    epilogue) against the fp32 torch convolution of the same bf16-rounded operands."""
+    from segmentation_pipeline.models import _plan
+    g = torch.Generator().manual_seed(79 + cin + cout)
+    n = ext[0]
+    x = torch.randn(n, cin, *ext[1:], generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g)
+    ref = F.conv3d(x, w, bias, padding=1)
+    if softmax:
+        ref = torch.softmax(ref, 1)
+    chunks = (cin + 7) // 8
+    phys = _plan.physical_weight(w, False, [(0, cin)], chunks, 0, cout)
+    packed = dev(_plan.pack_tc_weight(_plan.K3T, phys, chunks, cout))
+    assert packed.numel() * 2 == lib.conv3d_tc_wbytes(_plan.K3T, chunks, cout)
+    out = torch.full(ref.shape, float("nan"), device="cuda")
+    epi, keep = _epi(lib, cout, out=out, softmax=softmax, bias=bias)
+    lib.conv3d_tc(_plan.K3T, to_blocked(lib, x, torch.bfloat16).view(cin), packed, cout, epi)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()                       # every voxel is owned by exactly one tile
+    assert (out.cpu() - ref).abs().max() <= (2e-5 if softmax else 2e-4)
+
+
 def test_conv_tc_fused_two_destinations(lib):
     """conv0 || res_conv as one contraction: channels [0,40) -> ReLU'd tensor, [40,80) -> bias-only tensor."""
     from segmentation_pipeline.models import _plan

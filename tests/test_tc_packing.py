@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from segmentation_pipeline.models import _plan
-from tc_emulator import DOWN, K3, UP, emulate_conv_tc
+from tc_emulator import DOWN, K3, K3T, UP, emulate_conv_tc
 
 
 def _bf16(t):
@@ -33,6 +33,9 @@ CASES = [
     (UP, 16, 16, (3, 5, 9), None),
     (UP, 8, 40, (2, 17, 3), None),       # lone chunk, N spill
     (UP, 16, 80, (4, 4, 4), None),       # 4 planes x 80 > 256 -> column blocks of 2 planes
+    (K3T, 40, 2, (5, 30, 14), None),     # out_conv shape: 2 pairs + lone chunk, 3 x 3 tiles of 14 x 6, 18 tap columns
+    (K3T, 8, 1, (3, 15, 7), 2),          # lone chunk only, one column per tap, z split
+    (K3T, 16, 4, (4, 14, 6), None),      # widest tap block (36 -> 40 columns), tile exactly full
 ]
 
 
@@ -58,7 +61,7 @@ def test_engine_dataflow_matches_torch(mode, cin, cout, ext, tz):
     got = torch.from_numpy(out[:, :cout])
     assert not torch.isnan(got).any(), "engine read bytes it never wrote / accumulated before first touch"
     assert torch.allclose(got, ref, atol=1e-9, rtol=1e-9)
-    # padded output channels must come out exactly zero
+    # padded output channels must come out exactly zero (K3T returns the tap-summed channels only)
     assert np.all(out[:, cout:] == 0)
 
 

@@ -43,14 +43,14 @@ def main():
         if isinstance(call, _engine._ConvCall):
             lvl = compiled.plan.buffers[call.src.buf][1]
             ez, ey, ex = z >> lvl, y >> lvl, xx >> lvl
-            taps = 27 if call.mode == 0 else (64 if call.mode == 1 else 8)
+            taps = 27 if call.mode in (0, 3) else (64 if call.mode == 1 else 8)
             if call.mode == 1:
                 ez, ey, ex = ez // 2, ey // 2, ex // 2
             if call.mode == 2:
                 ez, ey, ex = ez * 2, ey * 2, ex * 2
             flop = 2.0 * n * ez * ey * ex * taps * call.src.c * call.cout
             total_flop += flop
-            print(f"{call.name:28s} {['k3','down','up'][call.mode]:5s} {call.src.c:4d} {call.cout:4d} "
+            print(f"{call.name:28s} {['k3','down','up','k3t'][call.mode]:5s} {call.src.c:4d} {call.cout:4d} "
                   f"{f'{ez}x{ey}x{ex}':>12s} {ms:8.3f} {flop / ms / 1e9:8.1f}")
         else:
             print(f"{type(call).__name__:28s} {'':5s} {'':4s} {'':4s} {'':>12s} {ms:8.3f}")
