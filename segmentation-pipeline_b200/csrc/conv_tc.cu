@@ -69,6 +69,8 @@ struct TcParams {
     int c8_total;     // in.c8_total
     int tiles_x, tiles_y, tiles_z;
     int tile_sx, tile_sy;      // tile pitch in voxels: 8 x 16, or 6 x 14 in K3T mode (the tile computes a 1-voxel border it does not own)
+    int stage_bytes;           // bytes of one A ring stage: 5760 (one chunk pair), K3T: all chunk groups of the plane
+    int cin_chunks;            // input chunks of the layer
     int tcout;                 // K3T: real output channels (Cpad holds 9 * tcout columns per plane)
     int tpitch;                // K3T: floats per row of the epilogue's shared-memory exchange buffer
     int out_z, out_y, out_x;   // extent the tile grid covers (K3/DOWN: output; UP: low-res input y/x, output z)
@@ -82,7 +84,7 @@ __host__ __device__ __forceinline__ uint32_t pad16(uint32_t n) { return (n + 15u
 // ------------------------------------------------------------------------------------------------ step tables
 // A-descriptor low word of step `st`, relative to the stage base and the parity base:
 //   (halo offset in 16-byte units) | (LBO in 16-byte units) << 16.        These are compile-time constants.
-enum StepKind { kK3Full = 0, kK3Lone = 1, kS2Full = 2, kS2Lone = 3, kT1Full = 4, kT1Lone = 5 };
+enum StepKind { kK3Full = 0, kK3Lone = 1, kS2Full = 2, kS2Lone = 3, kT = 4 };
 
 template <int KIND> struct Steps;
 template <> struct Steps<kK3Full> {
@@ -110,17 +112,6 @@ template <> struct Steps<kS2Lone> {
     static constexpr int n = 2;
     __device__ static constexpr uint32_t delta(int st) { return static_cast<uint32_t>(st * kHX) | (1u << 16); }
 };
-// K3T ("taps in N", tiny Cout): ONE step per chunk group, no tap shift -- row m of the MMA is halo voxel m.  The lone
-// chunk is paired with its x-neighbour (LBO = 16 B) against zero weights.
-template <> struct Steps<kT1Full> {
-    static constexpr int n = 1;
-    __device__ static constexpr uint32_t delta(int) { return static_cast<uint32_t>(kChunkBytes >> 4) << 16; }
-};
-template <> struct Steps<kT1Lone> {
-    static constexpr int n = 1;
-    __device__ static constexpr uint32_t delta(int) { return 1u << 16; }
-};
-
 // Parity base (16-byte units) of the stride-2 modes: DOWN parity 1 -> halo offset 0, parity 0 -> 1; UP: parity.
 __device__ __forceinline__ uint32_t parity_base(int mode, int pp) {
     if (mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T) return 0;
@@ -239,7 +230,7 @@ template <int KIND>
 __device__ __forceinline__ void run_image(bool first_image, int n_planes, int zstep, const PlaneTab* pt,
                                           uint64_t* full_a, uint64_t* empty_a, uint32_t& a_s, uint32_t& a_ph, int na,
                                           uint32_t sA16, uint32_t pbase, uint32_t b16, uint32_t b_lbo,
-                                          uint32_t bstep16, uint32_t tacc) {
+                                          uint32_t bstep16, uint32_t tacc, uint32_t stage16) {
     PlaneRegs cur = load_plane_regs(pt);
     for (int j = 0; j < n_planes; ++j) {
         const PlaneTab* ptn = pt + zstep;
@@ -252,7 +243,7 @@ __device__ __forceinline__ void run_image(bool first_image, int n_planes, int zs
             a_s = 0;
             a_ph ^= 1;
         }
-        const uint32_t a16 = sA16 + s * (kAStageBytes >> 4) + pbase;
+        const uint32_t a16 = sA16 + s * stage16 + pbase;
         if (first_image) {
             // first step of the pass: first-touch split (planes seen for the first time overwrite)
             const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 + Steps<KIND>::delta(0));
@@ -268,6 +259,56 @@ __device__ __forceinline__ void run_image(bool first_image, int n_planes, int zs
         umma_commit(&empty_a[s]);
         cur = nxt;
         pt = ptn;
+    }
+}
+
+// K3T ("taps in N", tiny Cout): the plane's stage holds every chunk group; step g multiplies chunk group g, unshifted
+// (row m of the MMA is halo voxel m), by the image's step g.  A lone last chunk pairs with its x-neighbour (LBO = 16 B)
+// against zero weights.  One MMA per group and column block: the per-plane overhead is paid once for the whole plane.
+__device__ __forceinline__ void run_image_t(int G, bool lone_last, int n_planes, const PlaneTab* pt, uint64_t* full_a,
+                                            uint64_t* empty_a, uint32_t& a_s, uint32_t& a_ph, int na, uint32_t sA16,
+                                            uint32_t b16, uint32_t b_lbo, uint32_t bstep16, uint32_t tacc,
+                                            uint32_t stage16) {
+    constexpr int kMaxG = 6;     // host limit: at most 12 input chunks
+    for (int j = 0; j < n_planes; ++j, ++pt) {
+        // MMA blocks of this plane, fetched before blocking on its data: [1] = step 0 (first-touch split), [0] = the rest
+        const PlaneRegs norm = load_plane_regs(pt);
+        const uint4 f0 = *reinterpret_cast<const uint4*>(&pt->blk[1][0]);
+        const uint4 f1 = *reinterpret_cast<const uint4*>(&pt->blk[1][1]);
+        const uint4 f2 = *reinterpret_cast<const uint4*>(&pt->blk[1][2]);
+        const int nb1 = pt->nblk[1];
+        const uint32_t s = a_s;
+        mbar_wait(&full_a[s], a_ph);
+        tc_fence_after();
+        if (++a_s == static_cast<uint32_t>(na)) {
+            a_s = 0;
+            a_ph ^= 1;
+        }
+        const uint32_t a16 = sA16 + s * stage16;
+        const uint32_t lbo_full = static_cast<uint32_t>(kChunkBytes >> 4) << 16;
+        {
+            const uint64_t adesc = kADescHi | static_cast<uint64_t>(a16 | ((lone_last && G == 1) ? (1u << 16) : lbo_full));
+            umma_bf16(tacc + f0.x, adesc, kBDescHi | static_cast<uint64_t>((b16 + f0.z) | b_lbo), f0.y, f0.w);
+            if (nb1 > 1) umma_bf16(tacc + f1.x, adesc, kBDescHi | static_cast<uint64_t>((b16 + f1.z) | b_lbo), f1.y, f1.w);
+            if (nb1 > 2) umma_bf16(tacc + f2.x, adesc, kBDescHi | static_cast<uint64_t>((b16 + f2.z) | b_lbo), f2.y, f2.w);
+        }
+#pragma unroll
+        for (int g = 1; g < kMaxG; ++g) {
+            if (g < G) {
+                const uint32_t lbo = (lone_last && g == G - 1) ? (1u << 16) : lbo_full;
+                const uint64_t adesc = kADescHi | static_cast<uint64_t>((a16 + g * (kAStageBytes >> 4)) | lbo);
+                const uint32_t bg = b16 + g * bstep16;
+                umma_bf16(tacc + norm.k0.dcol, adesc, kBDescHi | static_cast<uint64_t>((bg + norm.k0.brow) | b_lbo),
+                          norm.k0.idesc, 1u);
+                if (norm.nb > 1)
+                    umma_bf16(tacc + norm.k1.dcol, adesc, kBDescHi | static_cast<uint64_t>((bg + norm.k1.brow) | b_lbo),
+                              norm.k1.idesc, 1u);
+                if (norm.nb > 2)
+                    umma_bf16(tacc + norm.k2.dcol, adesc, kBDescHi | static_cast<uint64_t>((bg + norm.k2.brow) | b_lbo),
+                              norm.k2.idesc, 1u);
+            }
+        }
+        umma_commit(&empty_a[s]);
     }
 }
 
@@ -418,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     constexpr uint32_t kTmemCols = kSets == 2 ? 512 : 256;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                               // na x 5760
-    uint8_t* sB = smem + p.na * kAStageBytes;         // nbuf x bbuf_bytes
+    uint8_t* sB = smem + p.na * p.stage_bytes;        // nbuf x bbuf_bytes
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nbuf * p.bbuf_bytes);
     uint64_t* full_a = bars;                 // [kMaxA]
     uint64_t* empty_a = bars + kMaxA;        // [kMaxA]
@@ -429,7 +470,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     // 16-byte aligned tables; offsets are computed on the byte OFFSET (smem is 1024-byte aligned) so that the
     // pointers keep their shared-memory address space (LDS, not generic loads)
-    const uint32_t bars_off = static_cast<uint32_t>(p.na * kAStageBytes + p.nbuf * p.bbuf_bytes);
+    const uint32_t bars_off = static_cast<uint32_t>(p.na * p.stage_bytes + p.nbuf * p.bbuf_bytes);
     const uint32_t tab_off = (bars_off + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 8 + 15u) & ~15u;
     PlaneTab* plane_tab = reinterpret_cast<PlaneTab*>(smem + tab_off);                  // kMaxZin entries
     // epilogue parameters, per 8-channel chunk: 8 scales, 8 shifts, 8 slopes (float4 reads)
@@ -516,7 +557,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         cc = n * p.c8_total + p.chunk_base + 2 * g;
         zstep = 1;
         map = &maps.m[lone ? 1 : 0];
-        if (p.mode == B200SEG_TC_K3 || p.mode == B200SEG_TC_K3T) {
+        if (p.mode == B200SEG_TC_K3T) {
+            zc = z0 - 1;
+            bytes = static_cast<uint32_t>(p.cin_chunks) * kChunkBytes;   // one box with every chunk of the plane
+            map = &maps.m[2];
+        } else if (p.mode == B200SEG_TC_K3) {
             zc = z0 - 1;
         } else if (p.mode == B200SEG_TC_UP) {
             zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
@@ -541,7 +586,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (warp == 0) {
         // =============================================================== A producer (ring 0)
         if (elect_one()) {
-            const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : 2;
+            const int nmap = p.mode == B200SEG_TC_DOWN ? 8 : (p.mode == B200SEG_TC_K3T ? 3 : 2);
             for (int i = 0; i < nmap; ++i) prefetch_tmap(&maps.m[i]);
             uint32_t s = 0, ph = 0;
             for (int q = 0; q < n_seq; q += dual ? 2 : 1) {
@@ -554,7 +599,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     image_loads(tile, bi, x0, y0, zc, zstep, cc, bytes, map);
                     for (int j = 0; j < n_img_planes; ++j, zc += zstep) {
                         mbar_wait(&empty_a[s], ph ^ 1);
-                        issue_a(sA + s * kAStageBytes, map, &full_a[s], bytes, x0, y0, zc, cc);
+                        issue_a(sA + s * p.stage_bytes, map, &full_a[s], bytes, x0, y0, zc, cc);
                         if (++s == static_cast<uint32_t>(ring_n)) {
                             s = 0;
                             ph ^= 1;
@@ -589,7 +634,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 uint32_t b_s = 0, b_ph = 0;
                 uint64_t* const full_r = full_a + ring_n;
                 uint64_t* const empty_r = empty_a + ring_n;
-                uint8_t* const sA_r = sA + ring_n * kAStageBytes;
+                uint8_t* const sA_r = sA + ring_n * p.stage_bytes;
                 uint32_t s = 0, ph = 0;
                 int q = 1, bi = 0, j = 0, tile = 0, pass = 0;
                 int x0 = 0, y0 = 0, zc = 0, zstep = 1, cc = 0;
@@ -623,7 +668,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         progress = true;
                     }
                     if (!a_done && mbar_test(&empty_r[s], ph ^ 1)) {
-                        issue_a(sA_r + s * kAStageBytes, map, &full_r[s], bytes, x0, y0, zc, cc);
+                        issue_a(sA_r + s * p.stage_bytes, map, &full_r[s], bytes, x0, y0, zc, cc);
                         if (++s == static_cast<uint32_t>(ring_n)) {
                             s = 0;
                             ph ^= 1;
@@ -654,7 +699,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;
             uint64_t* const full_r = full_a + r * ring_n;
             uint64_t* const empty_r = empty_a + r * ring_n;
-            const uint32_t sA16 = smem_u32(sA + r * ring_n * kAStageBytes) >> 4, sB16 = smem_u32(sB) >> 4;
+            const uint32_t sA16 = smem_u32(sA + r * ring_n * p.stage_bytes) >> 4, sB16 = smem_u32(sB) >> 4;
+            const uint32_t stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4;
             const uint32_t bbuf16 = static_cast<uint32_t>(p.bbuf_bytes) >> 4;
             const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
             const uint32_t bstep16 = 2 * p.NB;                          // one step of a B image, in 16-byte units
@@ -683,7 +729,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     const uint32_t tacc = tmem + set * 256;
                     int g = 0, gq = 0;   // bi = gq * G + g
                     for (int bi = 0; bi < n_bimg; ++bi) {
-                        const bool lone = lone_last && g == G - 1;
+                        const bool lone = lone_last && g == G - 1 && mode != B200SEG_TC_K3T;
                         int zi0 = 0, zstep = 1, pp = 0;
                         if (mode == B200SEG_TC_DOWN) {
                             zi0 = gq >> 2;
@@ -696,7 +742,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             g = 0;
                             ++gq;
                         }
-                        const int kind = (mode == B200SEG_TC_K3 ? 0 : (mode == B200SEG_TC_K3T ? 4 : 2)) + (lone ? 1 : 0);
+                        const int kind = mode == B200SEG_TC_K3T ? 4 : (mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
                         const uint32_t pbase = parity_base(mode, pp);
                         const uint32_t bs = b_s;
                         mbar_wait(&full_b[bs], resident ? 0u : b_ph);   // resident images complete phase 0 once
@@ -711,27 +757,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         switch (kind) {
                             case kK3Full:
                                 run_image<kK3Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
                                 break;
                             case kK3Lone:
                                 run_image<kK3Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
                                 break;
                             case kS2Full:
                                 run_image<kS2Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
                                 break;
                             case kS2Lone:
                                 run_image<kS2Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc);
-                                break;
-                            case kT1Full:
-                                run_image<kT1Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
                                 break;
                             default:
-                                run_image<kT1Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc);
+                                run_image_t(G, lone_last, n_img_planes, pt, full_r, empty_r, a_s, a_ph, na, sA16, b16, b_lbo,
+                                            bstep16, tacc, stage16);
                                 break;
                         }
                         if (!resident) umma_commit(&empty_b[bs]);
@@ -1120,17 +1162,19 @@ static int tc_geometry(int mode, int cin_chunks, int cout, TcGeom* g) {
     B200SEG_CHECK_ARG(mode >= 0 && mode <= 3, "conv3d_tc: bad mode %d", mode);
     B200SEG_CHECK_ARG(cout >= 1 && cout <= 80, "conv3d_tc: cout %d not in [1,80] (split wider layers)", cout);
     B200SEG_CHECK_ARG(mode != B200SEG_TC_K3T || cout <= 4, "conv3d_tc K3T: cout %d not in [1,4]", cout);
+    B200SEG_CHECK_ARG(mode != B200SEG_TC_K3T || cin_chunks <= 12, "conv3d_tc K3T: at most 96 input channels");
     B200SEG_CHECK_ARG(cin_chunks >= 1, "conv3d_tc: no input chunks");
     // K3T: the 9 in-plane taps are columns of the accumulator (9 * cout per plane), summed in the epilogue
     g->Cpad = mode == B200SEG_TC_K3T ? (9 * cout + 7) / 8 * 8 : (cout + 7) / 8 * 8;
     g->blocks = (mode == B200SEG_TC_K3 || mode == B200SEG_TC_K3T) ? 3 : (mode == B200SEG_TC_DOWN ? 2 : 4);
     g->NB = g->blocks * g->Cpad + 16;
-    g->steps_full = mode == B200SEG_TC_K3 ? 9 : (mode == B200SEG_TC_K3T ? 1 : 4);
-    g->steps_lone = mode == B200SEG_TC_K3 ? 5 : (mode == B200SEG_TC_K3T ? 1 : 2);
     g->G = (cin_chunks + 1) / 2;
+    // K3T: ONE image per unit whose steps are the chunk groups
+    g->steps_full = mode == B200SEG_TC_K3 ? 9 : (mode == B200SEG_TC_K3T ? g->G : 4);
+    g->steps_lone = mode == B200SEG_TC_K3 ? 5 : (mode == B200SEG_TC_K3T ? g->G : 2);
     g->lone_last = cin_chunks & 1;
     g->n_pass = mode == B200SEG_TC_UP ? 4 : 1;
-    g->n_bimg = mode == B200SEG_TC_DOWN ? 8 * g->G : g->G;
+    g->n_bimg = mode == B200SEG_TC_DOWN ? 8 * g->G : (mode == B200SEG_TC_K3T ? 1 : g->G);
     g->bimg_stride = g->steps_full * 2 * g->NB * 16;
     g->TZmax = (256 - 16) / g->Cpad;   // one accumulator set = 256 TMEM columns
     if (g->TZmax > 12) g->TZmax = 12;
@@ -1292,6 +1336,11 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
             rc = encode_map(&maps.m[one], 4, in.data, dims, strides, box);
             if (rc) return rc;
         }
+        if (mode == B200SEG_TC_K3T) {   // one box with every chunk of the plane
+            cuuint32_t box[4] = {kHX * 8, kHY, 1, static_cast<cuuint32_t>(cin_chunks)};
+            rc = encode_map(&maps.m[2], 4, in.data, dims, strides, box);
+            if (rc) return rc;
+        }
     } else {
         cuuint64_t dims[5] = {8, X / 2, Y / 2, Z, NC};
         cuuint64_t strides[4] = {32, 2 * X * 16, Y * X * 16, Z * Y * X * 16};
@@ -1311,16 +1360,19 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
                         3 * static_cast<size_t>(g.Cpad) * 4 + 256 +
                         (mode == B200SEG_TC_K3T ? 2 * 128 * static_cast<size_t>(p.tpitch) * 4 : 0);
     const size_t budget = variant == 2 ? 224 * 1024 : 112 * 1024;
+    p.cin_chunks = cin_chunks;
+    p.stage_bytes = mode == B200SEG_TC_K3T ? g.G * kAStageBytes : kAStageBytes;
+    const size_t stage = static_cast<size_t>(p.stage_bytes);
     // weights stay resident (one slot per image, loaded once per CTA) when the whole packed operand fits next to
     // at least 8 A stages; otherwise the images stream through a ring (double-buffered when possible)
     const int n_images = g.n_pass * g.n_bimg;
     p.resident = (n_images <= kMaxB &&
-                  misc + static_cast<size_t>(n_images) * p.bbuf_bytes + 8 * kAStageBytes <= budget) ? 1 : 0;
+                  misc + static_cast<size_t>(n_images) * p.bbuf_bytes + 8 * stage <= budget) ? 1 : 0;
     p.nbuf = p.resident ? n_images
-                        : ((misc + 2 * static_cast<size_t>(p.bbuf_bytes) + 4 * kAStageBytes <= budget) ? 2 : 1);
-    B200SEG_CHECK_ARG(misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + 3 * kAStageBytes <= budget,
+                        : ((misc + 2 * static_cast<size_t>(p.bbuf_bytes) + 4 * stage <= budget) ? 2 : 1);
+    B200SEG_CHECK_ARG(misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + 3 * stage <= budget,
                       "conv3d_tc: weight image of %d bytes does not fit shared memory", p.bbuf_bytes);
-    long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / kAStageBytes);
+    long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / stage);
     if (na > kMaxA) na = kMaxA;
     p.na = static_cast<int>(na);
     // two MMA issuers (one per accumulator set, half of the A ring each) when every CTA has at least two tiles
@@ -1339,7 +1391,7 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
                          : issuers == 3 ? true
                                         : (mode != B200SEG_TC_UP || p.resident || g.Cpad >= 80);
     p.dual = (dual_ok && dual_rule) ? 1 : 0;
-    const size_t smem = misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * kAStageBytes;
+    const size_t smem = misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * stage;
     // ---- launch (persistent)
     const long long n_tiles = 1LL * p.tiles_x * p.tiles_y * p.tiles_z * in.n;
     const long long max_ctas = 1LL * sms * (variant == 2 ? 1 : 2);

@@ -144,7 +144,7 @@ class CompiledPlan:
         for lo, hi, d0, d1, split, res in pieces:
             call = self._new_call(op, True, geom)
             phys = _plan.physical_weight(op.weight, op.mode == UP, op.segments, n_chunks, lo, hi)
-            if op.final and op.mode == K3 and hi - lo <= _plan.K3T_MAX_COUT and not _NO_K3T:
+            if op.final and op.mode == K3 and hi - lo <= _plan.K3T_MAX_COUT and n_chunks <= 12 and not _NO_K3T:
                 call.mode = _plan.K3T      # tiny-Cout final layer: taps as accumulator columns (see conv_tc.cu)
             call.weight = _plan.pack_tc_weight(call.mode, phys, n_chunks, hi - lo).to(self.device)
             call.cout = hi - lo

@@ -516,20 +516,19 @@ def tc_geometry(mode: int, cin_chunks: int, cout: int) -> dict:
     cpad = c8(9 * cout if mode == K3T else cout) * 8
     blocks = {K3: 3, DOWN: 2, UP: 4, K3T: 3}[mode]
     nb = blocks * cpad + 16
-    steps_full = {K3: 9, K3T: 1}.get(mode, 4)
-    steps_lone = {K3: 5, K3T: 1}.get(mode, 2)
     groups = (cin_chunks + 1) // 2
+    # K3T: ONE image whose steps are the chunk groups (one MMA each; the whole plane is one shared-memory stage)
+    steps_full = {K3: 9, K3T: groups}.get(mode, 4)
+    steps_lone = {K3: 5, K3T: groups}.get(mode, 2)
+    n_bimg = {DOWN: 8 * groups, K3T: 1}.get(mode, groups)
     return dict(cpad=cpad, blocks=blocks, nb=nb, steps_full=steps_full, steps_lone=steps_lone, groups=groups,
                 lone_last=cin_chunks % 2, n_pass=4 if mode == UP else 1,
-                n_bimg=8 * groups if mode == DOWN else groups, bimg_elems=steps_full * 2 * nb * 8)
+                n_bimg=n_bimg, bimg_elems=steps_full * 2 * nb * 8)
 
 
 def step_units(mode: int, lone: bool, pp: int, st: int):
     """The two K-halves of MMA step ``st``: each is (sy, sx, chunk_in_group) or None (zero weights).
     (sy, sx) is the halo offset the A operand starts at -- must agree with step_desc() in csrc/conv_tc.cu."""
-    if mode == K3T:
-        # one step, A rows are the halo voxels themselves (offset 0); a lone chunk is paired with zero weights
-        return [(0, 0, 0), None] if lone else [(0, 0, 0), (0, 0, 1)]
     if mode == K3:
         if not lone:
             return [(st // 3, st % 3, 0), (st // 3, st % 3, 1)]
@@ -572,6 +571,20 @@ def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) ->
     g = tc_geometry(mode, cin_chunks, cout)
     cpad, nb = g["cpad"], g["nb"]
     img = torch.zeros((g["n_pass"], g["n_bimg"], g["steps_full"], 2, nb, 8), dtype=torch.float32)
+    if mode == K3T:
+        # step = chunk group; K halves = the two chunks of the group (a lone chunk pairs with zero weights);
+        # rows of block j: column (dy*3+dx)*cout + co = weight of tap (2-j, dy, dx), output channel co
+        for grp in range(g["groups"]):
+            for half in range(2):
+                chunk = 2 * grp + half
+                if chunk >= cin_chunks:
+                    continue
+                for j in range(3):
+                    for dy in range(3):
+                        for dx in range(3):
+                            r0 = j * cpad + (dy * 3 + dx) * cout
+                            img[0, 0, grp, half, r0:r0 + cout, :] = phys[2 - j, dy, dx, chunk * 8:(chunk + 1) * 8, :cout].t()
+        return img.to(torch.bfloat16).contiguous()
     for ps in range(g["n_pass"]):
         for bi in range(g["n_bimg"]):
             grp = bi % g["groups"]
@@ -588,16 +601,6 @@ def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) ->
                         continue
                     sy, sx, ck = unit
                     chunk = 2 * grp + ck
-                    if mode == K3T:
-                        # rows of block j: column (dy*3+dx)*cout + co = weight of tap (2-j, dy, dx), channel co
-                        for j in range(g["blocks"]):
-                            tz = block_tz(mode, j, zpar)
-                            for dy in range(3):
-                                for dx in range(3):
-                                    r0 = j * cpad + (dy * 3 + dx) * cout
-                                    img[ps, bi, st, half, r0:r0 + cout, :] = \
-                                        phys[tz, dy, dx, chunk * 8:(chunk + 1) * 8, :cout].t()
-                        continue
                     ty, tx = tap_of(mode, pp, sy, sx)
                     for j in range(g["blocks"]):
                         tz = block_tz(mode, j, zpar)

@@ -24,8 +24,6 @@ def pad16(n):
 
 def step_desc(mode, lone, pp, st):
     """(byte offset, LBO bytes) -- transcription of Steps<KIND>::delta() in conv_tc.cu."""
-    if mode == K3T:
-        return 0, (16 if lone else CHUNK_BYTES)
     if mode == K3:
         if not lone:
             return ((st // 3) * HX + (st % 3)) * 16, CHUNK_BYTES
@@ -71,11 +69,11 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
     cpad = ((9 * cout if mode == K3T else cout) + 7) // 8 * 8
     blocks = {K3: 3, DOWN: 2, UP: 4, K3T: 3}[mode]
     NB = blocks * cpad + 16
-    steps_full, steps_lone = {K3: (9, 5), K3T: (1, 1)}.get(mode, (4, 2))
     G = (C8 + 1) // 2
+    steps_full, steps_lone = {K3: (9, 5), K3T: (G, G)}.get(mode, (4, 2))
     lone_last = C8 % 2
     n_pass = 4 if mode == UP else 1
-    n_bimg = 8 * G if mode == DOWN else G
+    n_bimg = {DOWN: 8 * G, K3T: 1}.get(mode, G)
     assert wpacked.shape == (n_pass, n_bimg, steps_full, 2, NB, 8), wpacked.shape
     if mode in (K3, K3T):
         oz, oy, ox = Z, Y, X
@@ -109,7 +107,7 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
 
     def load_box(n, chunk, nch, cx, cy, cz, pp):
         """TMA box load -> flat stage array (elements); bytes not written stay NaN."""
-        stage = np.full(STAGE_BYTES // 2, np.nan)
+        stage = np.full(max(STAGE_BYTES, nch * CHUNK_BYTES) // 2, np.nan)
         box = np.zeros((nch, HY, HX, 8))
         for c in range(nch):
             for yy in range(HY):
@@ -135,7 +133,7 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
                     for ps in range(n_pass):
                         for bi in range(n_bimg):
                             g = bi % G
-                            lone = bool(lone_last) and g == G - 1
+                            lone = bool(lone_last) and g == G - 1 and mode != K3T
                             nsteps = steps_lone if lone else steps_full
                             bimg = np.full(steps_full * 2 * NB * 8, np.nan)
                             bimg[: nsteps * 2 * NB * 8] = wpacked[ps, bi, :nsteps].reshape(-1)
@@ -146,7 +144,9 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
                                 pp = ps
                             for zi in range(zi_start, zin, zi_step):
                                 nch = 1 if lone else 2
-                                if mode in (K3, K3T):
+                                if mode == K3T:      # one box with every chunk of the plane
+                                    stage = load_box(n, 0, C8, x0 - 1, y0 - 1, z0 - 1 + zi, 0)
+                                elif mode == K3:
                                     stage = load_box(n, 2 * g, nch, x0 - 1, y0 - 1, z0 - 1 + zi, 0)
                                 elif mode == UP:
                                     stage = load_box(n, 2 * g, nch, x0 - 1, y0 - 1, z0 // 2 - 1 + zi, 0)
@@ -154,7 +154,11 @@ def emulate_conv_tc(mode, x_blocked, wpacked, cout, TZ=None):
                                     stage = load_box(n, 2 * g, nch, x0 - 1, y0 - 1, 2 * z0 - 1 + zi, pp)
                                 lo, hi, jlo, ft = plane_window(mode, TZ, zi)
                                 for st in range(nsteps):
-                                    a_off, a_lbo = step_desc(mode, lone, pp, st)
+                                    if mode == K3T:   # step = chunk group st; the last one may be a lone chunk
+                                        a_off = st * STAGE_BYTES
+                                        a_lbo = 16 if (lone_last and st == G - 1) else CHUNK_BYTES
+                                    else:
+                                        a_off, a_lbo = step_desc(mode, lone, pp, st)
                                     A = _operand(stage, a_off, 128, a_lbo, HX * 16)
                                     b_step = st * (2 * NB * 16)
                                     split = min(max(ft, lo), hi + 1) if (bi == 0 and st == 0) else hi + 1
