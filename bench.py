@@ -317,7 +317,7 @@ def run_gpu_arm(args) -> None:
                      "frac": achieved_tf / peak_tf,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (up_blocks.0 conv0||res_conv,
                      # 48 patches) from the committed ncu --set full capture profiles/r01_ncu_full_up0_conv0res_b48_raw.csv
-                     "traffic": 16.659e9,
+                     "traffic": 14.721e9,
                      "traffic_note": "bytes per launch of the dominant conv layer (80->80 ch, 48 x 96^3); algorithmic "
                                      "bytes of that launch are 13.59e9 (activations in + out once)",
                      "kernel": "conv_tc_kernel",
