@@ -209,7 +209,11 @@ def run_gpu_arm(args) -> None:
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200SEG_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) to stdout
+        # unless it is given a file
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200SEG_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl.%h.%p.log")
+                              if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else os.devnull)
         dist.init_process_group("nccl", device_id=device)
 
     import b200seg

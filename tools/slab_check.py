@@ -22,6 +22,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
     dist.init_process_group("nccl", device_id=device)
     set_precision("bf16")
     model = bench.build_model().to(device)
