@@ -242,6 +242,14 @@ TC_CASES = [
     (2, 16, 16, (1, 3, 5, 9)),
     (2, 40, 40, (2, 7, 17, 11)),
     (2, 80, 80, (1, 4, 6, 6)),
+    # >= 2 tiles per SM: the dual-issuer schedule (two A rings, shared weight ring, ghost rounds for CTAs with an odd
+    # tile count), ragged extents
+    (0, 40, 40, (3, 29, 50, 44)),     # resident weights, 5-chunk epilogue with residual
+    (0, 80, 80, (2, 22, 50, 44)),     # streamed weights released by both issuers, 10-chunk epilogue
+    (0, 24, 16, (5, 40, 36, 28)),     # generic epilogue under the dual schedule
+    (1, 40, 40, (3, 44, 68, 60)),     # stride-2 conv, 24 streamed images per unit
+    (2, 80, 80, (4, 15, 34, 30)),     # transposed conv (4 passes per tile pair)
+    (2, 40, 40, (4, 15, 34, 30)),     # transposed conv on the single-issuer schedule (default rule)
 ]
 
 
