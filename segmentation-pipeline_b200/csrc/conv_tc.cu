@@ -19,15 +19,22 @@
 //     multiple of 16 multiplies zeros ("spill" columns add 0 to the next plane's accumulator).
 //   * accumulators: TZ planes x Cpad fp32 columns in TMEM; first touch of a plane uses accumulate=0.
 //
+//   * K3T (final layer, Cout <= 4): the nine in-plane taps are accumulator COLUMNS instead of MMA steps -- one
+//     unshifted MMA per chunk group, the epilogue sums each voxel's nine neighbours through shared memory; tiles
+//     own the 14 x 6 interior of the 16 x 8 voxels they compute (see run_image_t and the K3T epilogue).
+//
 // Execution: persistent CTAs loop over work units (tile x pass).
 //   warp 0  A producer : ring of halo planes (TMA box loads), in consumption order
-//   warp 2  B producer : ring of weight images (one bulk copy per chunk group)
+//   warp 2  B producer : weight images, resident (loaded once) or a ring of bulk copies; in dual mode it also
+//                        feeds the second A ring and therefore only polls its barriers
 //   warp 1  MMA issuer : per plane, the steps of the image are issued from an UNROLLED loop whose descriptor
-//                        deltas are compile-time constants, so one MMA costs a couple of uniform adds
+//   (warp 3)             deltas are compile-time constants, so one MMA costs a couple of uniform adds.  Dual mode:
+//                        warps 1 and 3 each own one accumulator set, half of the A ring and every other unit
 //   epilogue warps     : TMEM -> registers -> folded BN / bias, activation, residual, bf16 store
-//                        (or softmax -> fp32 NCDHW for the last layer)
-// kSets == 1: two CTAs per SM, one accumulator set each (the CTAs overlap each other's epilogue);
-// kSets == 2: one CTA per SM, two accumulator sets (epilogue of unit u overlaps the MMAs of unit u+1).
+//                        (or softmax -> fp32 NCDHW for the last layer); kEpi != 0 are compile-time
+//                        specialisations for 10 / 5 chunks with / without residual
+// kSets == 1: two CTAs per SM, one accumulator set each (the CTAs overlap each other's epilogue); test variant.
+// kSets == 2: one CTA per SM, two accumulator sets (epilogue of unit u overlaps the MMAs of unit u+1); default.
 #include <cstdlib>
 #include <cstring>
 
