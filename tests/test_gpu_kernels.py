@@ -100,11 +100,16 @@ def test_softmax_and_stochastic_matrix(lib):
 
 
 # ----------------------------------------------------------------------------------------------- grid
-@pytest.mark.parametrize("padding_mode,overlap", [(None, (4, 2, 2)), ("edge", (4, 2, 2)), (0.5, (4, 4, 0))])
-def test_grid_extract_bit_exact(lib, padding_mode, overlap):
+@pytest.mark.parametrize("padding_mode,overlap,size,patch", [
+    (None, (4, 2, 2), (20, 17, 13), (8, 8, 6)), ("edge", (4, 2, 2), (20, 17, 13), (8, 8, 6)),
+    (0.5, (4, 4, 0), (20, 17, 13), (8, 8, 6)),
+    # patch depth multiple of 4: the 4-wide kernel, with unaligned rows (D = 13) and with aligned ones (D = 32)
+    ("edge", (4, 2, 2), (20, 17, 13), (8, 8, 8)), (0.5, (4, 2, 4), (20, 17, 13), (8, 8, 8)),
+    ("edge", (4, 4, 8), (24, 16, 32), (8, 8, 16)), (None, (4, 4, 8), (24, 16, 32), (8, 8, 16)),
+])
+def test_grid_extract_bit_exact(lib, padding_mode, overlap, size, patch):
     rng = np.random.default_rng(3)
-    vol = rng.standard_normal((3, 20, 17, 13)).astype(np.float32)
-    patch = (8, 8, 6)
+    vol = rng.standard_normal((3, *size)).astype(np.float32)
     padded = ogrid.pad_volume(vol, overlap, padding_mode)
     loc = ogrid.grid_locations(padded.shape[1:], patch, overlap)
     ref = ogrid.extract_patches(padded, loc)
