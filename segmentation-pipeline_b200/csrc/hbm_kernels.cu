@@ -445,13 +445,11 @@ confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long lo
     constexpr int PER = 16 / sizeof(L);  // labels per 16-byte load
     const long long nvec = voxels / PER;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long v = blockIdx.x * 1LL * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        uint4 pr = __ldg(reinterpret_cast<const uint4*>(pred) + v);
-        uint4 tr = __ldg(reinterpret_cast<const uint4*>(targ) + v);
+    // one 16-byte vector of each label map: run-length accumulation -- label maps are piecewise constant, so
+    // consecutive voxels mostly hit the same bin and one shared-memory update covers the whole run
+    auto count_vec = [&](const uint4& pr, const uint4& tr) {
         const L* pp = reinterpret_cast<const L*>(&pr);
         const L* tp = reinterpret_cast<const L*>(&tr);
-        // run-length accumulation: label maps are piecewise constant, so consecutive voxels mostly hit the same bin
-        // and one shared-memory update covers the whole run
         int cur = -1;
         unsigned int run = 0;
 #pragma unroll
@@ -473,7 +471,23 @@ confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long lo
             if (shared_cols) atomicAdd(mine + cur * 32, run);
             else mine[cur * 32] += run;
         }
+    };
+    // four vector pairs (128 bytes) in flight per thread: the histogram needs so much shared memory that only 16
+    // warps fit on an SM, so the loads of several iterations have to overlap to cover the HBM latency
+    const uint4* pv = reinterpret_cast<const uint4*>(pred);
+    const uint4* tv = reinterpret_cast<const uint4*>(targ);
+    long long v = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < nvec; v += 4 * stride) {
+        uint4 pr[4], tr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            pr[u] = __ldg(pv + v + u * stride);
+            tr[u] = __ldg(tv + v + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) count_vec(pr[u], tr[u]);
     }
+    for (; v < nvec; v += stride) count_vec(__ldg(pv + v), __ldg(tv + v));
     // tail (voxels not a multiple of PER): first thread of the grid
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (long long v = nvec * PER; v < voxels; ++v) {
