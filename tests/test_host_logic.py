@@ -151,3 +151,14 @@ def test_c_abi_exports_every_declared_symbol():
     # argument validation happens before any CUDA call
     assert lib.b200seg_conv3d_tc_wbytes(0, 5, 200) == -1
     assert b"cout" in lib.b200seg_last_error()
+    # the engine-mode enum of the header, the Python packer and the C geometry agree (incl. the K3T final-layer mode)
+    from segmentation_pipeline.models import _plan
+    enum = re.search(r"enum \{ (B200SEG_TC_K3 = 0.*?) \};", header).group(1)
+    values = dict((k.strip(), int(v)) for k, v in (item.split("=") for item in enum.split(",")))
+    assert values == {"B200SEG_TC_K3": _plan.K3, "B200SEG_TC_DOWN": _plan.DOWN, "B200SEG_TC_UP": _plan.UP,
+                      "B200SEG_TC_K3T": _plan.K3T}
+    for mode, chunks, cout in [(_plan.K3, 5, 40), (_plan.DOWN, 5, 40), (_plan.UP, 10, 80), (_plan.K3T, 5, 2),
+                               (_plan.K3T, 1, 4)]:
+        g = _plan.tc_geometry(mode, chunks, cout)
+        assert lib.b200seg_conv3d_tc_wbytes(mode, chunks, cout) == g["n_pass"] * g["n_bimg"] * g["bimg_elems"] * 2
+    assert lib.b200seg_conv3d_tc_wbytes(_plan.K3T, 5, 5) == -1       # K3T serves at most 4 output channels
