@@ -456,8 +456,8 @@ __device__ __forceinline__ void epi_planes(const EpiArgs& a, int cbeg, int q0, i
     }
 }
 
-// kEpi selects the epilogue: 0 = any chunk count (run-time item cursor); 1 / 2 = 10 chunks without / with residual;
-// 3 / 4 = 5 chunks without / with residual.
+// kEpi selects the epilogue: 0 = any chunk count (run-time item cursor) and the plain final layer; 1 / 2 = 10 chunks
+// without / with residual; 3 / 4 = 5 chunks without / with residual; 5 = K3T final layer.
 template <int kSets, int kEpi>
 __global__ void __launch_bounds__(kSets == 2 ? 384 : 224, kSets == 2 ? 1 : 2)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
@@ -844,7 +844,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 mbar_wait(&acc_full[set], (kSets == 2 ? (unit >> 1) : unit) & 1);
                 tc_fence_after();
                 const uint32_t tbase = tmem + set * 256 + (static_cast<uint32_t>(lg * 32) << 16);
-                if (kEpi == 0 && p.mode == B200SEG_TC_K3T) {
+                if (kEpi == 5) {
                     // Final layer with tiny Cout: accumulator row m holds, for halo voxel m of the tile, the products of
                     // all nine in-plane taps (column (dy*3+dx)*cout + co).  The rows go through shared memory; every
                     // interior voxel sums the nine columns of its nine neighbours, then bias / softmax / fp32 store.
@@ -956,7 +956,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         if (half == 0) named_bar_sync<1>(128); else named_bar_sync<2>(128);
                     }
                 } else if (kEpi != 0 || e.out_ncdhw == nullptr) {
-                    if constexpr (kEpi != 0) {
+                    if constexpr (kEpi != 0 && kEpi != 5) {
                         // specialised epilogues: 10 chunks (the two warps of a lane quarter take 5 chunks each of
                         // every plane) or 5 chunks (they take alternate planes), with or without a residual
                         constexpr bool kRes = kEpi == 2 || kEpi == 4;
@@ -1412,13 +1412,15 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     if (variant == 2) {
         const bool res = de.residual.data != nullptr;
         const int c8 = p.Cpad / 8;
-        if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<2, 0>;
+        if (mode == B200SEG_TC_K3T) kernel = conv_tc_kernel<2, 5>;
+        else if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<2, 0>;
         else if (c8 == 10) kernel = res ? conv_tc_kernel<2, 2> : conv_tc_kernel<2, 1>;
         else kernel = res ? conv_tc_kernel<2, 4> : conv_tc_kernel<2, 3>;
     } else {
         const bool res = de.residual.data != nullptr;
         const int c8 = p.Cpad / 8;
-        if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<1, 0>;
+        if (mode == B200SEG_TC_K3T) kernel = conv_tc_kernel<1, 5>;
+        else if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<1, 0>;
         else if (c8 == 10) kernel = res ? conv_tc_kernel<1, 2> : conv_tc_kernel<1, 1>;
         else kernel = res ? conv_tc_kernel<1, 4> : conv_tc_kernel<1, 3>;
     }
