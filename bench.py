@@ -316,6 +316,8 @@ def run_gpu_arm(args) -> None:
                 "d2h_bytes_per_step": vol_bytes, "ms_per_step": e2e_ms,
                 "api": "PatchPredict.predict(model, device, [subject]) with a pinned host volume; returns host probabilities"},
         "gpu_launches": gpu_launches,
+        # SURVEY.md section 8(d) also asks for patch-voxels per second (network throughput incl. the 8x overlap)
+        "patch_mvoxel_per_s": world * N_PATCHES * PATCH ** 3 / (ms_per_step * 1e-3) / 1e6,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf,
