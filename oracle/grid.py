@@ -15,10 +15,14 @@ this image.  The reference pins it as ``torchio==0.18.45``
 ``torchio/data/sampler/grid.py`` (``GridSampler._pad / _parse_sizes / _get_patches_locations / __getitem__``)
 and ``torchio/data/inference/aggregator.py`` (``GridAggregator.add_batch / crop_batch / get_output_tensor``).
 
-PARITY UNPINNED: the reference repository holds no test, golden vector or fixture for this path (SURVEY.md
-section 8c) and the torchio wheel cannot be imported here, so this restatement is checked only against the
-structural properties the algorithm guarantees (tests/test_oracle_grid.py) and against the worked example in
-torchio's own source comment (image 10, patch 5, overlap 2 -> starts 0, 3, 5).
+PINNED (as far as this image allows): the reference repository holds no test or fixture for this path (SURVEY.md
+section 8c) and the torchio wheel cannot be imported here, so the restatement is pinned to
+``tests/golden/grid_torchio.json`` (written by ``oracle/make_grid_golden.py``): torchio's OWN unit-test fixtures for
+``GridSampler`` locations and ``GridAggregator`` crop / average (restated from its test-suite and re-derived by hand in
+that script) plus brute-force per-voxel cases that share no code with this module, including the centre-crop quirk of
+``crop_batch``.  ``tests/test_oracle_grid.py`` checks this module against them; ``tests/test_gpu_kernels.py`` checks
+the CUDA path against them and, when the box has torchio, against ``tio.GridSampler`` / ``tio.GridAggregator``
+themselves.  What remains unpinned: a byte-for-byte run of torchio 0.18.45 in this image.
 """
 from __future__ import annotations
 

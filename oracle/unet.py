@@ -24,6 +24,30 @@ import torch.nn.functional as F
 SD = Dict[str, torch.Tensor]
 BN_EPS = 1e-5
 
+# ---------------------------------------------------------------------------------------------- bf16 emulation
+# The CUDA throughput path keeps activations and weights in bf16 (fp32 accumulation, fp32 epilogue).  To predict
+# on the CPU what that does to labels, ``emulate_bf16()`` rounds exactly the tensors the kernels store in bf16:
+# conv inputs / weights and every block-level activation that goes to HBM.  Outside the context ``_q`` is the
+# identity and the oracle is the plain fp32 restatement.
+_QUANT = [None]
+
+
+def _q(t: torch.Tensor) -> torch.Tensor:
+    return t if _QUANT[0] is None else _QUANT[0](t)
+
+
+class emulate_bf16:
+    """Context manager: round-to-nearest-even bf16 storage of activations and weights (fp32 arithmetic)."""
+
+    def __enter__(self):
+        self._prev = _QUANT[0]
+        _QUANT[0] = lambda t: t.to(torch.bfloat16).to(torch.float32)
+        return self
+
+    def __exit__(self, *exc):
+        _QUANT[0] = self._prev
+        return False
+
 
 # --------------------------------------------------------------------------------------------- components
 def _standardize(weight: torch.Tensor) -> torch.Tensor:
@@ -34,7 +58,7 @@ def _standardize(weight: torch.Tensor) -> torch.Tensor:
 
 def ws_conv3d(x, weight, **kwargs):
     """models/components.py:81-88 -- note the reference never passes ``self.bias`` (bias unused)."""
-    return F.conv3d(x, _standardize(weight), **kwargs)
+    return F.conv3d(_q(x), _q(_standardize(weight)), **kwargs)
 
 
 def blur_weight(weight: torch.Tensor, kernel: torch.Tensor, in_channels: int) -> torch.Tensor:
@@ -50,7 +74,7 @@ def blur_conv3d(x, weight, kernel, in_channels, weight_standardization=False, **
     The bias parameter exists in the state_dict but is never applied (:119)."""
     if weight_standardization:
         weight = _standardize(weight)
-    return F.conv3d(x, blur_weight(weight, kernel, in_channels), **kwargs)
+    return _q(F.conv3d(_q(x), _q(blur_weight(weight, kernel, in_channels)), **kwargs))
 
 
 def blur_conv_transpose3d(x, weight, kernel, in_channels, weight_standardization=False, **kwargs):
@@ -59,7 +83,7 @@ def blur_conv_transpose3d(x, weight, kernel, in_channels, weight_standardization
     stride 2 (:136-141) -- a quirk that is part of the contract."""
     if weight_standardization:
         weight = _standardize(weight)
-    return F.conv_transpose3d(x, blur_weight(weight, kernel, in_channels), **kwargs)
+    return _q(F.conv_transpose3d(_q(x), _q(blur_weight(weight, kernel, in_channels)), **kwargs))
 
 
 def batch_norm_eval(x, sd: SD, prefix: str, eps: float = BN_EPS):
@@ -94,20 +118,24 @@ def block3d(x, sd: SD, prefix: str, cfg: dict):
     ``res_conv(x_in) + x`` when residual; Dropout3d is the identity in eval mode."""
     x_in = x
     conv = cfg.get("conv", "conv")
-    for i in range(cfg.get("num_convs", 2)):
+    n = cfg.get("num_convs", 2)
+    residual = cfg.get("residual", False)
+    for i in range(n):
         w = sd[f"{prefix}layers.conv{i}.weight"]
         b = sd.get(f"{prefix}layers.conv{i}.bias")
         if conv == "ws":
             x = ws_conv3d(x, w, padding=1)
         else:
-            x = F.conv3d(x, w, b, padding=1)
+            x = F.conv3d(_q(x), _q(w), b, padding=1)
         x = _norm(x, sd, f"{prefix}layers.norm{i}.", cfg.get("norm", "batch"))
         x = _activation(x, cfg.get("act", "relu"), cfg.get("slope", 0.01))
-    if cfg.get("residual", False):
+        if not (residual and i == n - 1):
+            x = _q(x)          # stored activation (the last one is stored after the residual add)
+    if residual:
         w = sd[f"{prefix}res_conv.weight"]
         b = sd.get(f"{prefix}res_conv.bias")
-        r = ws_conv3d(x_in, w, padding=1) if conv == "ws" else F.conv3d(x_in, w, b, padding=1)
-        x = r + x
+        r = ws_conv3d(x_in, w, padding=1) if conv == "ws" else F.conv3d(_q(x_in), _q(w), b, padding=1)
+        x = _q(_q(r) + x)
     return x
 
 
@@ -150,21 +178,23 @@ def modular_unet_forward(sd: SD, x: torch.Tensor, cfg: dict) -> torch.Tensor:
             skips.append(x)
             if cfg.get("down", "avgpool") == "avgpool":
                 # nn.AvgPool3d(kernel_size=2, stride=2, count_include_pad=False), modular_unet.py:40-41
-                x = F.avg_pool3d(x, 2, 2, count_include_pad=False)
+                x = _q(F.avg_pool3d(x, 2, 2, count_include_pad=False))
             else:
                 x = blur_conv3d(x, sd[f"downsampling.{i}.weight"], sd[f"downsampling.{i}.kernel"], filters[i],
                                 cfg.get("down_ws", False), stride=2, padding=1)
     for i in reversed(range(depth - 1)):
         if cfg.get("up", "trilinear") == "trilinear":
             # nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True), modular_unet.py:38-39
-            x = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+            x = _q(F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True))
         else:
             x = blur_conv_transpose3d(x, sd[f"upsampling.{i}.weight"], sd[f"upsampling.{i}.kernel"],
                                       filters[i + 1], cfg.get("up_ws", False), stride=2, padding=1,
                                       output_padding=0)
         # modular_unet.py:97 -- upsampled tensor FIRST, skip second
         x = block3d(torch.cat([x, skips[i]], dim=1), sd, f"up_blocks.{i}.", cfg["block"])
-    x = F.conv3d(x, sd["out_conv.weight"], sd.get("out_conv.bias"), padding=1)
+    if cfg.get("return_features", False):
+        return x                    # input of out_conv (tests fit a linear read-out on it)
+    x = F.conv3d(_q(x), _q(sd["out_conv.weight"]), sd.get("out_conv.bias"), padding=1)
     return _hypothesis(x, cfg)
 
 
@@ -172,21 +202,22 @@ def modular_unet_forward(sd: SD, x: torch.Tensor, cfg: dict) -> torch.Tensor:
 def _nested_block(x, sd: SD, name: str, residual: bool):
     """NestedResUNet.Block.forward, models/nested_residual_unet.py:30-47."""
     x_in = x
-    x = F.conv3d(x, sd[f"{name}.conv1.weight"], None, padding=1)
-    x = F.relu(batch_norm_eval(x, sd, f"{name}.bn1."))
-    x = F.conv3d(x, sd[f"{name}.conv2.weight"], None, padding=1)
+    x = F.conv3d(_q(x), _q(sd[f"{name}.conv1.weight"]), None, padding=1)
+    x = _q(F.relu(batch_norm_eval(x, sd, f"{name}.bn1.")))
+    x = F.conv3d(x, _q(sd[f"{name}.conv2.weight"]), None, padding=1)
     x = F.relu(batch_norm_eval(x, sd, f"{name}.bn2."))
     if residual:
-        x = F.conv3d(x_in, sd[f"{name}.res_conv.weight"], sd[f"{name}.res_conv.bias"], padding=1) + x
-    return x
+        r = F.conv3d(_q(x_in), _q(sd[f"{name}.res_conv.weight"]), sd[f"{name}.res_conv.bias"], padding=1)
+        return _q(_q(r) + x)
+    return _q(x)
 
 
 def nested_res_unet_forward(sd: SD, x: torch.Tensor, cfg: Optional[dict] = None) -> torch.Tensor:
     """NestedResUNet.forward, models/nested_residual_unet.py:88-106 (UNet++ of depth 4; residual only on the
     level-0 blocks :72,74,78,83; skip tensors come FIRST in every concat)."""
     cfg = cfg or {}
-    down = lambda t: F.avg_pool3d(t, 2, 2, count_include_pad=False)
-    up = lambda t: F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=True)
+    down = lambda t: _q(F.avg_pool3d(t, 2, 2, count_include_pad=False))
+    up = lambda t: _q(F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=True))
     x0_0 = _nested_block(x, sd, "conv0_0", True)
     x1_0 = _nested_block(down(x0_0), sd, "conv1_0", False)
     x0_1 = _nested_block(torch.cat((x0_0, up(x1_0)), 1), sd, "conv0_1", True)
@@ -197,7 +228,9 @@ def nested_res_unet_forward(sd: SD, x: torch.Tensor, cfg: Optional[dict] = None)
     x2_1 = _nested_block(torch.cat((x2_0, up(x3_0), down(x1_1)), 1), sd, "conv2_1", False)
     x1_2 = _nested_block(torch.cat((x1_1, up(x2_1), down(x0_2)), 1), sd, "conv1_2", False)
     x0_3 = _nested_block(torch.cat((x0_2, up(x1_2)), 1), sd, "conv0_3", True)
-    x_out = F.conv3d(x0_3, sd["out_conv.weight"], sd["out_conv.bias"], padding=1)
+    if cfg.get("return_features", False):
+        return x0_3                 # input of out_conv (tests fit a linear read-out on it)
+    x_out = F.conv3d(_q(x0_3), _q(sd["out_conv.weight"]), sd["out_conv.bias"], padding=1)
     return _hypothesis(x_out, cfg)
 
 

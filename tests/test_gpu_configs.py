@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import evalstats, grid as ogrid, unet
-from helpers import rel_err
+from helpers import label_agreement_report, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -60,11 +60,12 @@ def test_config1_full_run_fp32_and_bf16():
         out[precision] = (probs.cpu(), labels.cpu())
     assert rel_err(out["fp32"][0], torch.from_numpy(ref)) <= 1e-5
     assert rel_err(out["bf16"][0], torch.from_numpy(ref)) <= 2e-2
-    ref_labels = evalstats.argmax_labels(ref)[0]
-    top2 = np.sort(ref, axis=0)
-    decided = (top2[-1] - top2[-2]) > 0.05
-    assert (out["fp32"][1].numpy() == ref_labels)[decided].mean() == 1.0
-    assert (out["bf16"][1].numpy() == ref_labels)[decided].mean() >= 0.999
+    # unfiltered label agreement (random-init head: see tests/test_gpu_labels.py for the confident-head criterion)
+    ref_t = torch.from_numpy(ref)
+    rep32 = label_agreement_report(ref_t, out["fp32"][0], "config 1, fp32 path, random head")
+    rep16 = label_agreement_report(ref_t, out["bf16"][0], "config 1, bf16 path, random head")
+    assert rep32["agreement"] >= 0.9999 and rep32["disagree_margin_max"] <= 1e-4
+    assert rep16["agreement"] >= 0.97 and rep16["disagree_margin_max"] <= 2e-2
     # labels are exactly the argmax of the probabilities the same call returned
     for precision in out:
         np.testing.assert_array_equal(out[precision][1].numpy(), evalstats.argmax_labels(out[precision][0].numpy())[0])
@@ -101,10 +102,8 @@ def test_config2_network_one_patch_against_oracle():
         finally:
             set_precision("auto")
         assert rel_err(out, ref) <= tol, precision
-        top2 = torch.topk(ref, 2, dim=1).values
-        decided = (top2[:, 0] - top2[:, 1]) > 0.05
-        if decided.any():
-            assert (out.argmax(1) == ref.argmax(1))[decided].float().mean().item() >= 0.999
+        rep = label_agreement_report(ref, out, f"config 2 network, one patch, {precision}, random head")
+        assert rep["agreement"] >= (0.9999 if precision == "fp32" else 0.99)
 
 
 def test_config2_full_volume_properties():

@@ -170,6 +170,84 @@ def test_overlap_crop_matches_oracle(lib):
         np.testing.assert_array_equal(out.cpu().numpy(), ref)
 
 
+def _cuda_sliding_window(lib, vol, patch, overlap, padding_mode, overlap_mode, gain, batch=3):
+    """The product's host grid + CUDA extraction / aggregation / finalize with a 'model' that scales patch n by
+    gain(n, location) -- the device-side counterpart of oracle.grid.sliding_window."""
+    from segmentation_pipeline.grid import PatchGrid
+    grid = PatchGrid(vol.shape[1:], patch, overlap, padding_mode)
+    c = vol.shape[0]
+    dvol = dev(torch.from_numpy(vol))
+    out = torch.zeros((c, *grid.padded_shape), device="cuda")
+    n = 0
+    for locs in grid.batches(batch):
+        buf = lib.Blocked(len(locs), (c + 7) // 8, *grid.patch_size, torch.float32, "cuda")
+        lib.grid_extract(dvol, locs, grid.border, grid.pad_mode_code, grid.pad_value, buf.view(c))
+        y = torch.empty((len(locs), c, *grid.patch_size), device="cuda")
+        lib.unpack_ncdhw(buf.view(c), y)
+        for i, l in enumerate(locs):
+            y[i] *= gain(n, l)
+            n += 1
+        if overlap_mode == "average":
+            lib.overlap_add(out, y, locs)
+        else:
+            lib.overlap_crop(out, y, locs, [o // 2 for o in grid.patch_overlap], grid.volume_padded)
+    counts = None
+    if overlap_mode == "average":
+        counts = [torch.tensor(cc, dtype=torch.int32, device="cuda") for cc in grid.axis_counts()]
+    probs = torch.empty((c, *grid.spatial_shape), device="cuda")
+    lib.finalize(out, counts, grid.border, probs, None, None)
+    return grid, probs.cpu().numpy()
+
+
+def test_cuda_grid_path_matches_pinned_torchio_vectors(lib):
+    """tests/golden/grid_torchio.json: torchio's own unit-test fixtures + brute-force cases (oracle/make_grid_golden.py)."""
+    import json
+    import os
+    from helpers import GOLDEN
+    from segmentation_pipeline.grid import PatchGrid
+    with open(os.path.join(GOLDEN, "grid_torchio.json")) as f:
+        g = json.load(f)
+    t = g["torchio_test_locations"]
+    assert [list(l) for l in PatchGrid(t["image"], t["patch"], t["overlap"]).locations] == t["locations"]
+    a = g["torchio_test_aggregator"]
+    ones = np.ones((1, *a["image"]), np.float32)
+    for mode in ("crop", "average"):
+        _, res = _cuda_sliding_window(lib, ones, a["patch"], a["overlap"], None, mode,
+                                      lambda n, l: float(a["patch_values"][f"{l[1]},{l[2]}"]))
+        np.testing.assert_array_equal(res[0, 0], np.array(a[mode], np.float32))
+    for case in g["brute_force"]:
+        vol = np.array(case["volume"], np.float32)[None]
+        grid, res = _cuda_sliding_window(lib, vol, case["patch"], case["overlap"], case["padding_mode"],
+                                         case["overlap_mode"], lambda n, l: float(n + 1))
+        assert [list(l) for l in grid.locations] == case["locations"]
+        np.testing.assert_array_equal(res[0], np.array(case["output"], np.float32))
+
+
+def test_cuda_grid_path_against_real_torchio_when_installed(lib):
+    """Runs tio.GridSampler / tio.GridAggregator themselves when the box has torchio (the authoring image does not:
+    the test then SKIPS and says so; the pinned vectors above are the torchio-derived check that always runs)."""
+    tio = pytest.importorskip("torchio", reason="torchio is not installed on this box: real-torchio comparison skipped")
+    from torch.utils.data import DataLoader
+    rng = np.random.default_rng(11)
+    vol = rng.standard_normal((2, 20, 18, 14)).astype(np.float32)
+    for padding_mode, overlap_mode in ((None, "average"), ("edge", "average"), ("edge", "crop"), (None, "crop")):
+        subject = tio.Subject(X=tio.ScalarImage(tensor=torch.from_numpy(vol)))
+        sampler = tio.GridSampler(subject, (8, 8, 6), (4, 2, 2), padding_mode=padding_mode)
+        aggregator = tio.GridAggregator(sampler, overlap_mode=overlap_mode)
+        n = 0
+        for batch in DataLoader(sampler, batch_size=3):
+            data = batch["X"][tio.DATA].clone()
+            for i in range(data.shape[0]):
+                data[i] *= float(n + 1)
+                n += 1
+            aggregator.add_batch(data, batch[tio.LOCATION])
+        ref = aggregator.get_output_tensor().numpy()
+        _, res = _cuda_sliding_window(lib, vol, (8, 8, 6), (4, 2, 2), padding_mode, overlap_mode,
+                                      lambda k, l: float(k + 1))
+        np.testing.assert_array_equal(res, ref)
+    print("real torchio", tio.__version__, "compared")
+
+
 def test_argmax_ties_and_bit_exact(lib):
     rng = np.random.default_rng(6)
     for vox in (4 * 1000, 1003):

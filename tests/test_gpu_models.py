@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import evalstats, grid as ogrid, unet
-from helpers import GOLDEN, load_case, rel_err
+from helpers import GOLDEN, label_agreement_report, load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -78,12 +78,13 @@ def test_bf16_network_within_tolerance(name):
         set_precision("auto")
     assert rel_err(out.cpu(), y) <= 2e-2
     if meta["hypothesis"] == "softmax":
-        # label agreement, ignoring voxels whose top-2 margin is below the bf16 resolution of the logits
-        top2 = torch.topk(y, 2, dim=1).values
-        decided = (top2[:, 0] - top2[:, 1]) > 0.05
-        if decided.any():
-            agree = (out.cpu().argmax(1) == y.argmax(1))[decided].float().mean().item()
-            assert agree >= 0.999
+        # Unfiltered label agreement.  These fixtures are tiny RANDOM-INIT networks (p ~ 1/C everywhere), so the
+        # argmax hangs on the last bits of the logits: the >= 99.9 % criterion is asserted on confident heads in
+        # tests/test_gpu_labels.py; here every voxel is counted and a label may differ only where the reference's own
+        # top-2 margin is below twice the probability error.
+        rep = label_agreement_report(y, out.cpu(), f"{name} (random head, bf16)")
+        assert rep["agreement"] >= 0.95
+        assert rep["disagree_margin_max"] <= 2 * (out.cpu() - y).abs().max().item() + 1e-7
 
 
 def test_autocast_selects_bf16_path():

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import grid
+from oracle import grid as ogrid
 
 
 def test_torchio_source_comment_example():
@@ -78,3 +79,52 @@ def test_edge_padding_shape():
     pad = grid.pad_volume(vol, (2, 4, 0), "edge")
     assert pad.shape == (2, 6, 8, 4)
     assert pad[0, 0, 0, 0] == vol[0, 0, 0, 0] and pad[1, -1, -1, -1] == vol[1, -1, -1, -1]
+
+
+# ------------------------------------------------------------------------------------------------- pinned vectors
+def _golden():
+    import json
+    import os
+    from helpers import GOLDEN
+    with open(os.path.join(GOLDEN, "grid_torchio.json")) as f:
+        return json.load(f)
+
+
+def test_locations_match_torchio_unit_test_fixture():
+    g = _golden()["torchio_test_locations"]
+    loc = ogrid.grid_locations(g["image"], g["patch"], g["overlap"])
+    assert loc.tolist() == g["locations"]
+
+
+@pytest.mark.parametrize("mode", ["crop", "average"])
+def test_aggregator_matches_torchio_unit_test_fixture(mode):
+    g = _golden()["torchio_test_aggregator"]
+    vol = np.ones((1, *g["image"]), np.float32)
+
+    def model(patches, locs=[]):
+        return patches
+
+    loc = ogrid.grid_locations(g["image"], g["patch"], g["overlap"])
+    patches = ogrid.extract_patches(vol, loc)
+    for i, l in enumerate(loc):
+        patches[i] *= g["patch_values"][f"{l[1]},{l[2]}"]
+    if mode == "average":
+        out, cnt = ogrid.aggregate_average(patches, loc, g["image"])
+        res = ogrid.finalize(out, cnt, g["overlap"], False)
+    else:
+        res = ogrid.finalize(ogrid.aggregate_crop(patches, loc, g["image"], g["overlap"], False), None, g["overlap"],
+                             False)
+    np.testing.assert_array_equal(res[0, 0], np.array(g[mode], np.float32))
+
+
+def test_sliding_window_matches_brute_force_vectors():
+    for case in _golden()["brute_force"]:
+        vol = np.array(case["volume"], np.float32)[None]
+        loc = ogrid.grid_locations([s + 2 * (o // 2 if case["padding_mode"] is not None else 0)
+                                    for s, o in zip(case["shape"], case["overlap"])], case["patch"], case["overlap"])
+        assert loc.tolist() == case["locations"]
+        gains = iter(range(1, len(loc) + 1))
+        res = ogrid.sliding_window(vol, lambda p: p * np.array([next(gains) for _ in p], np.float32)[:, None, None, None, None],
+                                   case["patch"], case["overlap"], case["padding_mode"], case["overlap_mode"],
+                                   patch_batch_size=3)
+        np.testing.assert_array_equal(res[0], np.array(case["output"], np.float32))
