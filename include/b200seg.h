@@ -182,7 +182,10 @@ int b200seg_argmax(const float* probs, int32_t c, int64_t voxels, int64_t* label
  * Single pass over two label maps -> num_classes x num_classes joint histogram cm[target][prediction] (int64,
  * ACCUMULATED into cm so cohorts can be summed), from which TP/FP/TN/FN of segmentation_evaluator.py:69-77
  * and the volumes of label_map_evaluator.py:77-81 follow exactly.  label_bytes = 1 (uint8) or 8 (int64).
- * Values outside [0, num_classes) are ignored.  num_classes <= 64. */
+ * Values outside [0, num_classes) are counted in the LAST class (num_classes - 1) -- nothing is dropped, so callers
+ * that want the reference's semantics for labels they do not list ((target == v) & (pred != v) for ANY pred value,
+ * segmentation_evaluator.py:72-77) pass num_classes = max listed value + 2 and read the last row / column as
+ * "other".  num_classes <= 40 (per-lane histogram columns must fit shared memory). */
 int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes, int64_t voxels,
                       int32_t num_classes, int64_t* cm, void* stream);
 

@@ -31,11 +31,13 @@ def confusion_matrix(pred: np.ndarray, target: np.ndarray, num_classes: int) -> 
     """L x L joint histogram ``cm[t, p]`` = #voxels with target t and prediction p.  Not a reference function:
     it is the single-pass statistic from which every per-label count of
     segmentation_evaluator.py:69-77 follows (see ``counts_from_confusion``).  Values outside
-    [0, num_classes) are ignored, matching ``==`` comparisons that never fire."""
+    [0, num_classes) are counted in the LAST class ("other"): a voxel whose prediction is an unlisted label still is a
+    false negative of its target label, exactly as ``(target == v) & ~(pred == v)`` counts it."""
     p = np.asarray(pred).reshape(-1).astype(np.int64)
     t = np.asarray(target).reshape(-1).astype(np.int64)
-    ok = (p >= 0) & (p < num_classes) & (t >= 0) & (t < num_classes)
-    cm = np.bincount(t[ok] * num_classes + p[ok], minlength=num_classes * num_classes)
+    p = np.where((p >= 0) & (p < num_classes), p, num_classes - 1)
+    t = np.where((t >= 0) & (t < num_classes), t, num_classes - 1)
+    cm = np.bincount(t * num_classes + p, minlength=num_classes * num_classes)
     return cm.reshape(num_classes, num_classes).astype(np.int64)
 
 

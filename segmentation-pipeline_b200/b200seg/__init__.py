@@ -96,14 +96,42 @@ def _stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class on_device:
+    """``with on_device(t_or_device):`` makes that CUDA device current for the block, so the stream handed to the
+    library, the scratch allocations and cudaGetDevice() inside it all refer to the device the data lives on.  The
+    reference API is ``predict(model, device, subjects)``: the caller's *current* device may be another GPU."""
+
+    def __init__(self, where):
+        dev = where.device if isinstance(where, torch.Tensor) else torch.device(where)
+        if dev.type != "cuda":
+            raise RuntimeError("b200seg operates on CUDA devices only (no CPU fallback)")
+        self._ctx = torch.cuda.device(dev)
+
+    def __enter__(self):
+        return self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        return self._ctx.__exit__(*exc)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
     return c_void_p(0 if t is None else t.data_ptr())
 
 
 def _require_cuda(*tensors: torch.Tensor) -> None:
+    """Every tensor of a call must live on the CURRENT CUDA device: kernels are launched on its stream, so a pointer
+    from another GPU would fault or silently run through peer access (use ``on_device``)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("b200seg operates on CUDA tensors only (no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"b200seg: tensor on cuda:{t.device.index} but the current device is cuda:{cur}; "
+                               f"wrap the call in `with b200seg.on_device(tensor):`")
 
 
 def dtype_code(dtype: torch.dtype) -> int:
@@ -195,7 +223,7 @@ def instnorm(x: View, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor
     """In-place InstanceNorm3d + activation (+ residual) on a blocked view (three streaming launches)."""
     lib = load_library()
     need = int(lib.b200seg_instnorm_scratch_bytes(x))
-    scratch = torch.empty(need // 4, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+    scratch = torch.empty(max(need // 4, 1), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
     _LAUNCHES[0] += 3
     _check(lib.b200seg_instnorm(x, _ptr(gamma), _ptr(beta), float(eps), float(slope), residual, _ptr(scratch), need,
                                 _stream()), "instnorm")

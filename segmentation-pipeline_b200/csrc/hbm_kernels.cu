@@ -454,8 +454,12 @@ confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long lo
         unsigned int run = 0;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            long long p = static_cast<long long>(pp[q]), tt = static_cast<long long>(tp[q]);
-            const int bin = (p >= 0 && p < nc && tt >= 0 && tt < nc) ? static_cast<int>(tt) * nc + static_cast<int>(p) : -1;
+            // values outside [0, nc) fall into the LAST class ("other"): nothing is dropped, so row / column sums are
+            // the true marginals (the unsigned compare also catches negative int64 labels)
+            const unsigned long long pu = static_cast<unsigned long long>(pp[q]), tu = static_cast<unsigned long long>(tp[q]);
+            const int p = pu < static_cast<unsigned long long>(nc) ? static_cast<int>(pu) : nc - 1;
+            const int tt = tu < static_cast<unsigned long long>(nc) ? static_cast<int>(tu) : nc - 1;
+            const int bin = tt * nc + p;
             if (bin == cur) {
                 ++run;
             } else {
@@ -491,12 +495,12 @@ confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long lo
     // tail (voxels not a multiple of PER): first thread of the grid
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (long long v = nvec * PER; v < voxels; ++v) {
-            long long p = static_cast<long long>(pred[v]), tt = static_cast<long long>(targ[v]);
-            if (p >= 0 && p < nc && tt >= 0 && tt < nc) {
-                int bin = static_cast<int>(tt) * nc + static_cast<int>(p);
-                if (shared_cols) atomicAdd(mine + bin * 32, 1u);
-                else mine[bin * 32] += 1u;
-            }
+            const unsigned long long pu = static_cast<unsigned long long>(pred[v]), tu = static_cast<unsigned long long>(targ[v]);
+            const int p = pu < static_cast<unsigned long long>(nc) ? static_cast<int>(pu) : nc - 1;
+            const int tt = tu < static_cast<unsigned long long>(nc) ? static_cast<int>(tu) : nc - 1;
+            const int bin = tt * nc + p;
+            if (shared_cols) atomicAdd(mine + bin * 32, 1u);
+            else mine[bin * 32] += 1u;
         }
     }
     __syncthreads();
@@ -823,7 +827,7 @@ int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes,
                       int32_t num_classes, int64_t* cm, void* stream) {
     B200SEG_CHECK_ARG(pred && target && cm && voxels > 0, "confusion: bad arguments");
     B200SEG_CHECK_ARG(label_bytes == 1 || label_bytes == 8, "confusion: label_bytes must be 1 or 8");
-    B200SEG_CHECK_ARG(num_classes >= 1 && num_classes <= 64, "confusion: num_classes %d not in [1,64]", num_classes);
+    B200SEG_CHECK_ARG(num_classes >= 1 && num_classes <= 40, "confusion: num_classes %d not in [1,40]", num_classes);
     B200SEG_CHECK_ARG((reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0,
                       "confusion: label maps must be 16-byte aligned");
     int dev = 0, sms = 148;

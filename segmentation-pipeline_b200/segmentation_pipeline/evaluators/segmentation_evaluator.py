@@ -12,7 +12,7 @@ import torch
 from .evaluator import Evaluator
 from .labeled_tensor import LabeledTensor
 
-MAX_CLASSES = 64
+MAX_CLASSES = 40      # histogram classes of b200seg_confusion, including the 'other' class
 
 
 def _device_labels(image, device):
@@ -24,18 +24,22 @@ def confusion_counts(pred: torch.Tensor, target: torch.Tensor, label_values: Dic
     """-> {label_name: (TP, FP, TN, FN)} as Python ints, computed on the device."""
     import b200seg
     device = pred.device if pred.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    num_classes = max(int(v) for v in label_values.values()) + 1
-    if num_classes > MAX_CLASSES:
-        raise NotImplementedError(f"label values up to {num_classes - 1}: the device histogram handles values "
-                                  f"below {MAX_CLASSES}")
+    # one extra class: every value that is not below max(label_values) + 1 -- unlisted or negative labels -- lands
+    # in it, so FP = column sum - TP and FN = row sum - TP count them exactly like the reference's
+    # (~target_label & pred_label).sum() / (target_label & ~pred_label).sum() (segmentation_evaluator.py:75,77)
+    num_classes = max(int(v) for v in label_values.values()) + 2
+    if min(int(v) for v in label_values.values()) < 0 or num_classes > MAX_CLASSES:
+        raise NotImplementedError(f"label values must lie in [0, {MAX_CLASSES - 2}] for the device histogram, got "
+                                  f"{sorted(label_values.values())}")
     pred = pred.to(device).contiguous()
     target = target.to(device).contiguous()
     if pred.dtype != target.dtype or pred.dtype not in (torch.uint8, torch.int64):
         pred, target = pred.to(torch.int64), target.to(torch.int64)
     if pred.numel() != target.numel():
         raise RuntimeError("prediction and target label maps differ in size")
-    cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=device)
-    b200seg.confusion(pred, target, num_classes, cm)
+    with b200seg.on_device(device):
+        cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=device)
+        b200seg.confusion(pred, target, num_classes, cm)
     cm = cm.cpu()
     total = pred.numel()
     out = {}

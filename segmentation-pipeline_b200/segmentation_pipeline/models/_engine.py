@@ -235,6 +235,9 @@ class CompiledPlan:
                 lib.avgpool2(view(call.src), view(call.dst))
             elif isinstance(call, UpsampleOp):
                 lib.upsample_trilinear2(view(call.src), view(call.dst))
+            elif isinstance(call, _plan.UnpackOp):
+                lib.unpack_ncdhw(ws["out"].view(self.plan.out_channels), out)
+                wrote_final = True
             elif isinstance(call, SoftmaxOp):
                 lib.softmax_ncdhw(out, call.sm_channels, call.diag_bias)
             elif isinstance(call, _plan.InstNormOp):
@@ -294,13 +297,18 @@ def forward_native(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
                                for m in module.modules()):
         raise NotImplementedError("training-mode forward (batch statistics / dropout / autograd) is not part of "
                                   "the inference hot path; call model.eval()")
-    if isinstance(module, StochasticMatrix):
-        lib = _b200seg()
-        out = x.detach().to(torch.float32).contiguous().clone()
-        if out.shape[1] != module.channels ** 2:
-            raise RuntimeError("Expected dim 1 of input tensor to be the square of the number of out channels")
-        lib.softmax_ncdhw(out, module.channels, float(module.diag_bias or 0.0))
-        return out
-    precision = _resolve_precision(module, x)
-    y = compiled_for(module, precision, x.device).run(x)
-    return y if x.dtype == torch.float32 else y.to(x.dtype)
+    lib = _b200seg()
+    # the caller's current device may be another GPU: launch on the stream of the device that holds x
+    with lib.on_device(x):
+        if isinstance(module, StochasticMatrix):
+            out = x.detach().to(torch.float32).contiguous().clone()
+            if out.shape[1] != module.channels ** 2:
+                raise RuntimeError("Expected dim 1 of input tensor to be the square of the number of out channels")
+            lib.softmax_ncdhw(out, module.channels, float(module.diag_bias or 0.0))
+            return out
+        first = next(module.parameters(), None)
+        if first is not None and first.device != x.device:
+            raise RuntimeError(f"module parameters live on {first.device} but the input is on {x.device}")
+        precision = _resolve_precision(module, x)
+        y = compiled_for(module, precision, x.device).run(x)
+        return y if x.dtype == torch.float32 else y.to(x.dtype)

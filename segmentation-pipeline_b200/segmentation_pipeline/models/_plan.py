@@ -87,6 +87,11 @@ class SoftmaxOp:
 
 
 @dataclass
+class UnpackOp:
+    """blocked 'out' buffer -> fp32 NCDHW result (heads wider than the fused final epilogue)."""
+
+
+@dataclass
 class InstNormOp:
     """nn.InstanceNorm3d in place on ``ref`` + activation (+ residual): cannot be folded into the conv epilogue
     because its statistics depend on the whole conv output."""
@@ -287,7 +292,7 @@ def _lower_hypothesis(plan: Plan, hypothesis, out_channels: int):
     if isinstance(hypothesis, nn.Softmax):
         if hypothesis.dim != 1:
             raise UnsupportedModule("only Softmax(dim=1) is lowered")
-        if out_channels <= 16:
+        if out_channels <= FINAL_MAX_COUT:
             return True, []
         return False, [SoftmaxOp()]
     if isinstance(hypothesis, nn.Identity):
@@ -297,6 +302,27 @@ def _lower_hypothesis(plan: Plan, hypothesis, out_channels: int):
             raise RuntimeError("Expected dim 1 of input tensor to be the square of the number of out channels")
         return False, [SoftmaxOp(hypothesis.channels, float(hypothesis.diag_bias or 0.0))]
     raise UnsupportedModule(f"hypothesis {type(hypothesis).__name__} is not lowered")
+
+
+FINAL_MAX_COUT = 16      # widest layer the engines' fused NCDHW / softmax epilogue writes (make_depilogue, conv_direct)
+
+
+def _lower_head(plan: Plan, hypothesis, src: Ref, segments, out_w, out_b) -> None:
+    """out_conv + hypothesis.  Up to 16 output channels the last conv writes fp32 NCDHW itself (softmax fused); wider
+    heads (a StochasticMatrix with C >= 5, more than 16 classes) go through a blocked 'out' buffer that the engine
+    unpacks before the separate softmax pass."""
+    out_ch = out_w.shape[0]
+    fused, extra = _lower_hypothesis(plan, hypothesis, out_ch)
+    scale, shift, slope = _epilogue_arrays(out_ch, out_b, None, None)
+    plan.op_levels[len(plan.ops)] = 0
+    if out_ch <= FINAL_MAX_COUT:
+        plan.ops.append(ConvOp(K3, src, segments, out_w, scale, shift, slope, final=True, softmax=fused,
+                               name="out_conv"))
+    else:
+        dst = Ref(plan.add_buffer("out", out_ch, 0), 0, out_ch)
+        plan.ops.append(ConvOp(K3, src, segments, out_w, scale, shift, slope, dst0=dst, name="out_conv"))
+        plan.ops.append(UnpackOp())
+    plan.ops.extend(extra)
 
 
 def lower_modular_unet(model) -> Plan:
@@ -353,11 +379,7 @@ def lower_modular_unet(model) -> Plan:
         _lower_block(plan, i, f"up{i}", cat, [(0, filters[i + 1]), (c8(filters[i + 1]), filters[i])], convs, norms,
                      acts, res, out)
         x = out
-    fused, extra = _lower_hypothesis(plan, model.hypothesis, out_ch)
-    scale, shift, slope = _epilogue_arrays(out_ch, out_b, None, None)
-    plan.op_levels[len(plan.ops)] = 0
-    plan.ops.append(ConvOp(K3, x, [(0, x.c)], out_w, scale, shift, slope, final=True, softmax=fused, name="out_conv"))
-    plan.ops.extend(extra)
+    _lower_head(plan, model.hypothesis, x, [(0, x.c)], out_w, out_b)
     return plan
 
 
@@ -436,12 +458,7 @@ def lower_nested_res_unet(model) -> Plan:
     up_to(where["x1_2"], slot("conv0_3", "up(x1_2)"), 1)
     run_block("conv0_3", *cat_src("conv0_3"), home("x0_3", 0))
 
-    fused, extra = _lower_hypothesis(plan, model.hypothesis, out_ch)
-    scale, shift, slope = _epilogue_arrays(out_ch, out_b, None, None)
-    plan.op_levels[len(plan.ops)] = 0
-    plan.ops.append(ConvOp(K3, where["x0_3"], [(0, f)], out_w, scale, shift, slope, final=True, softmax=fused,
-                           name="out_conv"))
-    plan.ops.extend(extra)
+    _lower_head(plan, model.hypothesis, where["x0_3"], [(0, f)], out_w, out_b)
     return plan
 
 

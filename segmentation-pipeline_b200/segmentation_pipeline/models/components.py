@@ -31,6 +31,23 @@ class _NativeForward:
     def forward(self, x, *args, **kwargs):  # noqa: D401
         return _engine.forward_native(self, x)
 
+    def invalidate(self) -> None:
+        """Drops the packed device weights / workspaces of this module; the next forward re-packs them.
+
+        The cache key is (data_ptr, version counter) of every parameter and buffer, which catches ``load_state_dict``,
+        ``.to()`` and ordinary in-place ops -- but NOT edits made through ``.data`` (``weight.data.mul_()``, EMA / SWA
+        updates, manual BatchNorm-statistic patching), which do not bump the version counter: call ``invalidate()``
+        after those.  One module instance serves ONE stream at a time (its workspaces are shared)."""
+        self.__dict__.pop("_b200_cache", None)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop("_b200_cache", None)

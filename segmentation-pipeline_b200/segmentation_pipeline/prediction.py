@@ -95,10 +95,11 @@ class StandardPredict(Predictor):
         device = _require_cuda(device)
         batch = collate_subjects(subjects, image_names=self.image_names, device=device)
         label_attributes = {} if label_attributes is None else label_attributes
-        if self.sagittal_split:
-            y_pred = reverse_split_and_flip(model(split_and_flip(batch['X']).contiguous()))
-        else:
-            y_pred = model(batch["X"])
+        with _lib().on_device(device):
+            if self.sagittal_split:
+                y_pred = reverse_split_and_flip(model(split_and_flip(batch['X']).contiguous()))
+            else:
+                y_pred = model(batch["X"])
         batch['y_pred'] = y_pred
         out_subjects = []
         for i, subject in enumerate(subjects):
@@ -132,11 +133,18 @@ class PatchPredict(Predictor):
                        want_labels: bool = True):
         """volume: fp32 (C, W, H, D) already on the device.  Returns (probs fp32 (C_out, W, H, D) or None,
         labels uint8 (W, H, D) or None), both on the device."""
+        if not volume.is_cuda:
+            raise RuntimeError("predict_volume expects the volume on the CUDA device")
+        with _lib().on_device(volume):     # the caller's current device may be another GPU
+            return self._predict_volume(model, volume, want_probs, want_labels)
+
+    def _predict_volume(self, model, volume, want_probs, want_labels):
         lib = _lib()
         if self.overlap_mode not in ("average", "crop"):
             raise ValueError(f'Overlap mode must be "crop" or "average" but "{self.overlap_mode}" was passed')
         if not volume.is_cuda:
             raise RuntimeError("predict_volume expects the volume on the CUDA device")
+        in_dtype = volume.dtype          # 'auto' precision follows the caller's dtype (a bf16 volume -> bf16 path)
         volume = volume.detach().to(torch.float32).contiguous()
         grid = PatchGrid(volume.shape[1:], self.patch_size, self.patch_overlap, self.padding_mode)
         p0, p1, p2 = grid.patch_size
@@ -146,7 +154,7 @@ class PatchPredict(Predictor):
         if native:
             if model.training:
                 raise NotImplementedError("PatchPredict needs model.eval() (inference path only)")
-            precision = _engine._resolve_precision(model, volume)
+            precision = _engine._resolve_precision(model, volume if in_dtype == torch.float32 else volume.new_empty(0, dtype=in_dtype))
             compiled = _engine.compiled_for(model, precision, device)
             if compiled.plan.out_scale != 0:
                 raise RuntimeError("PatchPredict needs a network whose output extent equals its input extent")
@@ -201,7 +209,9 @@ class PatchPredict(Predictor):
             torch.cuda.current_stream(device).synchronize()
             image = _tio.make_label_map(probs_host, **copy.deepcopy(label_attributes))
             if labels is not None:
-                image[LABELS_KEY] = labels
+                # device label map + the identity of the probabilities it was computed from: add_evaluation_labels
+                # uses the stash only while 'data' is still that very tensor (post-processing may replace it)
+                image[LABELS_KEY] = (labels, probs_host.data_ptr(), probs_host._version)
             subject.add_image(image, "y_pred")
             out_subjects.append(_tio.enforce_consistent_affine(subject, "X"))
         # batch[name]: (S, C, W, H, D) on the device, as collate_subjects returns (utils/utils.py:75-85); the 'X'
@@ -225,11 +235,14 @@ def _argmax_labels(image) -> torch.Tensor:
     lib = _lib()
     stash = image.get(LABELS_KEY) if hasattr(image, "get") else None
     if stash is not None:
-        return stash.to(torch.int64).cpu()[None]
-    device = torch.device("cuda", torch.cuda.current_device())
-    probs = data.detach().to(device=device, dtype=torch.float32).contiguous()
-    labels = torch.empty(probs.shape[1:], dtype=torch.int64, device=device)
-    lib.argmax(probs, labels, None)
+        labels, ptr, version = stash
+        if data.data_ptr() == ptr and data._version == version:
+            return labels.to(torch.int64).cpu()[None]
+    device = data.device if data.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    with lib.on_device(device):
+        probs = data.detach().to(device=device, dtype=torch.float32).contiguous()
+        labels = torch.empty(probs.shape[1:], dtype=torch.int64, device=device)
+        lib.argmax(probs, labels, None)
     return labels.cpu()[None]
 
 

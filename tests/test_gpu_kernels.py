@@ -263,8 +263,10 @@ def test_argmax_ties_and_bit_exact(lib):
                                           (torch.int64, 17, 300_001), (torch.uint8, 40, 250_000)])
 def test_confusion_bit_exact(lib, dtype, nc, vox):
     rng = np.random.default_rng(7)
-    p = rng.integers(0, nc + 2, size=vox)      # includes values outside [0, nc): must be ignored
+    p = rng.integers(0, nc + 2, size=vox)      # includes values outside [0, nc): counted in the last class
     t = rng.integers(0, nc + 2, size=vox)
+    if dtype == torch.int64:
+        p[::97] = -3                           # negative labels too
     cm = torch.zeros((nc, nc), dtype=torch.int64, device="cuda")
     lib.confusion(dev(torch.from_numpy(p).to(dtype)), dev(torch.from_numpy(t).to(dtype)), nc, cm)
     np.testing.assert_array_equal(cm.cpu().numpy(), evalstats.confusion_matrix(p, t, nc))

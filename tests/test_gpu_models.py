@@ -87,6 +87,77 @@ def test_bf16_network_within_tolerance(name):
         assert rep["disagree_margin_max"] <= 2 * (out.cpu() - y).abs().max().item() + 1e-7
 
 
+@pytest.mark.parametrize("head", ["softmax17", "stochastic5"])
+def test_wide_heads_go_through_the_blocked_out_buffer(head):
+    """More than 16 output channels (17 classes; a StochasticMatrix with C = 5 -> 25 channels): the last conv writes a
+    blocked buffer, the engine unpacks it and runs the separate softmax pass (these branches used to fail)."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.models import set_precision
+    torch.manual_seed(5)
+    if head == "softmax17":
+        model = M.ModularUNet(1, 17, [8, 8], 2)
+        cfg = {"hypothesis": "softmax"}
+    else:
+        model = M.ModularUNet(1, 25, [8, 8], 2, hypothesis_class=M.StochasticMatrix,
+                              hypothesis_params={"channels": 5, "diag_bias": 2.0})
+        cfg = {"hypothesis": "stochastic_matrix", "sm_channels": 5, "sm_diag_bias": 2.0}
+    model.eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    cfg.update({"depth": 2, "filters": [8, 8], "block": {"residual": False}, "down": "avgpool", "up": "trilinear"})
+    x = torch.randn(2, 1, 16, 8, 8, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        ref = unet.modular_unet_forward(sd, x, cfg)
+    model.cuda()
+    for precision, tol in (("fp32", 1e-5), ("bf16", 2e-2)):
+        set_precision(precision)
+        try:
+            with torch.no_grad():
+                out = model(x.cuda()).cpu()
+        finally:
+            set_precision("auto")
+        assert out.shape == ref.shape
+        assert rel_err(out, ref) <= tol, (head, precision)
+
+
+def test_other_device_than_current(monkeypatch):
+    """predict(model, device, ...) with device != the current CUDA device.  Needs two GPUs; on one GPU
+    the guard itself is checked: a tensor from another device index is refused loudly."""
+    import b200seg
+    if torch.cuda.device_count() < 2:
+        t = torch.zeros(16, device="cuda:0")
+        monkeypatch.setattr(torch.cuda, "current_device", lambda: 1)
+        with pytest.raises(RuntimeError, match="current device"):
+            b200seg._require_cuda(t)
+        return
+    meta, sd, x, y = load_case("models_modular_default")
+    model = build_model(meta)
+    model.load_state_dict(sd)
+    model.eval().to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    with torch.no_grad():
+        out = model(x.to("cuda:1"))
+    assert out.device == torch.device("cuda:1") and rel_err(out.cpu(), y) <= 1e-5
+
+
+def test_invalidate_after_data_edit():
+    meta, sd, x, y = load_case("models_modular_default")
+    model = build_model(meta)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    with torch.no_grad():
+        a = model(x.cuda())
+        model.out_conv.weight.data.mul_(2.0)          # .data edit: no version bump
+        model.invalidate()
+        b = model(x.cuda())
+    assert not torch.equal(a, b)
+    sd2 = dict(sd)
+    sd2["out_conv.weight"] = sd["out_conv.weight"] * 2.0
+    cfg = dict(meta)
+    with torch.no_grad():
+        ref = unet.modular_unet_forward(sd2, x, cfg)
+    assert rel_err(b.cpu(), ref) <= 1e-5
+
+
 def test_autocast_selects_bf16_path():
     meta, sd, x, y = load_case("models_modular_blur")
     model = build_model(meta)
@@ -228,6 +299,29 @@ def test_segmentation_evaluator_matches_reference_fixture():
     np.testing.assert_array_equal(res["summary_stats"].data.numpy(), z["summary_stats"])
     vol = LabelMapEvaluator("pred")(subjects)["subject_stats"][["volume"]].to_numpy(dtype=np.float64)
     np.testing.assert_array_equal(vol, z["volumes"])
+
+
+def test_segmentation_evaluator_with_labels_outside_label_values():
+    """label_values lists a SUBSET of the labels present: a voxel with target == v and an unlisted or
+    larger prediction is a false negative, as the reference's boolean masks count it (segmentation_evaluator.py:69-77)."""
+    from segmentation_pipeline import _tio
+    from segmentation_pipeline.evaluators import LabelMapEvaluator, SegmentationEvaluator
+    rng = np.random.default_rng(31)
+    shape = (1, 24, 20, 18)
+    pred = rng.integers(0, 7, size=shape)        # labels 0..6 present
+    targ = rng.integers(0, 7, size=shape)
+    label_values = {"a": 1, "c": 3}              # only two of them are evaluated; 4, 5, 6 exceed max(label_values)
+    stats = list(evalstats.STATS)
+    subject = _tio.Subject(name="s", pred=_tio.LabelMap(tensor=torch.from_numpy(pred), label_values=label_values),
+                           targ=_tio.LabelMap(tensor=torch.from_numpy(targ), label_values=label_values))
+    res = SegmentationEvaluator("pred", "targ", stats_to_output=stats)([subject])
+    ref = evalstats.segmentation_stats(pred, targ, label_values, stats)
+    for i, name in enumerate(label_values):
+        row = res["subject_stats"].iloc[i]
+        for st in stats:
+            assert float(row[st]) == ref[name][st], (name, st)
+    vol = LabelMapEvaluator("pred")([subject])["subject_stats"]["volume"].to_numpy()
+    assert list(vol) == list(evalstats.label_volumes(pred, label_values).values())
 
 
 def test_slab_mode_single_rank_equals_patch_predict():
