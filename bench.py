@@ -47,15 +47,31 @@ WORKLOAD = ("config2: msseg2 ModularUNet 2->2 filters [40,40,80,80,120,120] dept
 
 
 # ------------------------------------------------------------------------------------------------- synthetic inputs
-def synthetic_volume(seed: int) -> torch.Tensor:
-    """Smooth-ish content in [-1, 1]: low-pass filtered noise + 0.1 * white noise."""
+def synthetic_volume(seed: int, with_mask: bool = False):
+    """Lesion-like content (the reference's msseg2 data are FLAIR volumes with small bright MS lesions): a smooth
+    low-amplitude background (low-pass filtered noise) + 0.05 * white noise, and ~60 compact
+    ellipsoidal lesions (semi-axes 6..14 voxels) that carry a fixed two-channel signature.  ``with_mask`` also
+    returns the lesion mask (uint8), which is the target the confident read-out head was fitted to and the target
+    of the Dice / confusion step."""
     g = torch.Generator().manual_seed(1234 + seed)
     c, w, h, d = VOLUME
-    coarse = torch.randn(1, c, w // 4, h // 4, d // 4, generator=g)
-    smooth = torch.nn.functional.interpolate(coarse, size=(w, h, d), mode="trilinear", align_corners=False)[0]
-    vol = smooth + 0.1 * torch.randn(c, w, h, d, generator=g)
-    vol = vol - vol.amin()
-    return (vol / vol.amax() * 2 - 1).contiguous()
+    coarse = torch.randn(1, c, w // 16, h // 16, d // 16, generator=g)
+    vol = 0.15 * torch.nn.functional.interpolate(coarse, size=(w, h, d), mode="trilinear", align_corners=False)[0]
+    vol += 0.05 * torch.randn(c, w, h, d, generator=g)
+    mask = torch.zeros((w, h, d), dtype=torch.bool)
+    n_lesions = 60
+    centres = torch.rand(n_lesions, 3, generator=g) * torch.tensor([w, h, d], dtype=torch.float32)
+    radii = 6 + 8 * torch.rand(n_lesions, 3, generator=g)
+    for ctr, r in zip(centres.tolist(), radii.tolist()):
+        lo = [max(int(ctr[a] - r[a]) - 1, 0) for a in range(3)]
+        hi = [min(int(ctr[a] + r[a]) + 2, (w, h, d)[a]) for a in range(3)]
+        zz, yy, xx = torch.meshgrid(*[torch.arange(lo[a], hi[a], dtype=torch.float32) for a in range(3)], indexing="ij")
+        inside = ((zz - ctr[0]) / r[0]) ** 2 + ((yy - ctr[1]) / r[1]) ** 2 + ((xx - ctr[2]) / r[2]) ** 2 < 1
+        mask[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] |= inside
+    sig = torch.tensor([1.0, -0.6])[:c]
+    vol += sig[:, None, None, None] * mask[None].float()
+    vol = vol.contiguous()
+    return (vol, mask.to(torch.uint8)) if with_mask else vol
 
 
 def perturb_bn(model, seed: int = 1) -> None:
@@ -77,7 +93,25 @@ def build_model():
                           upsample_class=M.BlurConvTranspose3d,
                           upsample_params={'kernel_size': 3, 'stride': 2, 'padding': 1, 'output_padding': 0})
     perturb_bn(model)
+    load_readout(model)
     return model.eval()
+
+
+READOUT = os.path.join(ROOT, "tests", "golden", "readout_msseg2.npz")
+
+
+def load_readout(model) -> bool:
+    """Confident head: out_conv = the linear read-out fitted once on the CPU oracle's features
+    of this very model / volume distribution by oracle/make_readout.py and committed as a small fixture -- so that
+    the bench's label check counts every voxel instead of measuring the last bits of a p ~ 0.5 random head."""
+    if not os.path.exists(READOUT):
+        return False
+    z = np.load(READOUT)
+    with torch.no_grad():
+        model.out_conv.weight.zero_()
+        model.out_conv.weight[:, :, 1, 1, 1] = torch.from_numpy(z["weight"])
+        model.out_conv.bias.copy_(torch.from_numpy(z["bias"]))
+    return True
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -123,47 +157,56 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(threads: int, n_patches: int = 1):
-    """The reference's CPU path (oracle port: oracle/unet.py + oracle/grid.py) on `n_patches` of the 144 patches:
-    extraction + fp32 forward + overlap-add per patch.  Returns seconds per patch."""
-    from oracle import grid as ogrid, unet
-    torch.set_num_threads(threads)
-    model = build_model()
-    sd = {k: v.clone() for k, v in model.state_dict().items()}
-    cfg = {"depth": 6, "filters": FILTERS, "block": {"residual": True}, "down": "blur", "up": "blur"}
-    vol = synthetic_volume(0).numpy()
-    padded = ogrid.pad_volume(vol, OVERLAP, PADDING)
-    loc = ogrid.grid_locations(padded.shape[1:], PATCH, OVERLAP)
-    assert len(loc) == N_PATCHES
-    state = {"padded": padded, "loc": loc, "sd": sd, "cfg": cfg,
-             "out": np.zeros((2, *padded.shape[1:]), np.float32), "cnt": np.zeros((2, *padded.shape[1:]), np.float32)}
+ORACLE_CFG = {"depth": 6, "filters": FILTERS, "block": {"residual": True}, "down": "blur", "up": "blur"}
+SAMPLE_PATCHES = (5, 23, 41, 59, 77, 95, 113, 131)      # spread over the 144-patch grid (lesions in every one)
 
-    def run(first: int) -> float:
+
+class CpuReference:
+    """The reference's CPU path (oracle port: oracle/unet.py + oracle/grid.py -- the reference is pure Python over
+    ATen + torchio and cannot be imported on the GPU box) for single patches of the config-2 volume:
+    GridSampler crop + fp32 forward + GridAggregator '+='.  Used by the cpu_baseline leg and by --impl reference."""
+
+    def __init__(self, threads: int):
+        from oracle import grid as ogrid, unet
+        torch.set_num_threads(threads)
+        self.ogrid, self.unet = ogrid, unet
+        model = build_model()
+        self.sd = {k: v.clone() for k, v in model.state_dict().items()}
+        vol = synthetic_volume(0).numpy()
+        self.padded = ogrid.pad_volume(vol, OVERLAP, PADDING)
+        self.loc = ogrid.grid_locations(self.padded.shape[1:], PATCH, OVERLAP)
+        assert len(self.loc) == N_PATCHES
+        self.out = np.zeros((2, *self.padded.shape[1:]), np.float32)
+        self.cnt = np.zeros((2, *self.padded.shape[1:]), np.float32)
+        self.outputs = {}
+
+    def patch_input(self, i: int) -> np.ndarray:
+        return self.ogrid.extract_patches(self.padded, self.loc[i % N_PATCHES][None])
+
+    def run_patch(self, i: int, keep: bool = False) -> float:
         t0 = time.perf_counter()
-        for i in range(first, first + n_patches):
-            l = loc[i % N_PATCHES]
-            patch = ogrid.extract_patches(padded, l[None])
-            with torch.no_grad():
-                y = unet.modular_unet_forward(sd, torch.from_numpy(patch), cfg).numpy()
-            i0, j0, k0, i1, j1, k1 = l
-            state["out"][:, i0:i1, j0:j1, k0:k1] += y[0]
-            state["cnt"][:, i0:i1, j0:j1, k0:k1] += 1
-        return (time.perf_counter() - t0) / n_patches
+        l = self.loc[i % N_PATCHES]
+        patch = self.patch_input(i)
+        with torch.no_grad():
+            y = self.unet.modular_unet_forward(self.sd, torch.from_numpy(patch), ORACLE_CFG).numpy()
+        i0, j0, k0, i1, j1, k1 = l
+        self.out[:, i0:i1, j0:j1, k0:k1] += y[0]
+        self.cnt[:, i0:i1, j0:j1, k0:k1] += 1
+        dt = time.perf_counter() - t0
+        if keep:
+            self.outputs[i] = y[0]
+        return dt
 
-    return run, state
-
-
-def cpu_finalize_seconds(state) -> float:
-    """divide + crop + argmax of the full padded volume on the CPU (the reference's get_output_tensor +
-    CustomArgMax), measured once."""
-    out = torch.from_numpy(state["out"])
-    cnt = torch.from_numpy(np.maximum(state["cnt"], 1))
-    t0 = time.perf_counter()
-    probs = torch.true_divide(out, cnt)                       # GridAggregator.get_output_tensor
-    b = OVERLAP // 2
-    probs = probs[:, b:-b, b:-b, b:-b]                        # torchio Crop of the padded border
-    torch.argmax(probs, dim=0, keepdim=True)                  # CustomArgMax (custom_label_transforms.py:267)
-    return time.perf_counter() - t0
+    def finalize_seconds(self) -> float:
+        """divide + crop + argmax of the full padded volume (get_output_tensor + CustomArgMax), measured once."""
+        out = torch.from_numpy(self.out)
+        cnt = torch.from_numpy(np.maximum(self.cnt, 1))
+        t0 = time.perf_counter()
+        probs = torch.true_divide(out, cnt)                       # GridAggregator.get_output_tensor
+        b = OVERLAP // 2
+        probs = probs[:, b:-b, b:-b, b:-b]                        # torchio Crop of the padded border
+        torch.argmax(probs, dim=0, keepdim=True)                  # CustomArgMax (custom_label_transforms.py:267)
+        return time.perf_counter() - t0
 
 
 def run_reference_arm(args) -> None:
@@ -171,21 +214,33 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    run, state = cpu_reference_sample(threads)
-    for w in range(args.warmup):
-        run(w)
-    times = [run(args.warmup + k) for k in range(args.steps)]
-    t_fin = cpu_finalize_seconds(state)
+    ref = CpuReference(threads)
+    # bounded sample per step so that the whole --steps/--warmup run ends within a few minutes; at least 8 patches
+    # are timed in total
+    per_step = 8 if args.steps <= 2 else (3 if args.steps <= 8 else 1)
+    per_step = max(per_step, -(-8 // max(args.steps, 1)))
+    k = 0
+    for _ in range(args.warmup):
+        ref.run_patch(SAMPLE_PATCHES[k % len(SAMPLE_PATCHES)])
+        k += 1
+    times = []
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            times.append(ref.run_patch(SAMPLE_PATCHES[k % len(SAMPLE_PATCHES)] + k // len(SAMPLE_PATCHES)))
+            k += 1
+    t_fin = ref.finalize_seconds()
     t_patch = sum(times) / len(times)
     vox = VOLUME[1] * VOLUME[2] * VOLUME[3]
     t_volume = N_PATCHES * t_patch + t_fin
     value = vox / t_volume / 1e6
-    sample = (f"1 of {N_PATCHES} patches per step (extract + fp32 forward + overlap-add), extrapolated x{N_PATCHES}; "
-              f"divide/crop/argmax of the padded volume measured once ({t_fin:.2f} s) and added")
+    sample = (f"{per_step} of {N_PATCHES} patches per step, {len(times)} timed in total (extract + fp32 forward + "
+              f"overlap-add; {t_patch:.2f} s per patch, min {min(times):.2f} max {max(times):.2f}), extrapolated "
+              f"x{N_PATCHES}; divide/crop/argmax of the padded volume measured once ({t_fin:.2f} s) and added")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_volume * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.replace("bf16", "fp32 on host CPU"), "sample": sample},
+            "config": {"workload": WORKLOAD, "arithmetic": "fp32 on the host CPU (the reference's own precision)",
+                       "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -201,6 +256,102 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def committed_traffic():
+    """DRAM bytes per launch of the dominant conv layer from the committed ncu --set full capture
+    (profiles/roofline_traffic.json, written by tools/ncu_summary.py from the .ncu-rep); None when absent."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    return t.get("dram_bytes_per_launch"), t
+
+
+class ConvTimer:
+    """CUDA-event pair around every conv_tc launch INSIDE the timed steps (on the launching stream); an event record
+    costs ~1 us of host time against ~700 us per launch."""
+
+    def __init__(self, b200seg):
+        self.lib = b200seg
+        self.orig = b200seg.conv3d_tc
+        self.pairs = []
+
+    def __enter__(self):
+        orig, pairs = self.orig, self.pairs
+
+        def traced(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(*a, **k)
+            e.record()
+            pairs.append((s, e))
+
+        self.lib.conv3d_tc = traced
+        return self
+
+    def __exit__(self, *exc):
+        self.lib.conv3d_tc = self.orig
+        return False
+
+    def total_ms(self) -> float:
+        return sum(s.elapsed_time(e) for s, e in self.pairs)
+
+
+def gpu_incumbent(ref: "CpuReference", device, n_batch: int = 8) -> dict:
+    """The 'existing' GPU path (SURVEY.md section 2.1 'bar to beat'): the same network as plain ATen/cuDNN calls
+    (oracle/unet.py's functional forward on CUDA tensors) under torch.autocast(bfloat16) with channels_last_3d input,
+    on the same box, same weights, batches of 8 patches.  Part of the baseline leg (rank 0, N = 1 only)."""
+    sd = {k: v.to(device) for k, v in ref.sd.items()}
+    x = torch.from_numpy(np.concatenate([ref.patch_input(i) for i in SAMPLE_PATCHES[:n_batch]])).to(device)
+    x = x.contiguous(memory_format=torch.channels_last_3d)
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(2):
+                y = ref.unet.modular_unet_forward(sd, x, ORACLE_CFG)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record()
+            for _ in range(reps):
+                y = ref.unet.modular_unet_forward(sd, x, ORACLE_CFG)
+            e1.record()
+            torch.cuda.synchronize()
+        ms_batch = e0.elapsed_time(e1) / reps
+    except Exception as exc:  # noqa: BLE001  (cuDNN may not have a bf16 NDHWC kernel for every layer)
+        return {"unavailable": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    vox = VOLUME[1] * VOLUME[2] * VOLUME[3]
+    ms_volume = ms_batch * N_PATCHES / n_batch
+    return {"value": vox / (ms_volume * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume_forward_only": ms_volume,
+            "tflops": FLOP_PER_PATCH * n_batch / (ms_batch * 1e-3) / 1e12,
+            "what": f"ATen/cuDNN functional forward, autocast bf16 + channels_last_3d, {n_batch} patches per batch, "
+                    f"{reps} timed batches, extrapolated x{N_PATCHES // n_batch}; forward only (no extraction / "
+                    f"aggregation / argmax)",
+            "out_dtype": str(y.dtype)}
+
+
+def label_check(ref: "CpuReference", model, device) -> dict:
+    """Unfiltered argmax agreement of the CUDA bf16 path with the CPU fp32 oracle on the sample patches the baseline
+    leg just ran (same weights incl. the fitted head), plus the oracle's top-2 margin histogram of the disagreeing
+    voxels."""
+    idx = sorted(ref.outputs)
+    x = torch.from_numpy(np.concatenate([ref.patch_input(i) for i in idx])).to(device)
+    with torch.no_grad():
+        got = model(x).float().cpu()
+    want = torch.from_numpy(np.stack([ref.outputs[i] for i in idx]))
+    lw, lg = want.argmax(1), got.argmax(1)
+    top2 = torch.topk(want, 2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    dis = margin[lw != lg]
+    edges = [0.0, 1e-4, 1e-3, 1e-2, 5e-2, 1.0 + 1e-6]
+    return {"patches": len(idx), "voxels": int(lw.numel()), "agreement": float((lw == lg).float().mean()),
+            "class_fractions": [round(float((lw == c).float().mean()), 4) for c in range(want.shape[1])],
+            "median_margin": float(margin.median()), "disagreeing": int(dis.numel()),
+            "disagree_margin_hist": dict(zip(["<1e-4", "<1e-3", "<1e-2", "<5e-2", ">=5e-2"],
+                                             [int(((dis >= lo) & (dis < hi)).sum()) for lo, hi in zip(edges[:-1], edges[1:])])),
+            "max_abs_prob_err": float((want - got).abs().max()),
+            "head": "fitted read-out (tests/golden/readout_msseg2.npz)" if os.path.exists(READOUT) else "random init"}
+
+
 def run_gpu_arm(args) -> None:
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,15 +360,11 @@ def run_gpu_arm(args) -> None:
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) to stdout
-        # unless it is given a file
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200SEG_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl.%h.%p.log")
-                              if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else os.devnull)
-        dist.init_process_group("nccl", device_id=device)
+        dist.init_process_group("nccl", device_id=device)     # NCCL_DEBUG & co. are left exactly as the launcher set them
 
     import b200seg
     from segmentation_pipeline import _tio
+    from segmentation_pipeline.evaluators.segmentation_evaluator import counts_from_cm
     from segmentation_pipeline.models import set_precision
     from segmentation_pipeline.prediction import PatchPredict
     b200seg.load_library()   # raises if the CUDA extension is missing: no fallback
@@ -225,9 +372,10 @@ def run_gpu_arm(args) -> None:
     model = build_model().to(device)
     predictor = PatchPredict(patch_batch_size=PATCH_BATCH, patch_size=PATCH, patch_overlap=OVERLAP,
                              padding_mode=PADDING, overlap_mode="average")
-    vol_host = synthetic_volume(rank).pin_memory()
+    vol, mask = synthetic_volume(rank, with_mask=True)
+    vol_host = vol.pin_memory()
     vol_dev = vol_host.to(device)
-    target = (torch.rand(VOLUME[1:], generator=torch.Generator().manual_seed(99 + rank)) > 0.5).to(torch.uint8).to(device)
+    target = mask.to(device)
     cm = torch.zeros((2, 2), dtype=torch.int64, device=device)
     vox = VOLUME[1] * VOLUME[2] * VOLUME[3]
 
@@ -254,16 +402,26 @@ def run_gpu_arm(args) -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    warmup = max(args.warmup, 3)
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             step_resident()
+        cm.zero_()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         launches0 = b200seg.launches()
-        ms = timed(step_resident, args.steps)
+        with ConvTimer(b200seg) as conv_timer:             # events INSIDE the timed steps
+            ms = timed(step_resident, args.steps)
         gpu_launches = b200seg.launches() - launches0
         clocks = sampler.stop() if rank == 0 else None
+        conv_ms = conv_timer.total_ms() / args.steps
+        n_conv = len(conv_timer.pairs) // args.steps
+        # Dice of the lesion class from the accumulated device confusion matrix (cohort: summed over ranks, exact)
+        if world > 1:
+            dist.all_reduce(cm, op=dist.ReduceOp.SUM)
+        tp, fp, tn, fn = counts_from_cm(cm.cpu(), 1)
+        dice = 2 * tp / max(2 * tp + fp + fn, 1)
 
         # ---- end to end through the reference-facing API: pinned host volume in, host probabilities out
         subject = _tio.Subject(X=_tio.ScalarImage(tensor=vol_host), name=f"bench{rank}")
@@ -271,32 +429,14 @@ def run_gpu_arm(args) -> None:
         def step_e2e():
             predictor.predict(model, device, [subject], {"label_values": {"lesion": 1}})
 
-        for _ in range(max(args.warmup, 3)):     # also warms the pinned-host allocator (two 100 MB blocks alternate)
+        for _ in range(warmup):     # also warms the pinned-host allocator (two 100 MB blocks alternate)
             step_e2e()
-        ms_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
-        e2e_steps = max(1, min(args.steps, 3))
-
-        # ---- roofline of the dominant kernel (conv_tc): per-launch CUDA events in a separate instrumented pass
-        events = []
-        orig = b200seg.conv3d_tc
-
-        def traced(*a, **k):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            orig(*a, **k)
-            e.record()
-            events.append((s, e))
-
-        b200seg.conv3d_tc = traced
-        try:
-            step_resident()
-            torch.cuda.synchronize()
-        finally:
-            b200seg.conv3d_tc = orig
-        conv_ms = sum(s.elapsed_time(e) for s, e in events)
-        n_conv = len(events)
+        e2e_steps = max(1, min(args.steps, 5))
+        ms_e2e = timed(step_e2e, e2e_steps)
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peak_tf, peak_gbs, peak_src = measured_peaks()
     ms_per_step = ms / args.steps
@@ -305,8 +445,9 @@ def run_gpu_arm(args) -> None:
     achieved_tf = flop_step / (conv_ms * 1e-3) / 1e12
     e2e_ms = ms_e2e / e2e_steps
     vol_bytes = vol_host.numel() * 4
+    traffic, traffic_meta = committed_traffic()
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "patch_batch": PATCH_BATCH, "volumes_per_step": world,
@@ -318,30 +459,32 @@ def run_gpu_arm(args) -> None:
         "gpu_launches": gpu_launches,
         # SURVEY.md section 8(d) also asks for patch-voxels per second (network throughput incl. the 8x overlap)
         "patch_mvoxel_per_s": world * N_PATCHES * PATCH ** 3 / (ms_per_step * 1e-3) / 1e6,
+        "dice_lesion": dice,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (up_blocks.0 conv0||res_conv,
-                     # 48 patches) from the committed ncu --set full capture profiles/r01_ncu_full_up0_conv0res_b48_raw.csv
-                     "traffic": 14.721e9,
-                     "traffic_note": "bytes per launch of the dominant conv layer (80->80 ch, 48 x 96^3); algorithmic "
-                                     "bytes of that launch are 13.59e9 (activations in + out once)",
+                     "frac_of_spec_2250": achieved_tf / 2250.0,
+                     "traffic": traffic, "traffic_source": traffic_meta,
                      "kernel": "conv_tc_kernel",
                      "launches_per_step": n_conv, "kernel_ms_per_step": conv_ms,
+                     "timing": "sum of CUDA-event pairs around every conv_tc launch inside the timed steps, averaged",
                      "share_of_step": conv_ms / ms_per_step,
                      "algorithmic_flop_per_step": flop_step, "peak_source": peak_src},
     }
     if world == 1:
         threads = os.cpu_count() or 1
-        run, state = cpu_reference_sample(threads)
-        run(0)
-        t_patch = (run(1) + run(2)) / 2
-        t_fin = cpu_finalize_seconds(state)
+        ref = CpuReference(threads)
+        ref.run_patch(SAMPLE_PATCHES[0])                                  # warm-up
+        times = [ref.run_patch(i, keep=True) for i in SAMPLE_PATCHES]
+        t_fin = ref.finalize_seconds()
+        t_patch = sum(times) / len(times)
         t_volume = N_PATCHES * t_patch + t_fin
         line["cpu_baseline"] = {"value": vox / t_volume / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"2 of {N_PATCHES} patches (extract + fp32 forward + overlap-add) after 1 warm-up, "
-                                          f"extrapolated x{N_PATCHES}, plus divide/crop/argmax of the padded volume "
-                                          f"({t_fin:.2f} s)"}
+                                "sample": f"{len(times)} of {N_PATCHES} patches (extract + fp32 forward + overlap-add, "
+                                          f"{t_patch:.2f} s each) after 1 warm-up, extrapolated x{N_PATCHES}, plus "
+                                          f"divide/crop/argmax of the padded volume ({t_fin:.2f} s)"}
+        line["label_check"] = label_check(ref, model, device)
+        line["gpu_incumbent"] = gpu_incumbent(ref, device)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

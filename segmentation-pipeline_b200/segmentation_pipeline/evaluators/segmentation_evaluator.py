@@ -41,15 +41,16 @@ def confusion_counts(pred: torch.Tensor, target: torch.Tensor, label_values: Dic
         cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=device)
         b200seg.confusion(pred, target, num_classes, cm)
     cm = cm.cpu()
-    total = pred.numel()
-    out = {}
-    for name, value in label_values.items():
-        v = int(value)
-        tp = int(cm[v, v])
-        fp = int(cm[:, v].sum()) - tp
-        fn = int(cm[v, :].sum()) - tp
-        out[name] = (tp, fp, total - tp - fp - fn, fn)
-    return out
+    return {name: counts_from_cm(cm, int(value)) for name, value in label_values.items()}
+
+
+def counts_from_cm(cm: torch.Tensor, value: int):
+    """(TP, FP, TN, FN) of one label from the joint histogram cm[target][pred] (exact integers)."""
+    total = int(cm.sum())
+    tp = int(cm[value, value])
+    fp = int(cm[:, value].sum()) - tp
+    fn = int(cm[value, :].sum()) - tp
+    return tp, fp, total - tp - fp - fn, fn
 
 
 class SegmentationEvaluator(Evaluator):
