@@ -16,7 +16,7 @@ except Exception:  # noqa: BLE001
     HAVE_TORCHIO = False
 
 
-class Image(dict):
+class _Image(dict):
     """dict-like image: ``image['data']`` / ``image.data`` (C, W, H, D) tensor, ``affine``, free attributes."""
 
     def __init__(self, tensor=None, affine=None, **attributes):
@@ -45,24 +45,24 @@ class Image(dict):
         return tuple(self["data"].shape[1:])
 
 
-class ScalarImage(Image):
+class _ScalarImage(_Image):
     pass
 
 
-class LabelMap(Image):
+class _LabelMap(_Image):
     pass
 
 
-class Subject(dict):
+class _Subject(dict):
     def add_image(self, image, name):
         self[name] = image
 
     def get_images_dict(self, intensity_only=True, include=None, exclude=None):
         out = {}
         for k, v in self.items():
-            if not isinstance(v, Image):
+            if not isinstance(v, _Image):
                 continue
-            if intensity_only and isinstance(v, LabelMap):
+            if intensity_only and isinstance(v, _LabelMap):
                 continue
             if include is not None and k not in include:
                 continue
@@ -79,6 +79,14 @@ class Subject(dict):
         return self.get_first_image().spatial_shape
 
 
+# With torchio importable the predictors hand real tio objects to the caller (the reference's trainer, transforms and
+# evaluators expect them); the stand-ins above only serve torchio-less scripts (bench.py, smoke()).
+if HAVE_TORCHIO:
+    Image, ScalarImage, LabelMap, Subject = tio.Image, tio.ScalarImage, tio.LabelMap, tio.Subject
+else:
+    Image, ScalarImage, LabelMap, Subject = _Image, _ScalarImage, _LabelMap, _Subject
+
+
 def make_label_map(tensor: torch.Tensor, **attributes):
     if HAVE_TORCHIO:
         return tio.LabelMap(tensor=tensor, **attributes)
@@ -88,6 +96,12 @@ def make_label_map(tensor: torch.Tensor, **attributes):
 def enforce_consistent_affine(subject, source_image_name="X"):
     """``EnforceConsistentAffine(source_image_name)(subject)`` of the reference
     (transforms/enforce_consistent_affine.py:14-29): every other image takes the source image's affine."""
+    if HAVE_TORCHIO:
+        try:    # overlay mode: the reference's own transform (returns a copy and records itself in the history)
+            from .transforms import EnforceConsistentAffine
+            return EnforceConsistentAffine(source_image_name=source_image_name)(subject)
+        except ImportError:
+            pass
     if source_image_name not in subject:
         return subject
     source = subject[source_image_name]

@@ -246,24 +246,83 @@ def _argmax_labels(image) -> torch.Tensor:
     return labels.cpu()[None]
 
 
-def add_evaluation_labels(subjects: Sequence[Any]):
-    """Adds 'y_pred_eval' / 'y_eval' label maps (int64, (1, W, H, D)) next to 'y_pred' / 'y'.
+_DEVICE_ARGMAX = []
 
-    The reference (prediction.py:155-170) inverts the subject's label-transform history; for the one-hot
-    targets every shipped config uses, that inverse is ``CustomArgMax``
-    (transforms/custom_label_transforms.py:264-272), which is what runs here, on the device.  Subjects whose
-    history contains other invertible label transforms need real torchio and are outside this path."""
+
+def _device_argmax_class():
+    """``CustomArgMax`` (reference transforms/custom_label_transforms.py:253-272) with the argmax on the device: same
+    constructor, history entry and inverse, so that it can stand in for it inside an inverted transform history."""
+    if not _DEVICE_ARGMAX:
+        from .transforms import CustomArgMax
+
+        class DeviceArgMax(CustomArgMax):
+            def apply_transform(self, subject):
+                for image in self.get_images(subject):
+                    image.set_data(_argmax_labels(image))
+                    image['one_hot'] = False
+                    if LABELS_KEY in image:
+                        del image[LABELS_KEY]
+                return subject
+
+        _DEVICE_ARGMAX.append(DeviceArgMax)
+    return _DEVICE_ARGMAX[0]
+
+
+def _swap_argmax(transform):
+    """Replaces every CustomArgMax of a (nested) Compose by its device version."""
+    from .transforms import CustomArgMax
+    compose = type(transform)
+    out = []
+    for t in transform:
+        if isinstance(t, compose):
+            out.append(_swap_argmax(t))
+        elif type(t) is CustomArgMax:
+            out.append(_device_argmax_class()(num_classes=t.num_classes, **t.kwargs))
+        else:
+            out.append(t)
+    return compose(out)
+
+
+def _history_inverse(subject):
+    """The evaluation transform of reference prediction.py:157-160: the subject's applied-transform history, filtered
+    to the label-affecting transforms, inverted.  None when the subject carries no torchio history (the torchio-less
+    stand-in subjects of bench.py / smoke())."""
+    if not (_tio.HAVE_TORCHIO and hasattr(subject, "get_composed_history")):
+        return None
+    try:
+        from torchio.transforms.preprocessing.label.label_transform import LabelTransform
+        from .transforms import ConcatenateImages, CopyProperty, RenameProperty, filter_transform
+    except ImportError:          # stand-alone package: the reference's transform classes are not present
+        return None
+    transform = subject.get_composed_history()
+    label_transform = filter_transform(transform, include_types=[LabelTransform, CopyProperty, RenameProperty,
+                                                                 ConcatenateImages])
+    return _swap_argmax(label_transform.inverse(warn=False))
+
+
+def add_evaluation_labels(subjects: Sequence[Any]):
+    """Adds 'y_pred_eval' / 'y_eval' next to 'y_pred' / 'y' (reference prediction.py:155-170).
+
+    With torchio subjects (the reference's callers) this is the reference's algorithm: the inverse of the
+    label-transform part of the subject's history is applied to ``Subject({'y': image})`` -- remaps, merges, copies and
+    renames run as the reference's own transform classes; the ``CustomArgMax`` that inverts ``CustomOneHot`` runs on
+    the device (``b200seg_argmax``, or the uint8 label map ``PatchPredict`` already produced there).
+    Without torchio (bench.py / smoke() stand-in subjects, which have no history) multi-channel maps are argmaxed --
+    the inverse of the one-hot targets every shipped config uses (int64, (1, W, H, D), ties -> lowest index)."""
     for subject in subjects:
+        evaluation_transform = _history_inverse(subject)
         for name, eval_name in (("y_pred", "y_pred_eval"), ("y", "y_eval")):
             if name not in subject:
                 continue
             source = subject[name]
+            if evaluation_transform is not None:
+                image = evaluation_transform(_tio.Subject({'y': source})).get_first_image()
+                if LABELS_KEY in image:
+                    del image[LABELS_KEY]
+                subject.add_image(image, eval_name)
+                continue
             attributes = {k: copy.deepcopy(v) for k, v in dict(source).items()
                           if k not in ("data", "affine", LABELS_KEY, "tensor", "path", "type", "stem")}
             attributes["one_hot"] = False
-            image = _tio.make_label_map(_argmax_labels(source), affine=source["affine"], **attributes) \
-                if not _tio.HAVE_TORCHIO else _tio.make_label_map(_argmax_labels(source), affine=source.affine)
-            if _tio.HAVE_TORCHIO:
-                for k, v in attributes.items():
-                    image[k] = v
+            image = _tio.make_label_map(_argmax_labels(source), affine=source["affine"], **attributes)
             subject.add_image(image, eval_name)
