@@ -71,7 +71,9 @@ typedef struct b200seg_epilogue {
     float* out_ncdhw;        /* softmax / final output, fp32 [N][cout][Z][Y][X]; NULL when unused */
     int32_t softmax;         /* 1: softmax over channels before writing out_ncdhw; 0: raw values */
     int32_t slope01;         /* 1: the caller guarantees 0 <= slope[c] <= 1 (ReLU / LeakyReLU / none), which lets the
-                                tensor-core epilogue use max(v, v*slope); 0: general v > 0 ? v : v*slope */
+                                tensor-core epilogue use max(v, v*slope); 0: general v > 0 ? v : v*slope;
+                                2: the caller guarantees scale == 1, shift == 0, slope == 1 for every channel (the blur
+                                convolutions): the tensor-core epilogue is a plain fp32 -> bf16 conversion */
 } b200seg_epilogue;
 
 /* ------------------------------------------------------------------------------------------------ misc */

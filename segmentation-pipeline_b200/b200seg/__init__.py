@@ -191,11 +191,12 @@ def unpack_ncdhw(src: View, dst: torch.Tensor) -> None:
 def make_epilogue(scale: torch.Tensor, shift: torch.Tensor, slope: torch.Tensor, dst0: View = NULL_VIEW,
                   dst1: View = NULL_VIEW, split: int = 0, residual: View = NULL_VIEW,
                   out_ncdhw: Optional[torch.Tensor] = None, softmax: bool = False,
-                  slope01: bool = False) -> Epilogue:
-    """``slope01``: the caller guarantees every slope is in [0, 1] (enables the cheaper max(v, v*slope) form)."""
+                  slope01: int = 0) -> Epilogue:
+    """``slope01``: 1 = the caller guarantees every slope is in [0, 1] (enables the cheaper max(v, v*slope) form);
+    2 = identity epilogue (scale 1, shift 0, slope 1 for every channel)."""
     _require_cuda(scale, shift, slope, out_ncdhw)
     return Epilogue(scale.data_ptr(), shift.data_ptr(), slope.data_ptr(), dst0, dst1, split, residual,
-                    0 if out_ncdhw is None else out_ncdhw.data_ptr(), 1 if softmax else 0, 1 if slope01 else 0)
+                    0 if out_ncdhw is None else out_ncdhw.data_ptr(), 1 if softmax else 0, int(slope01))
 
 
 def conv3d_direct(inp: View, weight: torch.Tensor, cout: int, ksize: int, stride: int, pad: int, transposed: bool,

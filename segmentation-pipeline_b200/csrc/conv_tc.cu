@@ -18,6 +18,8 @@
 //     image [step][k-half][row][8], row = (plane block, cout), plus 16 zero rows so that N rounded up to a
 //     multiple of 16 multiplies zeros ("spill" columns add 0 to the next plane's accumulator).
 //   * accumulators: TZ planes x Cpad fp32 columns in TMEM; first touch of a plane uses accumulate=0.
+//     Up to 120 output channels per launch (TZ = 2); the host keeps large layers at <= 80 (TZ = 3) and uses the wide
+//     form only on the small deep levels, where a second launch costs more than the thinner z tiles.
 //
 //   * K3T (final layer, Cout <= 4): the nine in-plane taps are accumulator COLUMNS instead of MMA steps -- one
 //     unshifted MMA per chunk group, the epilogue sums each voxel's nine neighbours through shared memory; tiles
@@ -355,11 +357,25 @@ __device__ __forceinline__ void epi_load(const EpiArgs& a, int q, int cc0, uint3
     }
 }
 
-template <int S, bool RES>
+template <int S, bool RES, bool ID>
 __device__ __forceinline__ void epi_finish(const EpiArgs& a, int q, int cc0, const uint32_t (&r)[3][8],
                                            const uint4 (&res)[3]) {
     if (!a.valid) return;
     const size_t qoff = static_cast<size_t>(static_cast<uint32_t>(q) * a.plane);
+    if constexpr (ID) {
+        // identity epilogue (scale 1, shift 0, no activation, no residual, one destination): the blur convolutions
+        // of the stride-2 / transposed layers.  tcgen05.ld -> 4 packs -> one 16-byte store per chunk.
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                oh[k] = __floats2bfloat162_rn(__uint_as_float(r[j][2 * k]), __uint_as_float(r[j][2 * k + 1]));
+            a.p0[qoff + static_cast<size_t>((cc0 + j) * a.cs)] = o;
+        }
+        return;
+    }
     const float4* par = reinterpret_cast<const float4*>(a.s_par + cc0 * 24);
 #pragma unroll
     for (int j = 0; j < S; ++j) {
@@ -416,7 +432,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& a, int q, int cc0, con
 }
 
 // planes q0, q0 + qstep, ... of one accumulator set; chunks [cbeg, cbeg + NCH)
-template <int NCH, bool RES>
+template <int NCH, bool RES, bool ID = false>
 __device__ __forceinline__ void epi_planes(const EpiArgs& a, int cbeg, int q0, int qstep) {
     constexpr int S0 = NCH <= 3 ? NCH : (NCH + 1) / 2;
     constexpr int S1 = NCH - S0;
@@ -430,11 +446,11 @@ __device__ __forceinline__ void epi_planes(const EpiArgs& a, int cbeg, int q0, i
         for (;;) {
             tmem_ld_wait();
             epi_load<S1c, RES>(a, q, cbeg + S0, rB, resB);
-            epi_finish<S0, RES>(a, q, cbeg, rA, resA);
+            epi_finish<S0, RES, ID>(a, q, cbeg, rA, resA);
             const int qn = q + qstep;
             tmem_ld_wait();
             if (qn < a.nq) epi_load<S0, RES>(a, qn, cbeg, rA, resA);
-            epi_finish<S1c, RES>(a, q, cbeg + S0, rB, resB);
+            epi_finish<S1c, RES, ID>(a, q, cbeg + S0, rB, resB);
             if (qn >= a.nq) break;
             q = qn;
         }
@@ -443,13 +459,13 @@ __device__ __forceinline__ void epi_planes(const EpiArgs& a, int cbeg, int q0, i
             tmem_ld_wait();
             int qn = q + qstep;
             if (qn < a.nq) epi_load<S0, RES>(a, qn, cbeg, rB, resB);
-            epi_finish<S0, RES>(a, q, cbeg, rA, resA);
+            epi_finish<S0, RES, ID>(a, q, cbeg, rA, resA);
             if (qn >= a.nq) break;
             q = qn;
             qn = q + qstep;
             tmem_ld_wait();
             if (qn < a.nq) epi_load<S0, RES>(a, qn, cbeg, rA, resA);
-            epi_finish<S0, RES>(a, q, cbeg, rB, resB);
+            epi_finish<S0, RES, ID>(a, q, cbeg, rB, resB);
             if (qn >= a.nq) break;
             q = qn;
         }
@@ -958,9 +974,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 } else if (kEpi != 0 || e.out_ncdhw == nullptr) {
                     if constexpr (kEpi != 0 && kEpi != 5) {
                         // specialised epilogues: 10 chunks (the two warps of a lane quarter take 5 chunks each of
-                        // every plane) or 5 chunks (they take alternate planes), with or without a residual
+                        // every plane) or 5 chunks (they take alternate planes), with or without a residual;
+                        // 6 / 7: 5 / 10 chunks with the identity epilogue
                         constexpr bool kRes = kEpi == 2 || kEpi == 4;
-                        constexpr bool kByPlane = kEpi >= 3;
+                        constexpr bool kByPlane = kEpi == 3 || kEpi == 4 || kEpi == 6;
+                        constexpr bool kId = kEpi == 6 || kEpi == 7;
                         EpiArgs a;
                         a.tbase = tbase;
                         a.Cpad = Cpad;
@@ -976,8 +994,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         a.split_c8 = split_c8;
                         a.s_par = s_par;
                         for (int h = kHalves == 2 ? half : 0; h < 2; h += kHalves) {
-                            if (kByPlane) epi_planes<5, kRes>(a, 0, h, 2);
-                            else epi_planes<5, kRes>(a, 5 * h, 0, 1);
+                            if (kByPlane) epi_planes<5, kRes, kId>(a, 0, h, 2);
+                            else epi_planes<5, kRes, kId>(a, 5 * h, 0, 1);
                         }
                     } else {
                         // Work items of this warp: (plane q, round of kR chunks).  Software pipelined: the TMEM and
@@ -1167,7 +1185,7 @@ struct TcGeom {
 
 static int tc_geometry(int mode, int cin_chunks, int cout, TcGeom* g) {
     B200SEG_CHECK_ARG(mode >= 0 && mode <= 3, "conv3d_tc: bad mode %d", mode);
-    B200SEG_CHECK_ARG(cout >= 1 && cout <= 80, "conv3d_tc: cout %d not in [1,80] (split wider layers)", cout);
+    B200SEG_CHECK_ARG(cout >= 1 && cout <= 120, "conv3d_tc: cout %d not in [1,120] (split wider layers)", cout);
     B200SEG_CHECK_ARG(mode != B200SEG_TC_K3T || cout <= 4, "conv3d_tc K3T: cout %d not in [1,4]", cout);
     B200SEG_CHECK_ARG(mode != B200SEG_TC_K3T || cin_chunks <= 12, "conv3d_tc K3T: at most 96 input channels");
     B200SEG_CHECK_ARG(cin_chunks >= 1, "conv3d_tc: no input chunks");
@@ -1412,8 +1430,10 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     if (variant == 2) {
         const bool res = de.residual.data != nullptr;
         const int c8 = p.Cpad / 8;
+        const bool ident = epi->slope01 == 2 && !res && de.dst1.data == nullptr;
         if (mode == B200SEG_TC_K3T) kernel = conv_tc_kernel<2, 5>;
         else if (epi->out_ncdhw != nullptr || generic_epilogue || (c8 != 10 && c8 != 5)) kernel = conv_tc_kernel<2, 0>;
+        else if (ident) kernel = c8 == 10 ? conv_tc_kernel<2, 7> : conv_tc_kernel<2, 6>;
         else if (c8 == 10) kernel = res ? conv_tc_kernel<2, 2> : conv_tc_kernel<2, 1>;
         else kernel = res ? conv_tc_kernel<2, 4> : conv_tc_kernel<2, 3>;
     } else {

@@ -20,10 +20,21 @@ from ._plan import DOWN, K3, UP, ConvOp, Plan, PoolOp, Ref, SoftmaxOp, UpsampleO
 
 _PRECISION = [os.environ.get("B200SEG_PRECISION", "auto")]
 TRACE = None    # set to a list to record (call, extent, (start, end) CUDA events) per op (tools/profile_layers.py)
-TC_MAX_COUT = 80
+TC_MAX_COUT = 80           # output channels per launch on the large levels (3 z-planes per accumulator set)
+TC_MAX_COUT_DEEP = 120     # deep levels (>= 3): one launch for 120 channels -- they are launch-bound, not MMA-bound
+if os.environ.get("B200SEG_TC_VARIANT") == "1":
+    TC_MAX_COUT_DEEP = 80  # the two-CTAs-per-SM test variant has half the shared memory: a 120-wide weight image does not fit
 
 
 _NO_K3T = os.environ.get("B200SEG_TC_NO_K3T", "0") == "1"     # profiling hook: final layer through the plain K3 mode
+
+# CUDA graphs: the op list of a plan is a fixed sequence of ~55-160 launches over fixed buffers.  On small inputs
+# (patch_batch_size = 1 as in the reference's ms-inference.py:32, the 48 x 88 x 24 half volumes of dmri_hippo) a launch
+# lasts a few microseconds while Python + ctypes + tensor-map encoding cost tens per call, so the host is the bottleneck:
+# there the whole list is captured once per workspace and replayed.  Large batches are GPU-bound and stay eager (their
+# launches can then be timed individually).  B200SEG_GRAPHS=0 disables, =all forces graphs for every size.
+_GRAPHS = os.environ.get("B200SEG_GRAPHS", "1")
+GRAPH_MAX_VOXELS = 4 * 96 ** 3
 
 
 def set_precision(mode: str) -> None:
@@ -128,6 +139,8 @@ class CompiledPlan:
         # tensor-core path: pieces of <= TC_MAX_COUT output channels; a fused two-destination conv stays one
         # launch when it fits, otherwise each destination gets its own launches
         pieces = []
+        level = self.plan.buffers[op.src.buf][1]
+        TC_MAX_COUT = TC_MAX_COUT_DEEP if level >= 3 else globals()["TC_MAX_COUT"]
         if op.dst1 is not None and op.cout <= TC_MAX_COUT:
             pieces.append((0, op.cout, op.dst0, op.dst1, op.split, op.residual))
         else:
@@ -168,7 +181,9 @@ class CompiledPlan:
         call.tc, call.mode, call.src = tc, op.mode, op.src
         call.ksize, call.stride, call.pad, call.transposed = geom
         call.final, call.softmax, call.name = op.final, op.softmax, op.name
-        call.slope01 = bool(((op.slope >= 0.0) & (op.slope <= 1.0)).all())   # ReLU / LeakyReLU / none
+        call.slope01 = int(bool(((op.slope >= 0.0) & (op.slope <= 1.0)).all()))   # ReLU / LeakyReLU / none
+        if bool((op.scale == 1.0).all() and (op.shift == 0.0).all() and (op.slope == 1.0).all()):
+            call.slope01 = 2                                                   # identity epilogue (blur convolutions)
         return call
 
     # ------------------------------------------------------------------ workspaces
@@ -202,13 +217,42 @@ class CompiledPlan:
 
     # ------------------------------------------------------------------ run
     def run_blocked(self, n: int, z: int, y: int, x: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Runs the plan on the workspace whose 'in' buffer has already been filled; returns fp32 NCDHW."""
-        lib = _b200seg()
+        """Runs the plan on the workspace whose 'in' buffer has already been filled; returns fp32 NCDHW.
+
+        Without ``out`` the result lives in a buffer owned by the workspace (valid until the next run on it) -- the
+        sliding-window predictor consumes it immediately; small inputs replay a captured CUDA graph."""
         ws = self._workspace(n, z, y, x)
         s = self.plan.out_scale
         oz, oy, ox = ((z << s, y << s, x << s) if s >= 0 else (z >> -s, y >> -s, x >> -s))
-        if out is None:
-            out = torch.empty((n, self.plan.out_channels, oz, oy, ox), dtype=torch.float32, device=self.device)
+        if out is not None:
+            self._launch_all(ws, out, (n, z, y, x))
+            return out
+        static = ws.get("__out__")
+        if static is None:
+            static = ws["__out__"] = torch.empty((n, self.plan.out_channels, oz, oy, ox), dtype=torch.float32,
+                                                 device=self.device)
+        graph_ok = _GRAPHS != "0" and TRACE is None and (_GRAPHS == "all" or n * z * y * x <= GRAPH_MAX_VOXELS) \
+            and not torch.cuda.is_current_stream_capturing()
+        if not graph_ok:
+            self._launch_all(ws, static, (n, z, y, x))
+            return static
+        graph = ws.get("__graph__")
+        if graph is None:
+            # first call: eager (loads kernels, sets function attributes); second call: capture
+            if not ws.get("__warm__"):
+                ws["__warm__"] = True
+                self._launch_all(ws, static, (n, z, y, x))
+                return static
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._launch_all(ws, static, (n, z, y, x))
+            ws["__graph__"] = graph
+        graph.replay()
+        return static
+
+    def _launch_all(self, ws, out: torch.Tensor, extent) -> None:
+        lib = _b200seg()
+        n, z, y, x = extent
         wrote_final = False
 
         def view(ref: Optional[Ref]):
@@ -249,7 +293,6 @@ class CompiledPlan:
                 ev[1].record()
         if not wrote_final:
             lib.unpack_ncdhw(ws["out"].view(self.plan.out_channels), out)
-        return out
 
     def run(self, x: torch.Tensor) -> torch.Tensor:
         lib = _b200seg()
@@ -259,7 +302,7 @@ class CompiledPlan:
         src = x.detach().to(torch.float32).contiguous()
         ws = self._workspace(n, z, y, xx)
         lib.pack_ncdhw(src, ws["in"].view(self.plan.in_channels))
-        return self.run_blocked(n, z, y, xx)
+        return self.run_blocked(n, z, y, xx).clone()      # the workspace keeps its own output buffer
 
 
 def _slope_pad(slope, cpad):

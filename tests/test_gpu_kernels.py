@@ -335,12 +335,20 @@ TC_CASES = [
     (1, 40, 40, (3, 44, 68, 60)),     # stride-2 conv, 24 streamed images per unit
     (2, 80, 80, (4, 15, 34, 30)),     # transposed conv (4 passes per tile pair)
     (2, 40, 40, (4, 15, 34, 30)),     # transposed conv on the single-issuer schedule (default rule)
+    # 120 output channels in one launch (deep levels): TZ = 2, 15-chunk generic epilogue, single weight slot
+    (0, 120, 120, (6, 3, 3, 3)),
+    (0, 240, 120, (3, 6, 6, 6)),
+    (1, 120, 120, (4, 6, 6, 6)),
+    (2, 120, 120, (4, 3, 3, 3)),
 ]
 
 
 @pytest.mark.parametrize("mode,cin,cout,ext", TC_CASES)
 def test_conv_tc_matches_fp32_oracle(lib, mode, cin, cout, ext):
     from segmentation_pipeline.models import _plan
+    import os
+    if cout > 80 and os.environ.get("B200SEG_TC_VARIANT") == "1":
+        pytest.skip("120-wide launches need the one-CTA-per-SM shared-memory budget")
     g = torch.Generator().manual_seed(100 + mode * 31 + cin + cout)
     n = ext[0]
     x = torch.randn(n, cin, *ext[1:], generator=g).to(torch.bfloat16).float()
@@ -372,6 +380,68 @@ def test_conv_tc_matches_fp32_oracle(lib, mode, cin, cout, ext):
     lib.unpack_ncdhw(dst.view(cout, 1), got)
     assert rel_err(got.cpu(), ref) <= 1e-2
     assert dst.tensor[:, 0].abs().max().item() == 0          # neighbouring chunk untouched
+
+
+@pytest.mark.parametrize("mode,cin,cout,ext", [(1, 40, 40, (2, 12, 36, 20)), (2, 40, 40, (2, 7, 17, 11)),
+                                               (2, 80, 80, (4, 15, 34, 30)), (1, 80, 80, (2, 8, 20, 12)),
+                                               (2, 24, 24, (1, 5, 9, 7))])
+def test_conv_tc_identity_epilogue(lib, mode, cin, cout, ext):
+    """slope01 = 2: the blur convolutions' epilogue (scale 1, shift 0, no activation) as a plain conversion -- must equal
+    the general epilogue bit for bit."""
+    from segmentation_pipeline.models import _plan
+    g = torch.Generator().manual_seed(500 + mode + cin)
+    x = torch.randn(ext[0], cin, *ext[1:], generator=g).to(torch.bfloat16).float()
+    if mode == 2:
+        w = (torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.05).to(torch.bfloat16).float()
+        ref = F.conv_transpose3d(x, w, stride=2, padding=1)
+    else:
+        w = (torch.randn(cout, cin, 4, 4, 4, generator=g) * 0.05).to(torch.bfloat16).float()
+        ref = F.conv3d(x, w, stride=2, padding=1)
+    chunks = (cin + 7) // 8
+    packed = dev(_plan.pack_tc_weight(mode, _plan.physical_weight(w, mode == 2, [(0, cin)], chunks, 0, cout), chunks, cout))
+    src = to_blocked(lib, x, torch.bfloat16)
+    outs = []
+    for flag in (1, 2):
+        dst = lib.Blocked(ext[0], (cout + 7) // 8, *ref.shape[2:], torch.bfloat16, "cuda")
+        dst.tensor.zero_()
+        cpad = (cout + 7) // 8 * 8
+        ones, zeros = dev(torch.ones(cpad)), dev(torch.zeros(cpad))
+        epi = lib.make_epilogue(ones, zeros, ones, dst.view(cout), slope01=flag)
+        lib.conv3d_tc(mode, src.view(cin), packed, cout, epi)
+        torch.cuda.synchronize()
+        outs.append(dst.tensor.clone())
+    assert torch.equal(outs[0], outs[1])
+    got = torch.empty(ref.shape, device="cuda")
+    dst.tensor.copy_(outs[1])
+    lib.unpack_ncdhw(dst.view(cout), got)
+    assert rel_err(got.cpu(), ref) <= 1e-2
+
+
+def test_plan_graph_replay_matches_eager():
+    """Small inputs replay a captured CUDA graph of the whole op list (third call on a workspace): same bits as the
+    eager launches, and the module-forward API hands out its own copy."""
+    from helpers import load_case
+    from test_gpu_models import build_model
+    from segmentation_pipeline.models import set_precision
+    meta, sd, x, y = load_case("models_modular_blur")
+    model = build_model(meta)
+    model.load_state_dict(sd)
+    model.eval().cuda()
+    set_precision("bf16")
+    try:
+        with torch.no_grad():
+            outs = [model(x.cuda()) for _ in range(4)]           # eager, capture, replay, replay
+            x2 = (x * 0.5).cuda()
+            o2 = model(x2)
+            compiled = next(iter(model.__dict__["_b200_cache"].values()))[1]
+            ws = next(iter(compiled.workspaces.values()))
+            assert "__graph__" in ws
+    finally:
+        set_precision("auto")
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert outs[0].data_ptr() != outs[1].data_ptr() and not torch.equal(o2, outs[0])
+    assert rel_err(outs[0].cpu(), y) <= 2e-2
 
 
 def test_conv_tc_softmax_head(lib):
