@@ -352,6 +352,92 @@ def label_check(ref: "CpuReference", model, device) -> dict:
             "head": "fitted read-out (tests/golden/readout_msseg2.npz)" if os.path.exists(READOUT) else "random init"}
 
 
+# ------------------------------------------------------------------------------------------------- z-slab (config 3)
+SLAB_VOLUME = (2, 224, 224, 224)
+SLAB_WORKLOAD = ("config3: qsm_deep_grey_matter-style NestedResUNet(2 -> 10, filters 40), synthetic 2x224^3 volume, patch 96^3 "
+                 "overlap 48 padding edge (125 patches), bf16, ONE volume partitioned over the GPUs")
+SLAB_FLOP_PER_PATCH = 1529078.0 * 96 ** 3
+
+
+def build_slab_model():
+    from segmentation_pipeline import models as M
+    torch.manual_seed(3)
+    model = M.NestedResUNet(2, 10, 40)
+    perturb_bn(model, 4)
+    return model.eval()
+
+
+def slab_volume() -> torch.Tensor:
+    g = torch.Generator().manual_seed(4321)
+    c, w, h, d = SLAB_VOLUME
+    coarse = torch.randn(1, c, w // 8, h // 8, d // 8, generator=g)
+    vol = torch.nn.functional.interpolate(coarse, size=(w, h, d), mode="trilinear", align_corners=False)[0]
+    return (vol + 0.1 * torch.randn(c, w, h, d, generator=g)).contiguous()
+
+
+def run_slab_section(world: int, rank: int, device, steps: int = 3, warmup: int = 2, patch_batch: int = 16) -> dict:
+    """Strong scaling of ONE config-3 volume over the ranks (segmentation_pipeline.distributed.slab_predict: balanced
+    runs of the sorted patch list, one all-to-all of raw output blocks over NCCL, owner-side accumulation in sorted
+    order, label all-gather), timed on the device as max over ranks -- and, on rank 0, the same volume on one GPU for
+    the speed-up and for the bit-exactness check of labels and probabilities."""
+    import torch.distributed as dist
+    from segmentation_pipeline.distributed import CudaSlabOps, make_slab_plan, slab_predict
+    from segmentation_pipeline.grid import PatchGrid
+    from segmentation_pipeline.prediction import PatchPredict
+    model = build_slab_model().to(device)
+    vol = slab_volume().to(device)
+    grid = PatchGrid(vol.shape[1:], PATCH, OVERLAP, PADDING)
+    ops = CudaSlabOps(model, patch_batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            labels, probs = slab_predict(vol, grid, ops, gather_probs=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            labels, _ = slab_predict(vol, grid, ops, gather_probs=False)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_slab = float(ms.item())
+        out = None
+        if rank == 0:
+            predictor = PatchPredict(patch_batch_size=patch_batch, patch_size=PATCH, patch_overlap=OVERLAP,
+                                     padding_mode=PADDING)
+            for _ in range(warmup):
+                ref_probs, ref_labels = predictor.predict_volume(model, vol)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                predictor.predict_volume(model, vol, want_probs=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_one = e0.elapsed_time(e1) / steps
+            plan = make_slab_plan(grid, world)
+            send, _ = plan.split_sizes(0, 10)
+            vox = SLAB_VOLUME[1] * SLAB_VOLUME[2] * SLAB_VOLUME[3]
+            out = {"workload": SLAB_WORKLOAD, "n_gpus": world, "scaling": "strong", "patches": len(grid.locations),
+                   "patches_per_rank": [b - a for a, b in plan.runs], "patch_batch": patch_batch,
+                   "ms_per_volume": ms_slab, "ms_per_volume_1gpu": ms_one, "speedup": ms_one / ms_slab,
+                   "efficiency": ms_one / ms_slab / world,
+                   "value": vox / (ms_slab * 1e-3) / 1e6, "unit": UNIT,
+                   "tflops": SLAB_FLOP_PER_PATCH * len(grid.locations) / (ms_slab * 1e-3) / 1e12,
+                   "labels_bit_identical_to_1gpu": bool(torch.equal(labels, ref_labels)),
+                   "probs_bit_identical_to_1gpu": bool(torch.equal(probs, ref_probs)),
+                   "all_to_all_bytes_sent_by_rank0": 4 * (sum(send) - send[0]),
+                   "collectives": "all_to_all_single (fp32 output blocks) + all_gather (uint8 label slabs), NCCL"}
+        barrier()
+    return out
+
+
 def run_gpu_arm(args) -> None:
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -434,6 +520,9 @@ def run_gpu_arm(args) -> None:
         e2e_steps = max(1, min(args.steps, 5))
         ms_e2e = timed(step_e2e, e2e_steps)
 
+    # ---- z-slab mode: one config-3 volume over all ranks (strong scaling; the collective path)
+    set_precision("bf16")
+    slab = run_slab_section(world, rank, device) if (world > 1 or args.slab) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -471,6 +560,8 @@ def run_gpu_arm(args) -> None:
                      "share_of_step": conv_ms / ms_per_step,
                      "algorithmic_flop_per_step": flop_step, "peak_source": peak_src},
     }
+    if slab is not None:
+        line["slab"] = slab
     if world == 1:
         threads = os.cpu_count() or 1
         ref = CpuReference(threads)
@@ -496,6 +587,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slab", action="store_true", help="also run the config-3 z-slab section at N = 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

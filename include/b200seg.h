@@ -134,6 +134,10 @@ int b200seg_avgpool2(b200seg_view in, b200seg_view out, void* stream);
 int b200seg_upsample_trilinear2(b200seg_view in, b200seg_view out, void* stream);
 /* Copy a view into a chunk range of another buffer (concat member that was not produced in place). */
 int b200seg_copy_view(b200seg_view in, b200seg_view out, void* stream);
+/* Planes [plane_lo, plane_hi) of one fp32 (c, p0, p1, p2) patch -> a dense (c, plane_hi - plane_lo, p1, p2) block:
+ * the staging step of the z-slab exchange (every output plane of a patch goes to the rank that owns it). */
+int b200seg_copy_planes(const float* patch, int32_t c, int32_t p0, int32_t p1, int32_t p2, int32_t plane_lo,
+                        int32_t plane_hi, float* dst, void* stream);
 /* Channel softmax / StochasticMatrix softmax (components.py:170-185) on fp32 NCDHW data, in place.
  * groups = 1 for nn.Softmax(dim=1); for StochasticMatrix groups = C, diag_bias added to the diagonal. */
 int b200seg_softmax_ncdhw(float* data, int64_t n, int32_t channels, int64_t voxels, int32_t sm_channels,

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "b200seg_avgpool2": (c_int32, [View, View, c_void_p]),
     "b200seg_upsample_trilinear2": (c_int32, [View, View, c_void_p]),
     "b200seg_copy_view": (c_int32, [View, View, c_void_p]),
+    "b200seg_copy_planes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                      c_void_p]),
     "b200seg_softmax_ncdhw": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_float, c_void_p]),
     "b200seg_grid_extract": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32), c_int32,
                                        POINTER(c_int32), c_int32, c_float, View, c_void_p]),
@@ -243,6 +245,16 @@ def upsample_trilinear2(inp: View, out: View) -> None:
 def copy_view(inp: View, out: View) -> None:
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_copy_view(inp, out, _stream()), "copy_view")
+
+
+def copy_planes(patch: torch.Tensor, plane_lo: int, plane_hi: int, dst: torch.Tensor) -> None:
+    """patch: fp32 (C, p0, p1, p2) contiguous; dst: fp32 buffer with room for (C, plane_hi - plane_lo, p1, p2)."""
+    _require_cuda(patch, dst)
+    assert patch.dtype == torch.float32 and dst.dtype == torch.float32 and patch.is_contiguous() and dst.is_contiguous()
+    c, p0, p1, p2 = patch.shape
+    assert dst.numel() >= c * (plane_hi - plane_lo) * p1 * p2
+    _check(load_library().b200seg_copy_planes(_ptr(patch), c, p0, p1, p2, plane_lo, plane_hi, _ptr(dst), _stream()),
+           "copy_planes")
 
 
 def softmax_ncdhw(data: torch.Tensor, sm_channels: int = 0, diag_bias: float = 0.0) -> None:

@@ -634,6 +634,20 @@ int b200seg_copy_view(b200seg_view in, b200seg_view out, void* stream) {
     return check_launch("copy_view");
 }
 
+int b200seg_copy_planes(const float* patch, int32_t c, int32_t p0, int32_t p1, int32_t p2, int32_t plane_lo,
+                        int32_t plane_hi, float* dst, void* stream) {
+    B200SEG_CHECK_ARG(patch != nullptr && dst != nullptr && c > 0 && p0 > 0 && p1 > 0 && p2 > 0, "copy_planes: bad arguments");
+    B200SEG_CHECK_ARG(plane_lo >= 0 && plane_lo < plane_hi && plane_hi <= p0, "copy_planes: planes [%d, %d) of %d", plane_lo,
+                      plane_hi, p0);
+    // c rows of (plane_hi - plane_lo) * p1 * p2 contiguous floats: a pitched copy on the copy engine, no kernel
+    const size_t width = static_cast<size_t>(plane_hi - plane_lo) * p1 * p2 * sizeof(float);
+    const size_t spitch = static_cast<size_t>(p0) * p1 * p2 * sizeof(float);
+    B200SEG_CHECK_CUDA(cudaMemcpy2DAsync(dst, width, patch + static_cast<size_t>(plane_lo) * p1 * p2, spitch, width,
+                                         static_cast<size_t>(c), cudaMemcpyDeviceToDevice,
+                                         static_cast<cudaStream_t>(stream)));
+    return B200SEG_OK;
+}
+
 int b200seg_softmax_ncdhw(float* data, int64_t n, int32_t channels, int64_t voxels, int32_t sm_channels,
                           float diag_bias, void* stream) {
     B200SEG_CHECK_ARG(data != nullptr && n > 0 && channels > 0 && voxels > 0, "softmax_ncdhw: bad arguments");

@@ -4,17 +4,25 @@ The reference has no distributed code at all; the path s
 
 * **cohort mode** -- subjects are independent (reference prediction.py:131): subject i goes to rank i mod N; the
   only collective is the all-reduce of the tiny int64 confusion matrices.
-* **z-slab mode** -- one volume, the sorted patch grid split along the first spatial axis.  Rank r evaluates the
-  patches whose start plane falls into its range and accumulates them into a local slab; a patch reaches up to
-  ``patch - 1`` planes past the range, and those partial sums ("halo") are sent forward to the rank that owns the
-  planes.  Counts need no exchange (they are analytic).  Each rank finalises the planes it owns and the uint8
-  label slabs are all-gathered.
+* **z-slab mode** -- one volume over N GPUs.  Two decoupled partitions (``SlabPlan``):
 
-The exchange logic is independent of where the arithmetic runs: ``SlabOps`` abstracts the four device steps so
-that the CPU tests (gloo, world_size 2) can drive the same plan / send / recv / gather code with oracle
-arithmetic, while production uses the CUDA kernels (``CudaSlabOps``).  Summation order: the halo is added to the
-owner's accumulator AFTER its own patches, i.e. (sum of own patches) + (partial sum received), which differs
-from the single-GPU order by fp32 re-association only ('determinism').
+    - *compute*: the sorted patch list (torchio's order) is cut into N contiguous runs of equal length, so every rank
+      evaluates floor/ceil(n / N) patches whatever the shape of the grid (config 3: 125 patches -> 15 or 16 each at
+      8 ranks; splitting by start PLANES, as round 1 did, left ranks idle as soon as N exceeded the 5 start planes);
+    - *ownership*: the padded output volume is cut into N slabs of planes along the first spatial axis; the owner of
+      a slab accumulates, divides, crops and arg-maxes it.
+
+  Every plane of every patch output belongs to exactly one owner, so after its forwards a rank stages, per patch and
+  owner, the dense block of planes that falls into that owner's slab (``b200seg_copy_planes``) and ONE
+  ``all_to_all_single`` over NCCL / NVLink moves all blocks (about 0.55 x the rank's outputs, < 1 ms at 8 GPUs for
+  config 3).  The owner then adds the blocks it holds IN SORTED PATCH ORDER -- exactly the per-voxel order of the
+  single-GPU accumulation and of torchio's ``add_batch`` -- so probabilities and labels are bit-identical to one GPU
+  (raw contributions are exchanged, not partial sums: partial sums would re-associate the fp32 additions).  Counts
+  need no exchange (they are analytic).  The uint8 label slabs are all-gathered.
+
+The exchange logic is independent of where the arithmetic runs: ``SlabOps`` abstracts the device steps so that the CPU
+tests (gloo, world_size 2 / 3) drive the same plan / staging / all-to-all / gather code with oracle arithmetic, while
+production uses the CUDA kernels (``CudaSlabOps``).
 """
 from __future__ import annotations
 
@@ -42,37 +50,58 @@ def all_reduce_confusion(cm: torch.Tensor, group=None) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------- z-slab plan
 @dataclass
+class Block:
+    """Planes [lo, hi) (padded coordinates) of patch ``patch`` -- computed on ``src``, accumulated by ``dst``."""
+    patch: int
+    src: int
+    dst: int
+    lo: int
+    hi: int
+
+
+@dataclass
 class SlabPlan:
-    """Partition of a PatchGrid along axis 0 (padded coordinates)."""
     grid: PatchGrid
     world: int
-    start_ranges: List[Tuple[int, int]]   # per rank: [first, last) index into grid.axis_starts[0]
-    own: List[Tuple[int, int]]            # per rank: owned padded planes [lo, hi)
-    local: List[Tuple[int, int]]          # per rank: planes its local accumulator covers [lo, hi)
+    runs: List[Tuple[int, int]]     # per rank: [first, last) indices into grid.locations (sorted order)
+    own: List[Tuple[int, int]]      # per rank: owned padded planes [lo, hi) along axis 0
 
     def patches_of(self, rank: int) -> List[Tuple[int, ...]]:
-        first, last = self.start_ranges[rank]
-        starts = set(self.grid.axis_starts[0][first:last])
-        return [loc for loc in self.grid.locations if loc[0] in starts]
+        a, b = self.runs[rank]
+        return self.grid.locations[a:b]
 
-    def sends(self, rank: int) -> List[Tuple[int, int, int]]:
-        """(destination rank, plane lo, plane hi) of every halo slab rank ``rank`` must send forward."""
-        lo, hi = self.local[rank]
+    def rank_of_patch(self, index: int) -> int:
+        for r, (a, b) in enumerate(self.runs):
+            if a <= index < b:
+                return r
+        raise IndexError(index)
+
+    def blocks(self) -> List[Block]:
+        """Every (patch, owner) intersection, ordered by (src, dst, patch): the order of the send buffers."""
         out = []
-        for dst in range(rank + 1, self.world):
-            a, b = max(self.own[dst][0], lo), min(self.own[dst][1], hi)
-            if a < b:
-                out.append((dst, a, b))
+        for src, (a, b) in enumerate(self.runs):
+            for dst, (lo, hi) in enumerate(self.own):
+                for p in range(a, b):
+                    i0, i1 = self.grid.locations[p][0], self.grid.locations[p][3]
+                    x, y = max(i0, lo), min(i1, hi)
+                    if x < y:
+                        out.append(Block(p, src, dst, x, y))
         return out
 
-    def recvs(self, rank: int) -> List[Tuple[int, int, int]]:
-        """(source rank, plane lo, plane hi) of every halo slab rank ``rank`` receives."""
-        out = []
-        for src in range(rank):
-            for dst, a, b in self.sends(src):
-                if dst == rank:
-                    out.append((src, a, b))
-        return out
+    def plane_elems(self, channels: int) -> int:
+        return channels * self.grid.patch_size[1] * self.grid.patch_size[2]
+
+    def split_sizes(self, rank: int, channels: int):
+        """(elements this rank sends to each rank, elements it receives from each rank)."""
+        per = self.plane_elems(channels)
+        send, recv = [0] * self.world, [0] * self.world
+        for blk in self.blocks():
+            n = (blk.hi - blk.lo) * per
+            if blk.src == rank:
+                send[blk.dst] += n
+            if blk.dst == rank:
+                recv[blk.src] += n
+        return send, recv
 
     def owned_output(self, rank: int) -> Tuple[int, int]:
         """Unpadded output planes [lo, hi) rank ``rank`` finalises (may be empty)."""
@@ -83,51 +112,38 @@ class SlabPlan:
 
 
 def make_slab_plan(grid: PatchGrid, world: int) -> SlabPlan:
-    starts = grid.axis_starts[0]
-    n = len(starts)
     if world < 1:
         raise ValueError("world must be >= 1")
-    # contiguous, balanced split of the start planes (ranks beyond the number of start planes get nothing)
-    ranges = []
-    for r in range(world):
-        a = (r * n) // world
-        b = ((r + 1) * n) // world
-        ranges.append((a, b))
-    p0 = grid.patch_size[0]
-    total = grid.padded_shape[0]
-    own, local = [], []
-    for r, (a, b) in enumerate(ranges):
-        if a == b:
-            own.append((0, 0))
-            local.append((0, 0))
-            continue
-        lo = starts[a] if a > 0 else 0
-        # the next non-empty rank's first start plane bounds the owned range
-        nxt = next((starts[ra] for ra, rb in ranges[r + 1:] if ra < rb), None)
-        hi = total if nxt is None else nxt
-        own.append((lo, hi))
-        local.append((starts[a], starts[b - 1] + p0))
-    return SlabPlan(grid, world, ranges, own, local)
+    n = len(grid.locations)
+    planes = grid.padded_shape[0]
+    runs = [((r * n) // world, ((r + 1) * n) // world) for r in range(world)]
+    own = [((r * planes) // world, ((r + 1) * planes) // world) for r in range(world)]
+    return SlabPlan(grid, world, runs, own)
 
 
 # ------------------------------------------------------------------------------------------------- device steps
 class SlabOps:
     """The arithmetic of one rank, on whatever device the tensors live on."""
 
-    def forward_accumulate(self, volume: torch.Tensor, grid: PatchGrid, patches, plane0: int, n_planes: int
-                           ) -> torch.Tensor:
-        """Extract + network forward + overlap-add of ``patches`` into a fresh fp32 accumulator
-        (C_out, n_planes, PH, PD) whose first plane is padded plane ``plane0``."""
+    def forward(self, volume: torch.Tensor, grid: PatchGrid, patches) -> torch.Tensor:
+        """Extract + network forward of ``patches`` -> fp32 (len(patches), C_out, p0, p1, p2)."""
         raise NotImplementedError
 
-    def add_slab(self, acc: torch.Tensor, slab: torch.Tensor, plane_offset: int) -> None:
-        """acc[:, plane_offset : plane_offset + slab.shape[1]] += slab"""
+    def out_channels(self, volume: torch.Tensor) -> int:
+        raise NotImplementedError
+
+    def stage(self, patch_out: torch.Tensor, lo: int, hi: int, dst: torch.Tensor) -> None:
+        """dst[: C * (hi - lo) * p1 * p2] = patch_out[:, lo:hi] (dense)."""
+        raise NotImplementedError
+
+    def accumulate(self, acc: torch.Tensor, block: torch.Tensor, loc) -> None:
+        """acc[:, loc[0]:loc[3], loc[1]:loc[4], loc[2]:loc[5]] += block  (block: (C, q, p1, p2))."""
         raise NotImplementedError
 
     def finalize(self, acc: torch.Tensor, grid: PatchGrid, plane0: int, out_lo: int, out_hi: int
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
         """(probs (C, out_hi-out_lo, H, D) fp32, labels (out_hi-out_lo, H, D) uint8) of unpadded planes
-        [out_lo, out_hi)."""
+        [out_lo, out_hi) from the accumulator whose first plane is padded plane ``plane0``."""
         raise NotImplementedError
 
 
@@ -138,31 +154,35 @@ class CudaSlabOps(SlabOps):
         self.model = model
         self.patch_batch_size = patch_batch_size
 
-    def forward_accumulate(self, volume, grid, patches, plane0, n_planes):
-        import b200seg
+    def _compiled(self, volume):
         from .models import _engine
-        device = volume.device
         precision = _engine._resolve_precision(self.model, volume)
-        compiled = _engine.compiled_for(self.model, precision, device)
+        return _engine.compiled_for(self.model, precision, volume.device)
+
+    def out_channels(self, volume):
+        return self._compiled(volume).plan.out_channels
+
+    def forward(self, volume, grid, patches):
+        import b200seg
+        compiled = self._compiled(volume)
         p0, p1, p2 = grid.patch_size
-        acc = None
+        out = torch.empty((len(patches), compiled.plan.out_channels, p0, p1, p2), dtype=torch.float32,
+                          device=volume.device)
         for start in range(0, len(patches), self.patch_batch_size):
             locs = patches[start:start + self.patch_batch_size]
             buf = compiled.input_buffer(len(locs), p0, p1, p2)
             b200seg.grid_extract(volume, locs, grid.border, grid.pad_mode_code, grid.pad_value,
                                  buf.view(volume.shape[0]))
-            y = compiled.run_blocked(len(locs), p0, p1, p2)
-            if acc is None:
-                acc = torch.zeros((y.shape[1], n_planes, *grid.padded_shape[1:]), dtype=torch.float32, device=device)
-            shifted = [(l[0] - plane0, l[1], l[2], l[3] - plane0, l[4], l[5]) for l in locs]
-            b200seg.overlap_add(acc, y, shifted)
-        return acc
+            compiled.run_blocked(len(locs), p0, p1, p2, out=out[start:start + len(locs)])
+        return out
 
-    def add_slab(self, acc, slab, plane_offset):
+    def stage(self, patch_out, lo, hi, dst):
         import b200seg
-        n = slab.shape[1]
-        loc = (plane_offset, 0, 0, plane_offset + n, slab.shape[2], slab.shape[3])
-        b200seg.overlap_add(acc, slab[None].contiguous(), [loc])
+        b200seg.copy_planes(patch_out, lo, hi, dst)
+
+    def accumulate(self, acc, block, loc):
+        import b200seg
+        b200seg.overlap_add(acc, block[None], [loc])
 
     def finalize(self, acc, grid, plane0, out_lo, out_hi):
         import b200seg
@@ -179,43 +199,66 @@ class CudaSlabOps(SlabOps):
 
 
 # ------------------------------------------------------------------------------------------------- z-slab driver
-def slab_predict(volume: torch.Tensor, grid: PatchGrid, ops: SlabOps, group=None, gather_probs: bool = False):
+def slab_predict(volume: torch.Tensor, grid: PatchGrid, ops: SlabOps, group=None, gather_probs: bool = False,
+                 timings: Optional[dict] = None):
     """Runs this rank's share of the sliding window and returns (labels uint8 (W, H, D) on every rank,
-    probs fp32 (C, W, H, D) or None).  ``volume`` is the full (C, W, H, D) volume on this rank's device."""
+    probs fp32 (C, W, H, D) or None).  ``volume`` is the full (C, W, H, D) volume on this rank's device.
+    Results are bit-identical to the single-device ``PatchPredict.predict_volume``."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     plan = make_slab_plan(grid, world)
-    patches = plan.patches_of(rank)
-    lo, hi = plan.local[rank]
-    acc = ops.forward_accumulate(volume, grid, patches, lo, hi - lo) if patches else None
+    device = volume.device
+    channels = ops.out_channels(volume)
+    per = plan.plane_elems(channels)
+    p1, p2 = grid.patch_size[1], grid.patch_size[2]
 
-    # ---- halo exchange: partial sums flow forward only (a patch never reaches planes before its start)
-    pending = []
-    send_bufs = []
+    # ---- forwards of this rank's run of patches
+    first, last = plan.runs[rank]
+    patches = plan.patches_of(rank)
+    y = ops.forward(volume, grid, patches) if patches else None
+
+    # ---- stage every plane of every patch for its owner; one all-to-all moves the blocks
+    blocks = plan.blocks()
+    send_sizes, recv_sizes = plan.split_sizes(rank, channels)
+    send = torch.empty(sum(send_sizes), dtype=torch.float32, device=device)
+    recv = torch.empty(sum(recv_sizes), dtype=torch.float32, device=device)
+    off = 0
+    for blk in blocks:                       # ordered by (src, dst, patch): contiguous per destination
+        if blk.src != rank:
+            continue
+        i0 = grid.locations[blk.patch][0]
+        n = (blk.hi - blk.lo) * per
+        ops.stage(y[blk.patch - first], blk.lo - i0, blk.hi - i0, send[off:off + n])
+        off += n
     if world > 1:
-        for dst, a, b in plan.sends(rank):
-            slab = acc[:, a - lo:b - lo].contiguous()
-            send_bufs.append(slab)
-            pending.append(dist.isend(slab, dst, group=group))
-        recv_bufs = []
-        for src, a, b in plan.recvs(rank):
-            buf = torch.empty((acc.shape[0], b - a, *acc.shape[2:]), dtype=acc.dtype, device=acc.device)
-            recv_bufs.append((a, buf))
-            pending.append(dist.irecv(buf, src, group=group))
-        for req in pending:
-            req.wait()
-        for a, buf in recv_bufs:
-            ops.add_slab(acc, buf, a - lo)
+        dist.all_to_all_single(recv, send, recv_sizes, send_sizes, group=group)
+    else:
+        recv = send
+    y = None
+
+    # ---- owner: add the blocks in sorted patch order (== the single-device per-voxel order)
+    lo, hi = plan.own[rank]
+    acc = torch.zeros((channels, hi - lo, *grid.padded_shape[1:]), dtype=torch.float32, device=device)
+    mine, off = [], 0
+    for blk in blocks:                       # (src, dst, patch) order == layout of ``recv`` (grouped by src)
+        if blk.dst != rank:
+            continue
+        n = (blk.hi - blk.lo) * per
+        mine.append((blk.patch, off, blk))
+        off += n
+    for _, o, blk in sorted(mine, key=lambda t: t[0]):
+        loc = grid.locations[blk.patch]
+        q = blk.hi - blk.lo
+        block = recv[o:o + q * per].view(channels, q, p1, p2)
+        ops.accumulate(acc, block, (blk.lo - lo, loc[1], loc[2], blk.hi - lo, loc[4], loc[5]))
 
     # ---- finalise the owned planes, gather the label slabs
     out_lo, out_hi = plan.owned_output(rank)
     w, h, d = grid.spatial_shape
-    device = volume.device
     if out_hi > out_lo:
         probs, labels = ops.finalize(acc, grid, lo, out_lo, out_hi)
     else:
-        c_out = 0 if acc is None else acc.shape[0]
-        probs = torch.empty((c_out, 0, h, d), dtype=torch.float32, device=device)
+        probs = torch.empty((channels, 0, h, d), dtype=torch.float32, device=device)
         labels = torch.empty((0, h, d), dtype=torch.uint8, device=device)
     if world == 1:
         return labels, (probs if gather_probs else None)
@@ -224,21 +267,20 @@ def slab_predict(volume: torch.Tensor, grid: PatchGrid, ops: SlabOps, group=None
     longest = max(b - a for a, b in spans)
     padded = torch.zeros((longest, h, d), dtype=torch.uint8, device=device)
     padded[:labels.shape[0]] = labels
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
+    gathered = torch.empty((world * longest, h, d), dtype=torch.uint8, device=device)   # concatenation along dim 0
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    gathered = gathered.view(world, longest, h, d)
     full = torch.empty((w, h, d), dtype=torch.uint8, device=device)
-    for (a, b), part in zip(spans, gathered):
-        full[a:b] = part[:b - a]
+    for r, (a, b) in enumerate(spans):
+        full[a:b] = gathered[r, :b - a]
     full_probs = None
     if gather_probs:
-        c_out = torch.tensor([probs.shape[0]], device=device)
-        dist.all_reduce(c_out, op=dist.ReduceOp.MAX, group=group)
-        c = int(c_out.item())
-        pp = torch.zeros((c, longest, h, d), dtype=torch.float32, device=device)
-        pp[:, :probs.shape[1]] = probs if probs.shape[0] == c else 0
-        parts = [torch.empty_like(pp) for _ in range(world)]
-        dist.all_gather(parts, pp, group=group)
-        full_probs = torch.empty((c, w, h, d), dtype=torch.float32, device=device)
-        for (a, b), part in zip(spans, parts):
-            full_probs[:, a:b] = part[:, :b - a]
+        pp = torch.zeros((channels, longest, h, d), dtype=torch.float32, device=device)
+        pp[:, :probs.shape[1]] = probs
+        parts = torch.empty((world * channels, longest, h, d), dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(parts, pp, group=group)
+        parts = parts.view(world, channels, longest, h, d)
+        full_probs = torch.empty((channels, w, h, d), dtype=torch.float32, device=device)
+        for r, (a, b) in enumerate(spans):
+            full_probs[:, a:b] = parts[r, :, :b - a]
     return full, full_probs
