@@ -438,6 +438,95 @@ def run_slab_section(world: int, rank: int, device, steps: int = 3, warmup: int 
     return out
 
 
+# ------------------------------------------------------------------------------------------------- cohort (config 4)
+COHORT_WORKLOAD = ("config4: dmri_hippo-style NestedResUNet(3 -> 2, filters 40, dropout 0.2) eval, cohort of 64 synthetic "
+                   "3x96x88x24 volumes, StandardPredict(sagittal_split=True), 64 / N volumes per GPU, Dice on device")
+COHORT_SHAPE = (3, 96, 88, 24)
+COHORT_SIZE = 64
+
+
+def run_cohort_section(world: int, rank: int, device, steps: int = 3, warmup: int = 2, subjects_per_call: int = 8) -> dict:
+    """BASELINE config 4: every rank runs its share of a 64-subject cohort through the reference-facing API --
+    StandardPredict(sagittal_split=True).predict -> add_evaluation_labels -> the device confusion histogram -- and the
+    int64 confusion matrices are all-reduced (the only collective of cohort mode; exact)."""
+    import torch.distributed as dist
+    import b200seg
+    from segmentation_pipeline import _tio, models as M
+    from segmentation_pipeline.distributed import all_reduce_confusion, shard_subjects
+    from segmentation_pipeline.evaluators.segmentation_evaluator import counts_from_cm
+    from segmentation_pipeline.prediction import StandardPredict, split_and_flip, reverse_split_and_flip
+    torch.manual_seed(11)
+    model = M.NestedResUNet(3, 2, 40, dropout_p=0.2)
+    perturb_bn(model, 12)
+    model.eval().to(device)
+    mine = shard_subjects(COHORT_SIZE, rank, world)
+    g = torch.Generator().manual_seed(500 + rank)
+    vols = [torch.randn(COHORT_SHAPE, generator=g).pin_memory() for _ in mine]
+    targets = [(torch.rand(COHORT_SHAPE[1:], generator=g) > 0.5).to(torch.uint8).to(device) for _ in mine]
+    subjects = [_tio.Subject(X=_tio.ScalarImage(tensor=v), name=f"c{rank}_{i}") for i, v in zip(mine, vols)]
+    predictor = StandardPredict(sagittal_split=True)
+    cm = torch.zeros((2, 2), dtype=torch.int64, device=device)
+    vox = COHORT_SHAPE[1] * COHORT_SHAPE[2] * COHORT_SHAPE[3]
+
+    def step_api():
+        """public API: pinned host volumes in, host probabilities (LabelMap) out, labels + counts on the device"""
+        for a in range(0, len(subjects), subjects_per_call):
+            chunk = subjects[a:a + subjects_per_call]
+            _, batch = predictor.predict(model, device, chunk, {"label_values": {"left_whole": 1}})
+            y = batch["y_pred"]
+            labels = torch.empty((y.shape[0], *y.shape[2:]), dtype=torch.uint8, device=device)
+            for i in range(y.shape[0]):
+                b200seg.argmax(y[i].contiguous(), None, labels[i])
+                b200seg.confusion(labels[i], targets[a + i], 2, cm)
+
+    dev_batches = [torch.stack(vols[a:a + subjects_per_call]).to(device) for a in range(0, len(vols), subjects_per_call)]
+
+    def step_resident():
+        for bi, xb in enumerate(dev_batches):
+            y = reverse_split_and_flip(model(split_and_flip(xb).contiguous()))
+            for i in range(y.shape[0]):
+                lab = torch.empty(y.shape[2:], dtype=torch.uint8, device=device)
+                b200seg.argmax(y[i].contiguous(), None, lab)
+                b200seg.confusion(lab, targets[bi * subjects_per_call + i], 2, cm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        cm.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        ms_res = timed(step_resident)
+        ms_api = timed(step_api)
+        all_reduce_confusion(cm)
+    tp, fp, tn, fn = counts_from_cm(cm.cpu(), 1)
+    flop = 1516118.0 * vox * COHORT_SIZE
+    return {"workload": COHORT_WORKLOAD, "n_gpus": world, "scaling": "strong (fixed cohort of 64)",
+            "volumes_per_gpu": len(mine), "subjects_per_call": subjects_per_call,
+            "ms_per_cohort": ms_res, "volumes_per_s": COHORT_SIZE / (ms_res * 1e-3),
+            "value": COHORT_SIZE * vox / (ms_res * 1e-3) / 1e6, "unit": UNIT, "tflops": flop / (ms_res * 1e-3) / 1e12,
+            "e2e": {"ms_per_cohort": ms_api, "value": COHORT_SIZE * vox / (ms_api * 1e-3) / 1e6, "unit": UNIT,
+                    "api": "StandardPredict(sagittal_split=True).predict on pinned host subjects -> host LabelMaps; argmax "
+                           "+ confusion on the device"},
+            "confusion_total": int(cm.sum()), "dice_vs_random_target": 2 * tp / max(2 * tp + fp + fn, 1),
+            "collective": "all_reduce(SUM) of the 2x2 int64 confusion matrix"}
+
+
 def run_gpu_arm(args) -> None:
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -523,6 +612,7 @@ def run_gpu_arm(args) -> None:
     # ---- z-slab mode: one config-3 volume over all ranks (strong scaling; the collective path)
     set_precision("bf16")
     slab = run_slab_section(world, rank, device) if (world > 1 or args.slab) else None
+    cohort4 = run_cohort_section(world, rank, device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -562,6 +652,7 @@ def run_gpu_arm(args) -> None:
     }
     if slab is not None:
         line["slab"] = slab
+    line["cohort_config4"] = cohort4
     if world == 1:
         threads = os.cpu_count() or 1
         ref = CpuReference(threads)

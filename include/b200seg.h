@@ -134,6 +134,23 @@ int b200seg_avgpool2(b200seg_view in, b200seg_view out, void* stream);
 int b200seg_upsample_trilinear2(b200seg_view in, b200seg_view out, void* stream);
 /* Copy a view into a chunk range of another buffer (concat member that was not produced in place). */
 int b200seg_copy_view(b200seg_view in, b200seg_view out, void* stream);
+/* ------------------------------------------------------------------------------------------------ test-time augmentation
+ * EnsembleFlips / EnsembleOrientations / EnsembleModels + apply_strategy (models/ensemble.py:16-103).  Member e is
+ * evaluated on x.permute(0, 1, *perm + 2).flip(dims); perm[k] in {0, 1, 2} names the source spatial axis of transformed
+ * axis k and flip[k] != 0 reverses transformed axis k.
+ *   pack_ncdhw_tta   fp32 (N, C, w0, w1, w2) -> blocked dst in the member's space (dst extent = permuted extent)
+ *   tta_accumulate   member output fp32 (N, C, S0, S1, S2), un-transformed on the fly, into EITHER the fp32 sum
+ *                    acc (N, C, w0, w1, w2) ('mean') OR the uint8 vote counts votes (N, C, w0, w1, w2) of the member's
+ *                    per-voxel argmax ('majority'; first maximum wins like torch.argmax)
+ *   tta_finalize     'mean': acc *= 1 / members in place; 'majority': int64 one-hot (N, C, voxels) of the label with the
+ *                    most votes, smallest label on ties (torch.mode). */
+int b200seg_pack_ncdhw_tta(const float* src, int32_t w0, int32_t w1, int32_t w2, const int32_t perm[3],
+                           const int32_t flip[3], b200seg_view dst, void* stream);
+int b200seg_tta_accumulate(const float* member, int64_t n, int32_t c, int32_t w0, int32_t w1, int32_t w2,
+                           const int32_t perm[3], const int32_t flip[3], float* acc, uint8_t* votes, void* stream);
+int b200seg_tta_finalize(float* acc, const uint8_t* votes, int64_t* onehot, int64_t n, int32_t c, int64_t voxels,
+                         int32_t members, void* stream);
+
 /* Planes [plane_lo, plane_hi) of one fp32 (c, p0, p1, p2) patch -> a dense (c, plane_hi - plane_lo, p1, p2) block:
  * the staging step of the z-slab exchange (every output plane of a patch goes to the rank that owns it). */
 int b200seg_copy_planes(const float* patch, int32_t c, int32_t p0, int32_t p1, int32_t p2, int32_t plane_lo,

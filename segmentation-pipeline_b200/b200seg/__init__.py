@@ -50,6 +50,11 @@ _SIGNATURES = {
     "b200seg_avgpool2": (c_int32, [View, View, c_void_p]),
     "b200seg_upsample_trilinear2": (c_int32, [View, View, c_void_p]),
     "b200seg_copy_view": (c_int32, [View, View, c_void_p]),
+    "b200seg_pack_ncdhw_tta": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), View,
+                                         c_void_p]),
+    "b200seg_tta_accumulate": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32),
+                                         POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
+    "b200seg_tta_finalize": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p]),
     "b200seg_copy_planes": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                       c_void_p]),
     "b200seg_softmax_ncdhw": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_float, c_void_p]),
@@ -245,6 +250,42 @@ def upsample_trilinear2(inp: View, out: View) -> None:
 def copy_view(inp: View, out: View) -> None:
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_copy_view(inp, out, _stream()), "copy_view")
+
+
+def pack_ncdhw_tta(src: torch.Tensor, perm: Sequence[int], flip: Sequence[bool], dst: View) -> None:
+    """src fp32 (N, C, w0, w1, w2) -> blocked ``dst`` holding src.permute(0, 1, *perm + 2).flip(axes with flip[k])."""
+    _require_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 5
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_pack_ncdhw_tta(_ptr(src), src.shape[2], src.shape[3], src.shape[4], _i32(perm),
+                                                 _i32([1 if f else 0 for f in flip]), dst, _stream()), "pack_ncdhw_tta")
+
+
+def tta_accumulate(member: torch.Tensor, perm: Sequence[int], flip: Sequence[bool], acc: Optional[torch.Tensor],
+                   votes: Optional[torch.Tensor]) -> None:
+    """member: fp32 (N, C, S0, S1, S2) in the member's space; acc fp32 / votes uint8: (N, C, w0, w1, w2) original space."""
+    _require_cuda(member, acc, votes)
+    target = acc if acc is not None else votes
+    assert member.dtype == torch.float32 and member.is_contiguous() and target.is_contiguous()
+    assert (acc is None or acc.dtype == torch.float32) and (votes is None or votes.dtype == torch.uint8)
+    n, c, w0, w1, w2 = target.shape
+    assert member.shape[:2] == (n, c) and tuple(member.shape[2:]) == tuple(target.shape[2 + p] for p in perm)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_tta_accumulate(_ptr(member), n, c, w0, w1, w2, _i32(perm),
+                                                 _i32([1 if f else 0 for f in flip]), _ptr(acc), _ptr(votes), _stream()),
+           "tta_accumulate")
+
+
+def tta_finalize(acc: Optional[torch.Tensor], votes: Optional[torch.Tensor], onehot: Optional[torch.Tensor],
+                 members: int) -> None:
+    _require_cuda(acc, votes, onehot)
+    target = acc if acc is not None else votes
+    n, c = target.shape[:2]
+    vox = target[0, 0].numel()
+    assert onehot is None or (onehot.dtype == torch.int64 and onehot.is_contiguous() and onehot.shape == votes.shape)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_tta_finalize(_ptr(acc), _ptr(votes), _ptr(onehot), n, c, vox, members, _stream()),
+           "tta_finalize")
 
 
 def copy_planes(patch: torch.Tensor, plane_lo: int, plane_hi: int, dst: torch.Tensor) -> None:

@@ -139,6 +139,111 @@ copy_view_kernel(DView in, DView out, long long total) {
     store_vec8<T>(out.data, n * out.sample_stride + (out.c8_off + cc) * out.chunk_stride + v, r);
 }
 
+// =========================================================================================== test-time augmentation
+// EnsembleFlips / EnsembleOrientations (models/ensemble.py:50-103): member e sees x.permute(0, 1, *perm).flip(dims) and
+// its output is flipped / permuted back before the reduction over members.  Both index shuffles are folded into the
+// kernels that touch the data anyway: the NCDHW -> blocked packing of the member's input, and the accumulation of the
+// member's output into the mean / vote buffers -- no flipped copies, no (E, N, C, ...) stack.
+struct TtaXform {
+    int perm[3];   // transformed spatial axis k is source axis perm[k] (0..2)
+    int flip[3];   // transformed axis k is reversed
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pack_ncdhw_tta_kernel(const float* __restrict__ src, DView dst, int w0, int w1, int w2, TtaXform xf, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long vox = dst.chunk_stride;
+    const int c8 = (dst.c + 7) / 8;
+    long long v = t % vox;
+    int cc = static_cast<int>((t / vox) % c8);
+    int n = static_cast<int>(t / (vox * c8));
+    int u[3];
+    u[2] = static_cast<int>(v % dst.x);
+    u[1] = static_cast<int>((v / dst.x) % dst.y);
+    u[0] = static_cast<int>(v / (1LL * dst.x * dst.y));
+    const int S[3] = {dst.z, dst.y, dst.x};
+    int w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[xf.perm[k]] = xf.flip[k] ? S[k] - 1 - u[k] : u[k];
+    const long long svox = 1LL * w0 * w1 * w2;
+    const long long sv = (1LL * w[0] * w1 + w[1]) * w2 + w[2];
+    Vec8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = cc * 8 + j;
+        r.v[j] = c < dst.c ? __ldg(src + (static_cast<long long>(n) * dst.c + c) * svox + sv) : 0.f;
+    }
+    store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, r);
+}
+
+// member: fp32 (N, C, S0, S1, S2) in the member's (transformed) space; one thread per ORIGINAL-space voxel.
+// mean: acc (N, C, W0, W1, W2) += member un-transformed.  majority: votes[n][argmax_c member][w] += 1 (uint8).
+__global__ void __launch_bounds__(kThreads)
+tta_accumulate_kernel(const float* __restrict__ member, int C, int w0, int w1, int w2, TtaXform xf,
+                      float* __restrict__ acc, uint8_t* __restrict__ votes, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long vox = 1LL * w0 * w1 * w2;
+    const long long v = t % vox;
+    const long long n = t / vox;
+    int w[3];
+    w[2] = static_cast<int>(v % w2);
+    w[1] = static_cast<int>((v / w2) % w1);
+    w[0] = static_cast<int>(v / (1LL * w2 * w1));
+    const int W[3] = {w0, w1, w2};
+    int S[3], u[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        S[k] = W[xf.perm[k]];
+        const int vk = w[xf.perm[k]];
+        u[k] = xf.flip[k] ? S[k] - 1 - vk : vk;
+    }
+    const float* m = member + n * C * vox + (1LL * u[0] * S[1] + u[1]) * S[2] + u[2];
+    if (acc != nullptr) {
+        float* a = acc + n * C * vox + v;
+        for (int c = 0; c < C; ++c) a[c * vox] += __ldg(m + c * vox);
+    } else {
+        // torch.argmax: first maximum wins, NaN counts as the maximum
+        float best = __ldg(m);
+        int arg = 0;
+        for (int c = 1; c < C; ++c) {
+            const float x = __ldg(m + c * vox);
+            if (!(best != best) && (x > best || x != x)) {
+                best = x;
+                arg = c;
+            }
+        }
+        votes[(n * C + arg) * vox + v] += 1;
+    }
+}
+
+// mean: acc *= 1 / E (ATen's mean multiplies the sum by the reciprocal).  majority: one-hot int64 of the label with
+// the most votes, smallest label on ties (torch.mode).
+__global__ void __launch_bounds__(kThreads)
+tta_finalize_kernel(float* __restrict__ acc, const uint8_t* __restrict__ votes, long long* __restrict__ onehot, int C,
+                    long long vox, float inv_members, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    if (acc != nullptr) {
+        acc[t] *= inv_members;       // total = N * C * vox
+        return;
+    }
+    const long long v = t % vox, n = t / vox;   // total = N * vox
+    const uint8_t* p = votes + n * C * vox + v;
+    int best = -1, arg = 0;
+    for (int c = 0; c < C; ++c) {
+        const int k = p[c * vox];
+        if (k > best) {
+            best = k;
+            arg = c;
+        }
+    }
+    long long* o = onehot + n * C * vox + v;
+    for (int c = 0; c < C; ++c) o[c * vox] = c == arg ? 1 : 0;
+}
+
 // =========================================================================================== softmax (NCDHW fp32, in place)
 __global__ void __launch_bounds__(kThreads)
 softmax_ncdhw_kernel(float* __restrict__ data, int channels, long long voxels, int sm_channels, float diag_bias,
@@ -632,6 +737,59 @@ int b200seg_copy_view(b200seg_view in, b200seg_view out, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_DTYPE(in.dtype, (copy_view_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(di, dout, total)));
     return check_launch("copy_view");
+}
+
+static int check_xform(const int32_t perm[3], const int32_t flip[3], TtaXform* xf, const char* what) {
+    int seen = 0;
+    for (int k = 0; k < 3; ++k) {
+        B200SEG_CHECK_ARG(perm[k] >= 0 && perm[k] <= 2, "%s: perm[%d] = %d", what, k, perm[k]);
+        seen |= 1 << perm[k];
+        xf->perm[k] = perm[k];
+        xf->flip[k] = flip[k] ? 1 : 0;
+    }
+    B200SEG_CHECK_ARG(seen == 7, "%s: perm is not a permutation of (0, 1, 2)", what);
+    return B200SEG_OK;
+}
+
+int b200seg_pack_ncdhw_tta(const float* src, int32_t w0, int32_t w1, int32_t w2, const int32_t perm[3],
+                           const int32_t flip[3], b200seg_view dst, void* stream) {
+    B200SEG_CHECK_ARG(src != nullptr, "pack_ncdhw_tta: null source");
+    int rc = validate_view(dst, "pack_ncdhw_tta dst");
+    if (rc) return rc;
+    TtaXform xf;
+    rc = check_xform(perm, flip, &xf, "pack_ncdhw_tta");
+    if (rc) return rc;
+    const int W[3] = {w0, w1, w2};
+    B200SEG_CHECK_ARG(dst.z == W[perm[0]] && dst.y == W[perm[1]] && dst.x == W[perm[2]],
+                      "pack_ncdhw_tta: dst extent (%d, %d, %d) is not the permuted source extent", dst.z, dst.y, dst.x);
+    DView dd = make_dview(dst);
+    long long total = 1LL * dd.n * ((dd.c + 7) / 8) * dd.chunk_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_DTYPE(dst.dtype, (pack_ncdhw_tta_kernel<T><<<blocks_for(total), kThreads, 0, s>>>(src, dd, w0, w1, w2, xf, total)));
+    return check_launch("pack_ncdhw_tta");
+}
+
+int b200seg_tta_accumulate(const float* member, int64_t n, int32_t c, int32_t w0, int32_t w1, int32_t w2,
+                           const int32_t perm[3], const int32_t flip[3], float* acc, uint8_t* votes, void* stream) {
+    B200SEG_CHECK_ARG(member != nullptr && n > 0 && c > 0 && w0 > 0 && w1 > 0 && w2 > 0, "tta_accumulate: bad arguments");
+    B200SEG_CHECK_ARG((acc != nullptr) != (votes != nullptr), "tta_accumulate: exactly one of acc / votes");
+    TtaXform xf;
+    int rc = check_xform(perm, flip, &xf, "tta_accumulate");
+    if (rc) return rc;
+    long long total = n * w0 * w1 * w2;
+    tta_accumulate_kernel<<<blocks_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(member, c, w0, w1, w2, xf,
+                                                                                                 acc, votes, total);
+    return check_launch("tta_accumulate");
+}
+
+int b200seg_tta_finalize(float* acc, const uint8_t* votes, int64_t* onehot, int64_t n, int32_t c, int64_t voxels,
+                         int32_t members, void* stream) {
+    B200SEG_CHECK_ARG(n > 0 && c > 0 && voxels > 0 && members > 0 && members <= 255, "tta_finalize: bad arguments");
+    B200SEG_CHECK_ARG((acc != nullptr) != (votes != nullptr && onehot != nullptr), "tta_finalize: acc, or votes + onehot");
+    long long total = acc != nullptr ? n * c * voxels : n * voxels;
+    tta_finalize_kernel<<<blocks_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        acc, votes, reinterpret_cast<long long*>(onehot), c, voxels, 1.0f / static_cast<float>(members), total);
+    return check_launch("tta_finalize");
 }
 
 int b200seg_copy_planes(const float* patch, int32_t c, int32_t p0, int32_t p1, int32_t p2, int32_t plane_lo,

@@ -206,7 +206,7 @@ class CompiledPlan:
                 # uninitialised memory may hold NaN bit patterns)
                 buf.tensor.zero_()
                 ws[name] = buf
-            if len(self.workspaces) >= 4:
+            if len(self.workspaces) >= 8:       # 6 orientations of a non-cubic patch + ragged last batches
                 self.workspaces.pop(next(iter(self.workspaces)))
             self.workspaces[key] = ws
         return ws

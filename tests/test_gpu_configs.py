@@ -180,3 +180,33 @@ def test_config3_nested_10class_sliding_window_against_oracle():
             set_precision("auto")
         assert probs.shape[0] == 10
         assert rel_err(probs.cpu(), torch.from_numpy(ref)) <= tol, precision
+
+
+def test_config4_full_width_standard_predict_sagittal_split():
+    """BASELINE config 4 at its real width: NestedResUNet(3, 2, 40, dropout 0.2) in eval mode on 3 x 96 x 88 x 24 whole
+    volumes through StandardPredict(sagittal_split=True) (reference prediction.py:73-102), vs the oracle."""
+    from segmentation_pipeline import _tio, models as M
+    from segmentation_pipeline.models import set_precision
+    from segmentation_pipeline.prediction import StandardPredict
+    torch.manual_seed(11)
+    model = M.NestedResUNet(3, 2, 40, dropout_p=0.2)
+    _perturb_bn(model, 12)
+    model.eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(13)
+    vols = [torch.randn(3, 96, 88, 24, generator=g) for _ in range(2)]
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        ref = unet.reverse_split_and_flip(unet.nested_res_unet_forward(sd, unet.split_and_flip(torch.stack(vols))))
+    model.cuda()
+    for precision, tol in (("fp32", 1e-5), ("bf16", 2e-2)):
+        subjects = [_tio.Subject(X=_tio.ScalarImage(tensor=v), name=f"s{i}") for i, v in enumerate(vols)]
+        set_precision(precision)
+        try:
+            for _ in range(3):          # third call replays the captured CUDA graph of the plan
+                out, batch = StandardPredict(sagittal_split=True).predict(model, torch.device("cuda"), subjects)
+        finally:
+            set_precision("auto")
+        assert batch["y_pred"].shape == (2, 2, 96, 88, 24)
+        assert rel_err(batch["y_pred"].cpu(), ref) <= tol, precision
+        assert rel_err(out[1]["y_pred"]["data"], ref[1]) <= tol

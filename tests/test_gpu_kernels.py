@@ -99,6 +99,44 @@ def test_softmax_and_stochastic_matrix(lib):
     assert rel_err(y.cpu(), unet.stochastic_matrix(x, 3, 1.5)) <= 1e-6
 
 
+# ----------------------------------------------------------------------------------------------- test-time augmentation
+def test_tta_kernels_match_tensor_expressions(lib):
+    """pack_ncdhw_tta / tta_accumulate / tta_finalize against the reference's flip / permute / stack / mean / argmax /
+    mode / one_hot expressions (models/ensemble.py:16-35, 88-103) on a non-cubic volume, all 48 orientations."""
+    import itertools
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 3, 6, 5, 4, generator=g)
+    flips = [()] + [c for k in (1, 2, 3) for c in itertools.combinations((2, 3, 4), k)]
+    members, packs = [], []
+    acc = torch.zeros(2, 5, 6, 5, 4, device="cuda")
+    votes = torch.zeros(2, 5, 6, 5, 4, dtype=torch.uint8, device="cuda")
+    e = 0
+    for perm in itertools.permutations((2, 3, 4)):
+        inv = tuple((torch.argsort(torch.tensor(perm)) + 2).tolist())
+        xp = x.permute(0, 1, *perm)
+        for dims in flips:
+            xt = xp.flip(dims).contiguous()
+            p0 = tuple(p - 2 for p in perm)
+            fl = tuple((k + 2) in dims for k in range(3))
+            # input side: packing with the transform == packing the transformed tensor
+            buf = lib.Blocked(2, 1, *xt.shape[2:], torch.float32, "cuda")
+            lib.pack_ncdhw_tta(dev(x), p0, fl, buf.view(3))
+            assert torch.equal(from_blocked(lib, buf, 3), xt)
+            # a fake member output in the member's space (integers -> many argmax ties, exact sums)
+            y = torch.randint(0, 3, (2, 5, *xt.shape[2:]), generator=g).float()
+            members.append(y.flip(dims).permute(0, 1, *inv))
+            lib.tta_accumulate(dev(y), p0, fl, acc, None)
+            lib.tta_accumulate(dev(y), p0, fl, None, votes)
+            e += 1
+    stacked = torch.stack(members)
+    lib.tta_finalize(acc, None, None, e)
+    assert rel_err(acc.cpu(), stacked.mean(0)) <= 1e-6
+    onehot = torch.empty(votes.shape, dtype=torch.int64, device="cuda")
+    lib.tta_finalize(None, votes, onehot, e)
+    want = F.one_hot(torch.mode(stacked.argmax(2), dim=0).values, num_classes=5).movedim(-1, 1)
+    assert torch.equal(onehot.cpu(), want)
+
+
 # ----------------------------------------------------------------------------------------------- grid
 @pytest.mark.parametrize("padding_mode,overlap,size,patch", [
     (None, (4, 2, 2), (20, 17, 13), (8, 8, 6)), ("edge", (4, 2, 2), (20, 17, 13), (8, 8, 6)),

@@ -208,7 +208,19 @@ def test_components_forward():
             assert rel_err(M.EnsembleFlips(base, "mean")(x).cpu(), t("ens_flips_mean")) <= 1e-5
             assert rel_err(M.EnsembleOrientations(base, "mean")(x).cpu(), t("ens_orient_mean")) <= 1e-5
             maj = M.EnsembleFlips(base, "majority")(x).cpu()
+            # two different members: EnsembleModels, fused, vs the oracle on both state_dicts
+            other = M.ModularUNet(1, 2, [8, 8], 2)
+            torch.manual_seed(9)
+            for prm in other.parameters():
+                torch.nn.init.normal_(prm, std=0.2)
+            other.eval().cuda()
+            got = M.EnsembleModels([base, other], "mean")(x).cpu()
         assert (maj.numpy() == z["ens_flips_majority"]).mean() >= 0.999
+        assert maj.dtype == torch.int64
+        cfg = {"depth": 2, "filters": [8, 8], "block": {"residual": False}, "down": "avgpool", "up": "trilinear"}
+        sds = [{k: v.detach().cpu() for k, v in m.state_dict().items()} for m in (base, other)]
+        want = unet.ensemble_models([lambda t, sd=sd: unet.modular_unet_forward(sd, t, cfg) for sd in sds], t("ens_x"))
+        assert rel_err(got, want) <= 1e-5
     finally:
         set_precision("auto")
 
