@@ -609,6 +609,27 @@ def run_gpu_arm(args) -> None:
         e2e_steps = max(1, min(args.steps, 5))
         ms_e2e = timed(step_e2e, e2e_steps)
 
+    # ---- patch_batch_size = 1, the reference inference script's setting (research/msseg2/competition/ms-inference.py:32):
+    #      144 single-patch forwards per volume; the plan of one patch is replayed as a CUDA graph
+    batch1 = None
+    if rank == 0:
+        p1 = PatchPredict(patch_batch_size=1, patch_size=PATCH, patch_overlap=OVERLAP, padding_mode=PADDING)
+        with torch.no_grad():
+            for _ in range(2):
+                p1.predict_volume(model, vol_dev, want_probs=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                _, lab1 = p1.predict_volume(model, vol_dev, want_probs=False)
+            e1.record()
+            torch.cuda.synchronize()
+            _, lab48 = predictor.predict_volume(model, vol_dev, want_probs=False)
+        ms1 = e0.elapsed_time(e1) / 3
+        batch1 = {"patch_batch": 1, "ms_per_volume": ms1, "value": vox / (ms1 * 1e-3) / 1e6, "unit": UNIT,
+                  "slowdown_vs_patch_batch_%d" % PATCH_BATCH: ms1 / (ms / args.steps),
+                  "labels_identical_to_batched": bool(torch.equal(lab1, lab48)),
+                  "how": "plan of one 96^3 patch captured once as a CUDA graph and replayed 144 times"}
     # ---- z-slab mode: one config-3 volume over all ranks (strong scaling; the collective path)
     set_precision("bf16")
     slab = run_slab_section(world, rank, device) if (world > 1 or args.slab) else None
@@ -653,6 +674,7 @@ def run_gpu_arm(args) -> None:
     if slab is not None:
         line["slab"] = slab
     line["cohort_config4"] = cohort4
+    line["patch_batch_1"] = batch1
     if world == 1:
         threads = os.cpu_count() or 1
         ref = CpuReference(threads)
