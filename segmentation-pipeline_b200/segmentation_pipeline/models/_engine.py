@@ -211,6 +211,15 @@ class CompiledPlan:
             self.workspaces[key] = ws
         return ws
 
+    def workspace_bytes(self, n: int, z: int, y: int, x: int) -> int:
+        """Device memory of the activation workspace of one (n, z, y, x) input (+ its fp32 output)."""
+        esize = 2 if self.act_dtype == torch.bfloat16 else 4
+        total = 0
+        for chunks, level in self.plan.buffers.values():
+            vox = (z * y * x) >> (3 * level) if level >= 0 else (z * y * x) << (-3 * level)
+            total += chunks * 8 * vox * esize
+        return n * (total + self.plan.out_channels * z * y * x * 4)
+
     def input_buffer(self, n: int, z: int, y: int, x: int):
         """The blocked input buffer of a workspace (so that the grid sampler can extract patches into it)."""
         return self._workspace(n, z, y, x)["in"]

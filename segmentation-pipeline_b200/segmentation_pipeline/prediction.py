@@ -26,6 +26,19 @@ from .utils import Config, collate_subjects
 
 LABELS_KEY = "_b200_labels"   # device uint8 label map stashed next to 'y_pred' by PatchPredict
 
+# Device-side regrouping of patches.  ``patch_batch_size`` is a MEMORY knob of the reference (the msseg2 inference script
+# uses 1 to fit a 32 GB V100, research/msseg2/competition/ms-inference.py:32): patch forwards are independent and the
+# aggregation runs in sorted patch order whatever the grouping, so the result does not depend on it bit for bit (tested).
+# On a 180 GB B200 a native network therefore evaluates up to DEVICE_BATCH patches per launch sequence when the caller's
+# batch is smaller and the activation workspace fits in a quarter of the free memory.  0 = literal patch_batch_size.
+DEVICE_BATCH = [int(__import__("os").environ.get("B200SEG_DEVICE_BATCH", "48"))]
+
+
+def set_device_batch(n: int) -> None:
+    """Upper bound of the device-side patch regrouping of native networks (0: use ``patch_batch_size`` literally)."""
+    DEVICE_BATCH[0] = int(n)
+
+
 
 def _lib():
     import b200seg
@@ -158,8 +171,14 @@ class PatchPredict(Predictor):
             compiled = _engine.compiled_for(model, precision, device)
             if compiled.plan.out_scale != 0:
                 raise RuntimeError("PatchPredict needs a network whose output extent equals its input extent")
+        batch_size = self.patch_batch_size
+        if native and DEVICE_BATCH[0] > batch_size:
+            per_patch = compiled.workspace_bytes(1, p0, p1, p2)
+            free = torch.cuda.mem_get_info(device)[0]
+            fit = max(int(0.25 * free // max(per_patch, 1)), 1)
+            batch_size = max(batch_size, min(DEVICE_BATCH[0], fit, len(grid.locations)))
         out = None
-        for locations in grid.batches(self.patch_batch_size):
+        for locations in grid.batches(batch_size):
             b = len(locations)
             if native:
                 in_buf = compiled.input_buffer(b, p0, p1, p2)

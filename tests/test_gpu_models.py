@@ -233,11 +233,13 @@ def _small_model():
     return meta, sd, model.eval().cuda()
 
 
+@pytest.mark.parametrize("device_batch", [0, 48])     # literal patch_batch_size (ragged batches) / regrouped on the device
 @pytest.mark.parametrize("padding_mode,overlap_mode", [(None, "average"), ("edge", "average"), ("edge", "crop")])
-def test_patch_predict_matches_oracle_sliding_window(padding_mode, overlap_mode):
-    from segmentation_pipeline import _tio
+def test_patch_predict_matches_oracle_sliding_window(padding_mode, overlap_mode, device_batch, monkeypatch):
+    from segmentation_pipeline import _tio, prediction
     from segmentation_pipeline.models import set_precision
     from segmentation_pipeline.prediction import PatchPredict, add_evaluation_labels
+    monkeypatch.setattr(prediction, "DEVICE_BATCH", [device_batch])
     meta, sd, model = _small_model()
     g = torch.Generator().manual_seed(21)
     vol = torch.randn(2, 40, 36, 28, generator=g)
@@ -260,6 +262,30 @@ def test_patch_predict_matches_oracle_sliding_window(padding_mode, overlap_mode)
     assert lab.dtype == torch.int64 and lab.shape == (1, 40, 36, 28)
     # labels are the argmax of the probabilities we returned, bit-exactly (ties -> lowest index)
     np.testing.assert_array_equal(lab.numpy(), evalstats.argmax_labels(y_pred["data"].numpy()))
+
+
+def test_device_regrouping_does_not_change_a_bit(monkeypatch):
+    """patch_batch_size is a memory knob: 1, 5 (ragged) or regrouped to 48 on the device give identical outputs."""
+    from segmentation_pipeline import prediction
+    from segmentation_pipeline.models import set_precision
+    from segmentation_pipeline.prediction import PatchPredict
+    meta, sd, model = _small_model()
+    vol = torch.randn(2, 40, 36, 28, generator=torch.Generator().manual_seed(24)).cuda()
+    outs = []
+    set_precision("bf16")
+    try:
+        with torch.no_grad():
+            for batch, device_batch in ((1, 0), (5, 0), (1, 48), (16, 48)):
+                monkeypatch.setattr(prediction, "DEVICE_BATCH", [device_batch])
+                p = PatchPredict(patch_batch_size=batch, patch_size=(16, 16, 16), patch_overlap=(8, 8, 4),
+                                 padding_mode="edge")
+                for _ in range(3 if batch == 1 else 1):          # batch 1 literal: third call replays the CUDA graph
+                    probs, labels = p.predict_volume(model, vol)
+                outs.append((probs.clone(), labels.clone()))
+    finally:
+        set_precision("auto")
+    for probs, labels in outs[1:]:
+        assert torch.equal(probs, outs[0][0]) and torch.equal(labels, outs[0][1])
 
 
 def test_patch_predict_config_attributes():
