@@ -212,6 +212,19 @@ int b200seg_argmax(const float* probs, int32_t c, int64_t voxels, int64_t* label
 int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes, int64_t voxels,
                       int32_t num_classes, int64_t* cm, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ criterion
+ * HybridLogisticDiceLoss.forward (criterions/hybrid_logistic_dice_loss.py:13-43): prediction / target fp32
+ * (N, C, voxels) contiguous.  ONE pass produces sums[n*c][4] = {sum p t, sum p^2 | p, sum t^2 | t,
+ * sum t log((p + 1e-8) / (1 + 1e-8))} and out3 = {loss, dice_loss, logistic_loss}; class_weights may be NULL.
+ * The backward call writes d loss / d prediction * grad_loss[0] from the saved sums (one elementwise pass). */
+int64_t b200seg_hybrid_loss_scratch_bytes(int64_t n, int32_t c);
+int b200seg_hybrid_loss_forward(const float* prediction, const float* target, int64_t n, int32_t c, int64_t voxels,
+                                float dice_weight, const float* class_weights, int32_t square_dice, void* scratch,
+                                int64_t scratch_bytes, float* sums, float* out3, void* stream);
+int b200seg_hybrid_loss_backward(const float* prediction, const float* target, const float* sums, int64_t n, int32_t c,
+                                 int64_t voxels, float dice_weight, const float* class_weights, int32_t square_dice,
+                                 const float* grad_loss, float* grad_prediction, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,8 +10,8 @@ Why an import hook.  Both trees are regular packages called ``segmentation_pipel
 ``transforms``, ``loggers`` ..., none of which this package rebuilds).  ``install`` therefore registers a meta-path
 finder that resolves every ``segmentation_pipeline.*`` module FILE BY FILE:
 
-  * the modules of the hot path come from this package (``SHADOW``): ``prediction``, ``models.*`` and the two
-    evaluators whose voxel work is the device confusion histogram;
+  * the modules of the hot path come from this package (``SHADOW``): ``prediction``, ``models.*``, the two
+    evaluators whose voxel work is the device confusion histogram, and the criterion;
   * every other module, and every package ``__init__``, is the reference's own file, executed unmodified -- so
     ``segmentation_trainer.py``, the transforms, ``TorchContext``, the data loaders and the ``research/*`` configs see
     exactly the namespace they were written against (``from .evaluators import *``, ``from segmentation_pipeline
@@ -40,6 +40,7 @@ SHADOW = frozenset({
     "models",                       # the package __init__ too (same exports + set_precision / get_precision)
     "models.components", "models.modular_unet", "models.nested_residual_unet", "models.ensemble", "models.utils",
     "evaluators.segmentation_evaluator", "evaluators.label_map_evaluator",
+    "criterions.hybrid_logistic_dice_loss",
 })
 
 

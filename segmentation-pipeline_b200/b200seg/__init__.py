@@ -69,6 +69,11 @@ _SIGNATURES = {
     "b200seg_finalize_region": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                           POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200seg_argmax": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200seg_hybrid_loss_scratch_bytes": (c_int64, [c_int64, c_int32]),
+    "b200seg_hybrid_loss_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p, c_int32,
+                                              c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200seg_hybrid_loss_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p,
+                                               c_int32, c_void_p, c_void_p, c_void_p]),
     "b200seg_confusion": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -406,3 +411,36 @@ def confusion(pred: torch.Tensor, target: torch.Tensor, num_classes: int, cm: to
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_confusion(_ptr(pred), _ptr(target), pred.element_size(), pred.numel(), num_classes,
                                             _ptr(cm), _stream()), "confusion")
+
+
+def hybrid_loss_forward(prediction: torch.Tensor, target: torch.Tensor, dice_weight: float,
+                        class_weights: Optional[torch.Tensor], square_dice: bool):
+    """-> (out3 fp32 [loss, dice_loss, logistic_loss], sums fp32 (N*C, 4)) on the device."""
+    _require_cuda(prediction, target, class_weights)
+    assert prediction.dtype == torch.float32 and target.dtype == torch.float32
+    assert prediction.is_contiguous() and target.is_contiguous() and prediction.shape == target.shape
+    n, c = prediction.shape[:2]
+    vox = prediction[0, 0].numel()
+    lib = load_library()
+    need = int(lib.b200seg_hybrid_loss_scratch_bytes(n, c))
+    scratch = torch.empty(need // 8, dtype=torch.float64, device=prediction.device)
+    sums = torch.empty((n * c, 4), dtype=torch.float32, device=prediction.device)
+    out3 = torch.empty(3, dtype=torch.float32, device=prediction.device)
+    _LAUNCHES[0] += 2
+    _check(lib.b200seg_hybrid_loss_forward(_ptr(prediction), _ptr(target), n, c, vox, float(dice_weight),
+                                           _ptr(class_weights), 1 if square_dice else 0, _ptr(scratch), need, _ptr(sums),
+                                           _ptr(out3), _stream()), "hybrid_loss_forward")
+    return out3, sums
+
+
+def hybrid_loss_backward(prediction: torch.Tensor, target: torch.Tensor, sums: torch.Tensor, dice_weight: float,
+                         class_weights: Optional[torch.Tensor], square_dice: bool, grad_loss: torch.Tensor) -> torch.Tensor:
+    _require_cuda(prediction, target, sums, grad_loss, class_weights)
+    n, c = prediction.shape[:2]
+    vox = prediction[0, 0].numel()
+    grad = torch.empty_like(prediction)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_hybrid_loss_backward(_ptr(prediction), _ptr(target), _ptr(sums), n, c, vox,
+                                                       float(dice_weight), _ptr(class_weights), 1 if square_dice else 0,
+                                                       _ptr(grad_loss), _ptr(grad), _stream()), "hybrid_loss_backward")
+    return grad

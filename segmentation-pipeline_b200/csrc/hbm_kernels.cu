@@ -402,45 +402,70 @@ overlap_add_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const
     const int kk = (t - jj * bdv) * VEC + bk0;
     const int j = jj + bj0;
     float* o = out + ((static_cast<long long>(c) * PW + i) * PH + j) * PD + kk;
-    float acc[VEC];
-    bool touched = false, loaded = false;
+    // Pass 1: which patches of the batch cover this voxel (batch order = the reference's accumulation order).
+    // Pass 2: issue the loads of up to 8 of them together (8 = 2 per axis at overlap <= 50 %), then add in order --
+    // the loads are independent, so the latency of the gather is paid once per group instead of once per patch.
+    constexpr int kGroup = 8;
     const long long pvox = 1LL * p0 * p1 * p2;
+    unsigned long long list = 0;      // up to 8 patch indices, one byte each (a dynamically indexed array would spill)
+    int n_src = 0;
+    float acc[VEC];
+    bool loaded = false;
+    auto flush = [&]() {
+        float v[kGroup][VEC];
+#pragma unroll
+        for (int q = 0; q < kGroup; ++q) {
+            if (q < n_src) {
+                const int b = static_cast<int>((list >> (8 * q)) & 0xffull);
+                const float* sp = patches + (static_cast<long long>(b) * C + c) * pvox +
+                                  (static_cast<long long>(i - lb.loc[b][0]) * p1 + (j - lb.loc[b][1])) * p2 +
+                                  (kk - lb.loc[b][2]);
+                if constexpr (VEC == 4) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(sp));
+                    v[q][0] = t4.x; v[q][1] = t4.y; v[q][2] = t4.z; v[q][VEC - 1] = t4.w;
+                } else {
+                    v[q][0] = __ldg(sp);
+                }
+            }
+        }
+        if (!loaded) {
+            if constexpr (VEC == 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(o);
+                acc[0] = t4.x; acc[1] = t4.y; acc[2] = t4.z; acc[VEC - 1] = t4.w;
+            } else {
+                acc[0] = *o;
+            }
+            loaded = true;
+        }
+#pragma unroll
+        for (int q = 0; q < kGroup; ++q) {
+            if (q < n_src) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += v[q][e];
+            }
+        }
+        n_src = 0;
+        list = 0;
+    };
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         unsigned int m = cand[half];
         while (m) {
             const int b = (__ffs(m) - 1) + half * 32;
             m &= m - 1;
-            const int i0 = lb.loc[b][0], j0 = lb.loc[b][1], k0 = lb.loc[b][2];
-            if (j < j0 || j >= lb.loc[b][4] || kk < k0 || kk >= lb.loc[b][5]) continue;
-            if (!loaded) {
-                if constexpr (VEC == 4) {
-                    float4 v = *reinterpret_cast<const float4*>(o);
-                    acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[VEC - 1] = v.w;
-                } else {
-                    acc[0] = *o;
-                }
-                loaded = true;
-            }
-            const float* p = patches + (static_cast<long long>(b) * C + c) * pvox +
-                             (static_cast<long long>(i - i0) * p1 + (j - j0)) * p2 + (kk - k0);
-            if constexpr (VEC == 4) {
-                float4 v = __ldg(reinterpret_cast<const float4*>(p));
-                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[VEC - 1] += v.w;
-            } else {
-                acc[0] += __ldg(p);
-            }
-            touched = true;
+            if (j < lb.loc[b][1] || j >= lb.loc[b][4] || kk < lb.loc[b][2] || kk >= lb.loc[b][5]) continue;
+            list |= static_cast<unsigned long long>(b) << (8 * n_src);
+            if (++n_src == kGroup) flush();
         }
     }
-    if (!touched) return;
+    if (n_src) flush();
+    if (!loaded) return;
     if constexpr (VEC == 4) {
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[VEC - 1]);
     } else {
         *o = acc[0];
     }
 }
-
 // 'crop' mode: every patch assigns the centre crop of itself; patches are processed in order, later wins.
 __global__ void __launch_bounds__(kThreads)
 overlap_crop_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
@@ -533,88 +558,94 @@ finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, co
 }
 
 // =========================================================================================== confusion histogram
-// Per-lane private columns in shared memory: hist[bin][lane] is only ever touched by lane `lane` of one warp,
-// so increments are plain read-modify-writes with bank == lane (no atomics, no conflicts).  One int64 global
-// atomic per bin per block at the end.
+// One private histogram per WARP in shared memory (bins = nc * nc counters: 400 bytes for 10 classes, so every SM runs
+// at full occupancy; round 1 kept a column per LANE, 32 x the memory, and ran at 8-16 warps per SM).  Label maps are
+// piecewise constant, so the common case is a 16-byte vector whose voxels all fall into one bin: the lanes of the warp
+// that hold the same bin are grouped with __match_any_sync, the group's voxel count is summed with __reduce_add_sync
+// and ONE lane adds it (a single conflict-free shared-memory atomic per distinct bin).  Vectors that straddle a label
+// boundary take the run-length path, one shared-memory atomic per run.  One int64 global atomic per non-empty bin per block at the end.
 template <typename L>
 __global__ void __launch_bounds__(kThreads)
 confusion_kernel(const L* __restrict__ pred, const L* __restrict__ targ, long long voxels, int nc,
-                 unsigned long long* __restrict__ cm, int warps_with_hist) {
-    extern __shared__ unsigned int hist[];  // [warp][bin][32]
+                 unsigned long long* __restrict__ cm) {
+    extern __shared__ unsigned int hist[];  // [warp][bin]
     const int bins = nc * nc;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    for (int i = threadIdx.x; i < warps_with_hist * bins * 32; i += blockDim.x) hist[i] = 0;
+    constexpr int kWarps = kThreads / 32;
+    for (int i = threadIdx.x; i < kWarps * bins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    unsigned int* mine = hist + (warp % warps_with_hist) * bins * 32 + lane;
-    const bool shared_cols = warps_with_hist < static_cast<int>(blockDim.x / 32);
+    unsigned int* mine = hist + warp * bins;
     constexpr int PER = 16 / sizeof(L);  // labels per 16-byte load
     const long long nvec = voxels / PER;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    // one 16-byte vector of each label map: run-length accumulation -- label maps are piecewise constant, so
-    // consecutive voxels mostly hit the same bin and one shared-memory update covers the whole run
-    auto count_vec = [&](const uint4& pr, const uint4& tr) {
+    // values outside [0, nc) fall into the LAST class ("other"): nothing is dropped, so row / column sums are the
+    // true marginals (the unsigned compare also catches negative int64 labels)
+    auto bin_of = [&](L p, L t) -> int {
+        const unsigned long long pu = static_cast<unsigned long long>(p), tu = static_cast<unsigned long long>(t);
+        const int pi = pu < static_cast<unsigned long long>(nc) ? static_cast<int>(pu) : nc - 1;
+        const int ti = tu < static_cast<unsigned long long>(nc) ? static_cast<int>(tu) : nc - 1;
+        return ti * nc + pi;
+    };
+    // called by ALL 32 lanes together (lanes past the end pass valid = false)
+    auto count_vec = [&](const uint4& pr, const uint4& tr, bool valid) {
         const L* pp = reinterpret_cast<const L*>(&pr);
         const L* tp = reinterpret_cast<const L*>(&tr);
-        int cur = -1;
-        unsigned int run = 0;
+        bool uniform = true;
+        int bin0 = 0;
+        if (valid) {
+            // all labels of the vector equal <=> every 32-bit word equals the first one rotated ... cheap exact test:
+            bin0 = bin_of(pp[0], tp[0]);
 #pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            // values outside [0, nc) fall into the LAST class ("other"): nothing is dropped, so row / column sums are
-            // the true marginals (the unsigned compare also catches negative int64 labels)
-            const unsigned long long pu = static_cast<unsigned long long>(pp[q]), tu = static_cast<unsigned long long>(tp[q]);
-            const int p = pu < static_cast<unsigned long long>(nc) ? static_cast<int>(pu) : nc - 1;
-            const int tt = tu < static_cast<unsigned long long>(nc) ? static_cast<int>(tu) : nc - 1;
-            const int bin = tt * nc + p;
-            if (bin == cur) {
-                ++run;
-            } else {
-                if (cur >= 0) {
-                    if (shared_cols) atomicAdd(mine + cur * 32, run);
-                    else mine[cur * 32] += run;
-                }
-                cur = bin;
-                run = 1;
-            }
+            for (int q = 1; q < PER; ++q) uniform = uniform && (pp[q] == pp[0]) && (tp[q] == tp[0]);
         }
-        if (cur >= 0) {
-            if (shared_cols) atomicAdd(mine + cur * 32, run);
-            else mine[cur * 32] += run;
+        const unsigned fast = __ballot_sync(0xffffffffu, valid && uniform);
+        if (valid && uniform) {
+            const unsigned peers = __match_any_sync(fast, bin0);
+            if (lane == __ffs(peers) - 1) atomicAdd(mine + bin0, static_cast<unsigned>(PER * __popc(peers)));
+        } else if (valid) {
+            int cur = bin0;
+            unsigned run = 1;
+#pragma unroll
+            for (int q = 1; q < PER; ++q) {
+                const int b = bin_of(pp[q], tp[q]);
+                if (b == cur) {
+                    ++run;
+                } else {
+                    atomicAdd(mine + cur, run);
+                    cur = b;
+                    run = 1;
+                }
+            }
+            atomicAdd(mine + cur, run);
         }
     };
-    // four vector pairs (128 bytes) in flight per thread: the histogram needs so much shared memory that only 16
-    // warps fit on an SM, so the loads of several iterations have to overlap to cover the HBM latency
+    // four vector pairs (128 bytes) in flight per thread
     const uint4* pv = reinterpret_cast<const uint4*>(pred);
     const uint4* tv = reinterpret_cast<const uint4*>(targ);
-    long long v = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
-    for (; v + 3 * stride < nvec; v += 4 * stride) {
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const long long warp_base = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) - lane;   // first vector of this warp
+    for (long long w0 = warp_base; w0 < nvec; w0 += 4 * stride) {      // warp-uniform trip count
         uint4 pr[4], tr[4];
+        bool ok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            pr[u] = __ldg(pv + v + u * stride);
-            tr[u] = __ldg(tv + v + u * stride);
+            const long long v = w0 + lane + u * stride;
+            ok[u] = v < nvec;
+            pr[u] = ok[u] ? __ldg(pv + v) : zero;
+            tr[u] = ok[u] ? __ldg(tv + v) : zero;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) count_vec(pr[u], tr[u]);
+        for (int u = 0; u < 4; ++u) count_vec(pr[u], tr[u], ok[u]);
     }
-    for (; v < nvec; v += stride) count_vec(__ldg(pv + v), __ldg(tv + v));
     // tail (voxels not a multiple of PER): first thread of the grid
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (long long v = nvec * PER; v < voxels; ++v) {
-            const unsigned long long pu = static_cast<unsigned long long>(pred[v]), tu = static_cast<unsigned long long>(targ[v]);
-            const int p = pu < static_cast<unsigned long long>(nc) ? static_cast<int>(pu) : nc - 1;
-            const int tt = tu < static_cast<unsigned long long>(nc) ? static_cast<int>(tu) : nc - 1;
-            const int bin = tt * nc + p;
-            if (shared_cols) atomicAdd(mine + bin * 32, 1u);
-            else mine[bin * 32] += 1u;
-        }
+        for (long long v = nvec * PER; v < voxels; ++v) atomicAdd(mine + bin_of(pred[v], targ[v]), 1u);
     }
     __syncthreads();
-    for (int bin = warp; bin < bins; bin += blockDim.x / 32) {
+    for (int bin = threadIdx.x; bin < bins; bin += blockDim.x) {
         unsigned long long s = 0;
-        for (int w = 0; w < warps_with_hist; ++w) s += hist[(w * bins + bin) * 32 + lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && s) atomicAdd(cm + bin, s);
+        for (int w = 0; w < kWarps; ++w) s += hist[w * bins + bin];
+        if (s) atomicAdd(cm + bin, s);
     }
 }
 
@@ -1006,14 +1037,11 @@ int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes,
     B200SEG_CHECK_CUDA(cudaGetDevice(&dev));
     B200SEG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int bins = num_classes * num_classes;
-    const int warps = kThreads / 32;
-    int warps_with_hist = warps;
-    while (warps_with_hist > 1 && 1LL * warps_with_hist * bins * 32 * 4 > 96 * 1024) warps_with_hist /= 2;
-    size_t smem = 1ULL * warps_with_hist * bins * 32 * 4;
-    B200SEG_CHECK_ARG(smem <= 200 * 1024, "confusion: histogram does not fit shared memory");
+    const size_t smem = static_cast<size_t>(kThreads / 32) * bins * sizeof(unsigned int);   // <= 51 KB
     const long long per = label_bytes == 1 ? 16 : 2;
-    long long want = (voxels / per + kThreads - 1) / kThreads;
-    int per_sm = smem > 48 * 1024 ? 2 : 4;
+    // a warp's counter holds up to 2^32 voxels: one CTA sees voxels / grid of them
+    long long want = (voxels / per + 4LL * kThreads - 1) / (4LL * kThreads);
+    const int per_sm = smem > 24 * 1024 ? 4 : 8;
     unsigned grid = static_cast<unsigned>(want < 1LL * sms * per_sm ? (want > 0 ? want : 1) : 1LL * sms * per_sm);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (label_bytes == 1) {
@@ -1022,16 +1050,14 @@ int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes,
         confusion_kernel<uint8_t><<<grid, kThreads, smem, s>>>(static_cast<const uint8_t*>(pred),
                                                                 static_cast<const uint8_t*>(target), voxels,
                                                                 num_classes,
-                                                                reinterpret_cast<unsigned long long*>(cm),
-                                                                warps_with_hist);
+                                                                reinterpret_cast<unsigned long long*>(cm));
     } else {
         B200SEG_CHECK_CUDA(cudaFuncSetAttribute(confusion_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(smem)));
         confusion_kernel<long long><<<grid, kThreads, smem, s>>>(static_cast<const long long*>(pred),
                                                                   static_cast<const long long*>(target), voxels,
                                                                   num_classes,
-                                                                  reinterpret_cast<unsigned long long*>(cm),
-                                                                  warps_with_hist);
+                                                                  reinterpret_cast<unsigned long long*>(cm));
     }
     return check_launch("confusion");
 }

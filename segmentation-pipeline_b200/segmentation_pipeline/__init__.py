@@ -7,12 +7,12 @@ torchio, a GPU or the shared library; calling a forward without libb200seg.so ra
 """
 from . import utils  # noqa: F401
 
-__all__ = ["models", "prediction", "evaluators", "transforms", "utils"]
+__all__ = ["models", "prediction", "evaluators", "criterions", "transforms", "utils"]
 
 
 def __getattr__(name):
     import importlib
-    if name in ("models", "prediction", "evaluators", "transforms", "grid"):
+    if name in ("models", "prediction", "evaluators", "transforms", "grid", "criterions", "distributed"):
         return importlib.import_module(f"{__name__}.{name}")
     if name in ("StandardPredict", "PatchPredict"):
         return getattr(importlib.import_module(f"{__name__}.prediction"), name)

@@ -98,8 +98,18 @@ def main():
     class StubTrainPredictor(sp.prediction.Predictor):
         """Stands in for the training-mode forward (f3, not built): returns tensors the criterion can consume."""
         def predict(self, model, device, subjects, label_attributes=None):
-            y = torch.stack([s["y"]["data"] for s in subjects]).float()
+            y = torch.stack([s["y"]["data"] for s in subjects]).float().to(device)
             return subjects, {"y": y, "y_pred": (y * 0 + 1.0 / y.shape[1]).requires_grad_(True)}
+
+    grads = []
+
+    def criterion(y_pred, y):
+        """On the GPU: the b200 HybridLogisticDiceLoss (fused device kernels, autograd) through the reference namespace;
+        on a CPU-only box the product criterion refuses CPU tensors, so the wiring test uses a trivial stand-in."""
+        if device.type != "cuda":
+            return {"loss": (y_pred * y).mean()}
+        y_pred.register_hook(lambda g: grads.append(float(g.abs().sum())))
+        return sp.HybridLogisticDiceLoss()(y_pred, y)
 
     logs = []
 
@@ -119,7 +129,7 @@ def main():
     dummy = torch.nn.Parameter(torch.zeros(1))
     context = types.SimpleNamespace(
         dataset=dataset, model=model.to(device) if device.type == "cuda" else model, device=device,
-        criterion=sp.HybridLogisticDiceLoss(),                                # the reference's own criterion (CPU, ATen)
+        criterion=criterion,
         optimizer=torch.optim.SGD([dummy], lr=0.1))
     sampler = torch.utils.data.SequentialSampler
     evaluator = sp.SegmentationEvaluator("y_pred_eval", "y_eval", stats_to_output=("TP", "FP", "TN", "FN", "dice"))
@@ -149,6 +159,10 @@ def main():
     out["subject_stats"] = json.loads(stats.to_json(orient="split"))
     out["model_score"] = log["model_score"]
     out["timer_keys"] = sorted(log["timer"].keys())
+    out["train_loss"] = {k: float(log[k]) for k in ("loss", "dice_loss", "logistic_loss") if k in log}
+    out["train_grad_abs_sum"] = grads[-1] if grads else None
+    out["criterion_module"] = sp.HybridLogisticDiceLoss.__module__ + " from " + \
+        ("b200" if "segmentation-pipeline_b200" in finder.resolved.get("segmentation_pipeline.criterions.hybrid_logistic_dice_loss", "") else "reference")
 
     # ------------------------------------------------------------------ the same thing on the CPU oracle
     from oracle import evalstats, grid as ogrid, unet

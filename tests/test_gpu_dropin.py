@@ -34,3 +34,9 @@ def test_reference_trainer_validation_branch_on_gpu(precision):
                                       "served_from": res["served_from"], "subject_stats": stats["data"],
                                       "oracle": res["oracle"], "model_score": res["model_score"]}))
     assert "model_forward_evaluation" in res["timer_keys"] and "evaluation.seg.validation" in res["timer_keys"]
+    # the training step of the same iteration used the b200 criterion (device kernels + autograd) via the reference's name
+    assert res["criterion_module"].endswith("from b200")
+    # uniform prediction 1/3 against a one-hot target: logistic = -log(1/3)/3 per channel on average
+    import math
+    assert abs(res["train_loss"]["logistic_loss"] - math.log(3.0) / 3.0) < 1e-4
+    assert res["train_grad_abs_sum"] is not None and res["train_grad_abs_sum"] > 0

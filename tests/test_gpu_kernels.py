@@ -99,6 +99,32 @@ def test_softmax_and_stochastic_matrix(lib):
     assert rel_err(y.cpu(), unet.stochastic_matrix(x, 3, 1.5)) <= 1e-6
 
 
+# ----------------------------------------------------------------------------------------------- criterion
+@pytest.mark.parametrize("square_dice,weights", [(True, None), (False, [0.3, 1.0, 2.0]), (True, [1.0, 0.5, 0.25])])
+def test_hybrid_logistic_dice_loss_matches_oracle_and_autograd(lib, square_dice, weights):
+    """Fused device loss vs the oracle restatement of criterions/hybrid_logistic_dice_loss.py:13-43 (itself pinned to the
+    reference class by tests/golden/components.npz), values within 1e-5 and d loss / d prediction within 1e-4 of
+    torch autograd through the oracle expression."""
+    from oracle import unet
+    from segmentation_pipeline.criterions import HybridLogisticDiceLoss
+    g = torch.Generator().manual_seed(61)
+    logits = torch.randn(2, 3, 9, 10, 11, generator=g)
+    pred = torch.softmax(logits, 1)
+    targ = F.one_hot(torch.randint(0, 3, (2, 9, 10, 11), generator=g), 3).permute(0, 4, 1, 2, 3).float()
+    p_ref = pred.clone().requires_grad_(True)
+    ref = unet.hybrid_logistic_dice_loss(p_ref, targ, dice_weight=0.3, logistic_class_weights=weights,
+                                         square_dice=square_dice)
+    ref["loss"].backward()
+    p_dev = pred.cuda().requires_grad_(True)
+    got = HybridLogisticDiceLoss(dice_weight=0.3, logistic_class_weights=weights, square_dice=square_dice)(p_dev, targ.cuda())
+    (got["loss"] * 2.0).backward()                       # non-unit upstream gradient
+    for k in ("loss", "dice_loss", "logistic_loss"):
+        assert abs(float(got[k]) - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), k
+    assert rel_err(p_dev.grad.cpu(), 2.0 * p_ref.grad) <= 1e-4
+    with pytest.raises(RuntimeError):
+        HybridLogisticDiceLoss()(pred, targ)             # CPU tensors: loud error
+
+
 # ----------------------------------------------------------------------------------------------- test-time augmentation
 def test_tta_kernels_match_tensor_expressions(lib):
     """pack_ncdhw_tta / tta_accumulate / tta_finalize against the reference's flip / permute / stack / mean / argmax /

@@ -16,7 +16,19 @@ import b200seg  # noqa: E402
 from segmentation_pipeline.grid import PatchGrid  # noqa: E402
 
 
+ONCE = "--once" in sys.argv      # under ncu: one warm-up + one measured launch per kernel (ncu reports the durations)
+
+
 def timed(fn, flush, reps=10):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        flush.zero_()
+        torch.cuda.nvtx.range_push("measured")
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return float("nan")
     best = 1e9
     for i in range(3 + reps):
         flush.zero_()
@@ -97,6 +109,9 @@ def main():
     t = timed(lambda: b200seg.confusion(a64, b64, 10, cm), flush)
     rows.append(("confusion 10 classes, int64, 224^3", 2 * 8 * v3, t))
 
+    if ONCE:
+        print(json.dumps([{"name": n, "bytes": b} for n, b, _ in rows]))
+        return
     print(f"{'kernel':52s} {'MB':>9s} {'ms':>8s} {'GB/s':>8s} {'of measured copy peak':>22s}")
     for name, nbytes, ms in rows:
         gbs = nbytes / ms / 1e6
