@@ -438,6 +438,46 @@ def run_slab_section(world: int, rank: int, device, steps: int = 3, warmup: int 
     return out
 
 
+# ------------------------------------------------------------------------------------------------- config 1
+CONFIG1_WORKLOAD = ("config1: reference ModularUNet(1 -> 2, filters [40, 80, 120], depth 3, AvgPool / trilinear), synthetic "
+                    "1x96^3 volume, patch 64^3 overlap 16 (8 patches)")
+
+
+def run_config1_section(device, steps: int = 3, warmup: int = 2) -> dict:
+    """BASELINE config 1 (the reference's CPU-runnable case) on the GPU in both precisions: the fp32 CUDA-core path
+    (logits within 1e-5 of the reference) and the bf16 tensor-core path."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.models import set_precision
+    from segmentation_pipeline.prediction import PatchPredict
+    torch.manual_seed(0)
+    model = M.ModularUNet(1, 2, [40, 80, 120], 3)
+    perturb_bn(model, 1)
+    model.eval().to(device)
+    g = torch.Generator().manual_seed(3)
+    vol = torch.randn(1, 96, 96, 96, generator=g).to(device)
+    predictor = PatchPredict(patch_batch_size=8, patch_size=64, patch_overlap=16, padding_mode=None)
+    out = {"workload": CONFIG1_WORKLOAD, "flop_per_volume": 0.953e12}
+    labels = {}
+    with torch.no_grad():
+        for precision in ("fp32", "bf16"):
+            set_precision(precision)
+            for _ in range(warmup):
+                predictor.predict_volume(model, vol, want_probs=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                _, labels[precision] = predictor.predict_volume(model, vol, want_probs=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[precision] = {"ms_per_volume": ms, "value": 96 ** 3 / (ms * 1e-3) / 1e6, "unit": UNIT,
+                              "tflops": 0.953e12 / (ms * 1e-3) / 1e12}
+    set_precision("bf16")
+    out["label_agreement_bf16_vs_fp32_path"] = float((labels["fp32"] == labels["bf16"]).float().mean())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------- cohort (config 4)
 COHORT_WORKLOAD = ("config4: dmri_hippo-style NestedResUNet(3 -> 2, filters 40, dropout 0.2) eval, cohort of 64 synthetic "
                    "3x96x88x24 volumes, StandardPredict(sagittal_split=True), 64 / N volumes per GPU, Dice on device")
@@ -681,6 +721,9 @@ def run_gpu_arm(args) -> None:
     if slab is not None:
         line["slab"] = slab
     line["cohort_config4"] = cohort4
+    if world == 1:
+        line["config1"] = run_config1_section(device)
+        set_precision("bf16")
     line["patch_batch_1"] = batch1
     if world == 1:
         threads = os.cpu_count() or 1

@@ -402,70 +402,45 @@ overlap_add_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const
     const int kk = (t - jj * bdv) * VEC + bk0;
     const int j = jj + bj0;
     float* o = out + ((static_cast<long long>(c) * PW + i) * PH + j) * PD + kk;
-    // Pass 1: which patches of the batch cover this voxel (batch order = the reference's accumulation order).
-    // Pass 2: issue the loads of up to 8 of them together (8 = 2 per axis at overlap <= 50 %), then add in order --
-    // the loads are independent, so the latency of the gather is paid once per group instead of once per patch.
-    constexpr int kGroup = 8;
-    const long long pvox = 1LL * p0 * p1 * p2;
-    unsigned long long list = 0;      // up to 8 patch indices, one byte each (a dynamically indexed array would spill)
-    int n_src = 0;
     float acc[VEC];
-    bool loaded = false;
-    auto flush = [&]() {
-        float v[kGroup][VEC];
-#pragma unroll
-        for (int q = 0; q < kGroup; ++q) {
-            if (q < n_src) {
-                const int b = static_cast<int>((list >> (8 * q)) & 0xffull);
-                const float* sp = patches + (static_cast<long long>(b) * C + c) * pvox +
-                                  (static_cast<long long>(i - lb.loc[b][0]) * p1 + (j - lb.loc[b][1])) * p2 +
-                                  (kk - lb.loc[b][2]);
-                if constexpr (VEC == 4) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(sp));
-                    v[q][0] = t4.x; v[q][1] = t4.y; v[q][2] = t4.z; v[q][VEC - 1] = t4.w;
-                } else {
-                    v[q][0] = __ldg(sp);
-                }
-            }
-        }
-        if (!loaded) {
-            if constexpr (VEC == 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(o);
-                acc[0] = t4.x; acc[1] = t4.y; acc[2] = t4.z; acc[VEC - 1] = t4.w;
-            } else {
-                acc[0] = *o;
-            }
-            loaded = true;
-        }
-#pragma unroll
-        for (int q = 0; q < kGroup; ++q) {
-            if (q < n_src) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[e] += v[q][e];
-            }
-        }
-        n_src = 0;
-        list = 0;
-    };
+    bool touched = false, loaded = false;
+    const long long pvox = 1LL * p0 * p1 * p2;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         unsigned int m = cand[half];
         while (m) {
             const int b = (__ffs(m) - 1) + half * 32;
             m &= m - 1;
-            if (j < lb.loc[b][1] || j >= lb.loc[b][4] || kk < lb.loc[b][2] || kk >= lb.loc[b][5]) continue;
-            list |= static_cast<unsigned long long>(b) << (8 * n_src);
-            if (++n_src == kGroup) flush();
+            const int i0 = lb.loc[b][0], j0 = lb.loc[b][1], k0 = lb.loc[b][2];
+            if (j < j0 || j >= lb.loc[b][4] || kk < k0 || kk >= lb.loc[b][5]) continue;
+            if (!loaded) {
+                if constexpr (VEC == 4) {
+                    float4 v = *reinterpret_cast<const float4*>(o);
+                    acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[VEC - 1] = v.w;
+                } else {
+                    acc[0] = *o;
+                }
+                loaded = true;
+            }
+            const float* p = patches + (static_cast<long long>(b) * C + c) * pvox +
+                             (static_cast<long long>(i - i0) * p1 + (j - j0)) * p2 + (kk - k0);
+            if constexpr (VEC == 4) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(p));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[VEC - 1] += v.w;
+            } else {
+                acc[0] += __ldg(p);
+            }
+            touched = true;
         }
     }
-    if (n_src) flush();
-    if (!loaded) return;
+    if (!touched) return;
     if constexpr (VEC == 4) {
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[VEC - 1]);
     } else {
         *o = acc[0];
     }
 }
+
 // 'crop' mode: every patch assigns the centre crop of itself; patches are processed in order, later wins.
 __global__ void __launch_bounds__(kThreads)
 overlap_crop_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
@@ -486,19 +461,19 @@ overlap_crop_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, cons
 }
 
 // =========================================================================================== finalize (+ argmax)
+// Block = 64 k-vectors x 4 rows; grid = (k blocks, row blocks, planes): no per-thread 64-bit div / mod.  The channel
+// loop loads up to 4 channels' vectors before touching them, so every thread keeps 4 x 16 bytes in flight (round 1
+// loaded, divided and compared one channel at a time and sat at 22 % of the copy bandwidth with 2 channels).
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, const int* __restrict__ cw,
                 const int* __restrict__ ch, const int* __restrict__ cd, int b0, int b1, int b2, int W, int H, int D,
-                float* __restrict__ probs, long long* __restrict__ lab64, uint8_t* __restrict__ lab8,
-                long long total) {
-    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
-    if (t >= total) return;
-    const int dv = D / VEC;
-    int k = static_cast<int>(t % dv) * VEC;
-    long long r = t / dv;
-    int j = static_cast<int>(r % H);
-    int i = static_cast<int>(r / H);
+                float* __restrict__ probs, long long* __restrict__ lab64, uint8_t* __restrict__ lab8) {
+    const int kv = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int i = blockIdx.z;
+    const int k = kv * VEC;
+    if (k >= D || j >= H) return;
     const long long pvox = 1LL * PW * PH * PD;
     const long long vox = 1LL * W * H * D;
     const long long src = (static_cast<long long>(i + b0) * PH + (j + b1)) * PD + (k + b2);
@@ -516,31 +491,42 @@ finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, co
         best[q] = -INFINITY;
         arg[q] = 0;
     }
-    for (int c = 0; c < C; ++c) {
-        float v[VEC];
-        if constexpr (VEC == 4) {
-            float4 f = __ldg(reinterpret_cast<const float4*>(out + c * pvox + src));
-            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[VEC - 1] = f.w;
-        } else {
-            v[0] = __ldg(out + c * pvox + src);
-        }
-        if (cw != nullptr) {
+    for (int c0 = 0; c0 < C; c0 += 4) {
+        float v[4][VEC];
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) v[q] = v[q] / cnt[q];
-        }
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-            // torch.argmax: first maximal index; NaN counts as maximal
-            if (v[q] > best[q] || (v[q] != v[q] && best[q] == best[q])) {
-                best[q] = v[q];
-                arg[q] = c;
+        for (int u = 0; u < 4; ++u) {
+            if (c0 + u < C) {
+                if constexpr (VEC == 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(out + (c0 + u) * pvox + src));
+                    v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][VEC - 1] = f.w;
+                } else {
+                    v[u][0] = __ldg(out + (c0 + u) * pvox + src);
+                }
             }
         }
-        if (probs != nullptr) {
-            if constexpr (VEC == 4) {
-                *reinterpret_cast<float4*>(probs + c * vox + dst) = make_float4(v[0], v[1], v[2], v[VEC - 1]);
-            } else {
-                probs[c * vox + dst] = v[0];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (c0 + u < C) {
+                const int c = c0 + u;
+                if (cw != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) v[u][q] = v[u][q] / cnt[q];
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    // torch.argmax: first maximal index; NaN counts as maximal
+                    if (v[u][q] > best[q] || (v[u][q] != v[u][q] && best[q] == best[q])) {
+                        best[q] = v[u][q];
+                        arg[q] = c;
+                    }
+                }
+                if (probs != nullptr) {
+                    if constexpr (VEC == 4) {
+                        *reinterpret_cast<float4*>(probs + c * vox + dst) = make_float4(v[u][0], v[u][1], v[u][2], v[u][VEC - 1]);
+                    } else {
+                        probs[c * vox + dst] = v[u][0];
+                    }
+                }
             }
         }
     }
@@ -992,18 +978,15 @@ int b200seg_finalize_region(const float* out, int32_t c, int32_t pw, int32_t ph,
     bool vec = (D % 4 == 0) && (pd % 4 == 0) && (border[2] % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                (probs == nullptr || (reinterpret_cast<uintptr_t>(probs) & 15) == 0) &&
                (labels_u8 == nullptr || (reinterpret_cast<uintptr_t>(labels_u8) & 3) == 0);
+    B200SEG_CHECK_ARG(W <= 65535 && (H + 3) / 4 <= 65535, "finalize: extent (%d, %d) exceeds the launch grid", W, H);
     if (vec) {
-        long long total = 1LL * W * H * (D / 4);
-        finalize_kernel<4><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1],
-                                                                 border[2], W, H, D, probs,
-                                                                 reinterpret_cast<long long*>(labels_i64), labels_u8,
-                                                                 total);
+        dim3 grid(static_cast<unsigned>((D / 4 + 63) / 64), static_cast<unsigned>((H + 3) / 4), static_cast<unsigned>(W));
+        finalize_kernel<4><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1], border[2], W, H, D,
+                                                    probs, reinterpret_cast<long long*>(labels_i64), labels_u8);
     } else {
-        long long total = 1LL * W * H * D;
-        finalize_kernel<1><<<blocks_for(total), kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1],
-                                                                 border[2], W, H, D, probs,
-                                                                 reinterpret_cast<long long*>(labels_i64), labels_u8,
-                                                                 total);
+        dim3 grid(static_cast<unsigned>((D + 63) / 64), static_cast<unsigned>((H + 3) / 4), static_cast<unsigned>(W));
+        finalize_kernel<1><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1], border[2], W, H, D,
+                                                    probs, reinterpret_cast<long long*>(labels_i64), labels_u8);
     }
     return check_launch("finalize");
 }

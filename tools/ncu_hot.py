@@ -9,7 +9,12 @@ rows = list(csv.reader(open(path)))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hdr_i + 1:]:
+    if r and r[0] == "Address":      # next kernel of a multi-launch dump: keep the first one only
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 total = sum(int(r[col["# Samples"]] or 0) for r in data)
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 print("total samples", total)
