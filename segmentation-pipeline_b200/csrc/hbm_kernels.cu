@@ -478,11 +478,21 @@ finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, co
     const long long vox = 1LL * W * H * D;
     const long long src = (static_cast<long long>(i + b0) * PH + (j + b1)) * PD + (k + b2);
     const long long dst = (static_cast<long long>(i) * H + j) * D + k;
-    float cnt[VEC];
+    // ncu: the round-1 kernel was INSTRUCTION bound (issue slots 66 % busy at 21 % DRAM) by the IEEE divisions.  The
+    // coverage count is a product of per-axis counts, i.e. a power of two whenever the overlap is <= 50 % (counts 1 or 2
+    // per axis): then x / cnt == x * (1 / cnt) exactly (scaling by 2^-k is exact, and both sides round a subnormal
+    // result identically), one multiply instead of a division sequence.  Other counts keep the division.
+    float cnt[VEC], rcp[VEC];
+    bool pow2 = true;
     if (cw != nullptr) {
         int cij = __ldg(cw + i + b0) * __ldg(ch + j + b1);
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) cnt[q] = static_cast<float>(cij * __ldg(cd + k + b2 + q));
+        for (int q = 0; q < VEC; ++q) {
+            const int n = cij * __ldg(cd + k + b2 + q);
+            cnt[q] = static_cast<float>(n);
+            rcp[q] = __frcp_rn(cnt[q]);
+            pow2 = pow2 && ((n & (n - 1)) == 0);
+        }
     }
     float best[VEC];
     int arg[VEC];
@@ -509,8 +519,13 @@ finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, co
             if (c0 + u < C) {
                 const int c = c0 + u;
                 if (cw != nullptr) {
+                    if (pow2) {
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) v[u][q] = v[u][q] / cnt[q];
+                        for (int q = 0; q < VEC; ++q) v[u][q] = v[u][q] * rcp[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) v[u][q] = v[u][q] / cnt[q];
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Achieved HBM bandwidth of the streaming kernels of the path (extraction, overlap-add, finalize+argmax, argmax,
-confusion) at config-2 / config-3 scale.  CUDA events, 3 warm-ups, best of 10; inputs are far larger than L2 or an
-L2 flush (256 MB memset) runs between iterations.  Prints one line per kernel: algorithmic bytes, time, GB/s and
+confusion) at config-2 / config-3 scale.  Timed on the device inside a CUDA graph (10 launches, an L2 flush before
+each -- a 256 MB READ, so that no dirty lines are left behind -- flush time subtracted; see ``timed``).  Prints one line per kernel: algorithmic bytes, time, GB/s and
 the fraction of the measured copy bandwidth (MEASURED_PEAKS.json)."""
 import json
 import os
@@ -20,6 +20,10 @@ ONCE = "--once" in sys.argv      # under ncu: one warm-up + one measured launch 
 
 
 def timed(fn, flush, reps=10):
+    """ms per launch.  The kernels here last 20-200 us, less than a Python + ctypes call costs when the GPU is idle, so
+    CUDA events around a single eager call would time the host.  Instead ``reps`` launches, each preceded by an L2
+    flush, are captured into ONE CUDA graph; the same graph with the flushes only is timed too and
+    subtracted."""
     if ONCE:
         fn()
         torch.cuda.synchronize()
@@ -29,17 +33,35 @@ def timed(fn, flush, reps=10):
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_pop()
         return float("nan")
-    best = 1e9
-    for i in range(3 + reps):
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        fn()
-        e.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            best = min(best, s.elapsed_time(e))
-    return best
+
+    sink = torch.zeros(1, dtype=torch.int64, device=flush.device)
+
+    def capture(with_kernel):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                # flush by READING 256 MB: the lines left in L2 are clean.  (A memset leaves ~126 MB of dirty lines whose
+                # write-back is then charged to the kernel under test -- ~40 us, half the time of the small kernels.)
+                sink.add_(flush.view(torch.int64).sum())
+                if with_kernel:
+                    fn()
+        return g
+
+    fn()
+    torch.cuda.synchronize()
+    both, only_flush = capture(True), capture(False)
+    best = []
+    for g in (both, only_flush):
+        t = 1e9
+        for _ in range(5):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            g.replay()
+            e.record()
+            torch.cuda.synchronize()
+            t = min(t, s.elapsed_time(e))
+        best.append(t)
+    return (best[0] - best[1]) / reps
 
 
 def main():
