@@ -24,7 +24,7 @@ def get(r, name, default=float("nan")):
 def scale(name):
     u = units[col[name]] if name in col else ""
     return {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1e-3, "usecond": 1e-6, "second": 1.0,
-            "nsecond": 1e-9}.get(u, 1.0)
+            "nsecond": 1e-9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(u, 1.0)
 
 
 out = []
