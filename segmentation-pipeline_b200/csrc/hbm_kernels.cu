@@ -2,6 +2,8 @@
 // softmax, grid patch extraction, overlap-add aggregation, finalize (+argmax) and the confusion histogram.
 // All of them are pure streaming kernels: one 16/32-byte vector per thread access, x (the contiguous axis)
 // mapped to threadIdx.x, grids sized from the element count.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200seg {
@@ -438,6 +440,78 @@ overlap_add_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[VEC - 1]);
     } else {
         *o = acc[0];
+    }
+}
+
+// Row-owner variant of the 128-bit path (round 2).  ncu on the kernel above: ~110 instructions per 16-byte patch load
+// (every thread re-tests every candidate patch of its block against its own j and k, reading the location table from
+// the parameter bank) -- issue slots 57 % busy at 32 % DRAM.  Here one WARP owns one accumulator row (c, i, j): its
+// lanes test the batch's patches against (i, j) once (ballot + ordered compaction into shared memory, with the
+// patch-row base pointer and k range precomputed), then every lane walks the short list for its two 16-byte vectors:
+// one broadcast LDS.128, two compares, one load, four adds per candidate.  Batch order is preserved, so the sums are
+// bit-identical to the sequential CPU +=.
+struct RowCand {
+    int k0, k1;            // covered k range of the row, in floats
+    long long off;         // element offset of the patch row such that patches[off + k] is the value for out k
+};
+
+__global__ void __launch_bounds__(kThreads)
+overlap_add_rows_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
+                        LocBatch lb, int p0, int p1, int p2, int bi0, int bj0, int bk0, int bh, int bd) {
+    __shared__ RowCand cand[kThreads / 32][64];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int jrow = blockIdx.y * (kThreads / 32) + warp;
+    if (jrow >= bh) return;
+    const int j = jrow + bj0;
+    const int c = blockIdx.z % C;
+    const int i = blockIdx.z / C + bi0;
+    int n = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int b = lane + 32 * half;
+        const bool hit = b < lb.count && i >= lb.loc[b][0] && i < lb.loc[b][3] && j >= lb.loc[b][1] && j < lb.loc[b][4];
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            RowCand rc;
+            rc.k0 = lb.loc[b][2];
+            rc.k1 = lb.loc[b][5];
+            rc.off = ((static_cast<long long>(b) * C + c) * p0 + (i - lb.loc[b][0])) * p1 * p2 +
+                     static_cast<long long>(j - lb.loc[b][1]) * p2 - rc.k0;
+            cand[warp][n + __popc(m & ((1u << lane) - 1u))] = rc;
+        }
+        n += __popc(m);
+    }
+    __syncwarp();
+    if (n == 0) return;
+    float* orow = out + ((static_cast<long long>(c) * PW + i) * PH + j) * PD;
+    const int kend = bk0 + bd;
+    for (int kb = bk0 + blockIdx.x * 256; kb < kend; kb += gridDim.x * 256) {      // 64 vectors per warp pass
+        const int ka = kb + lane * 4, kc = ka + 128;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+        bool ta = false, tb = false;
+        // the accumulator values are needed only if some patch covers the vector: load them up front (independent
+        // of the gathers), use them when touched
+        const bool ina = ka < kend, inb = kc < kend;
+        float4 oa = a, ob = a;
+        if (ina) oa = *reinterpret_cast<const float4*>(orow + ka);
+        if (inb) ob = *reinterpret_cast<const float4*>(orow + kc);
+        a = oa;
+        b4 = ob;
+        for (int q = 0; q < n; ++q) {
+            const RowCand rc = cand[warp][q];
+            if (ina && ka >= rc.k0 && ka < rc.k1) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(patches + rc.off + ka));
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                ta = true;
+            }
+            if (inb && kc >= rc.k0 && kc < rc.k1) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(patches + rc.off + kc));
+                b4.x += v.x; b4.y += v.y; b4.z += v.z; b4.w += v.w;
+                tb = true;
+            }
+        }
+        if (ta) *reinterpret_cast<float4*>(orow + ka) = a;
+        if (tb) *reinterpret_cast<float4*>(orow + kc) = b4;
     }
 }
 
@@ -919,7 +993,16 @@ int b200seg_overlap_add(float* out, int32_t c, int32_t pw, int32_t ph, int32_t p
         }
         const int bw = bb[3] - bb[0], bh = bb[4] - bb[1], bd = bb[5] - bb[2];
         const float* pp = patches + 1LL * b0 * c * p0 * p1 * p2;
-        if (vec) {
+        static const bool legacy = [] {
+            const char* v = getenv("B200SEG_OVERLAP_ADD_V1");      // test / A-B hook: the round-1 kernel
+            return v && v[0] == '1';
+        }();
+        if (vec && !legacy && 1LL * bw * c <= 65535) {
+            dim3 grid(static_cast<unsigned>((bd + 255) / 256), static_cast<unsigned>((bh + kThreads / 32 - 1) / (kThreads / 32)),
+                      static_cast<unsigned>(bw * c));
+            overlap_add_rows_kernel<<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0], bb[1], bb[2],
+                                                              bh, bd);
+        } else if (vec) {
             dim3 grid(blocks_for(1LL * bh * (bd / 4)), static_cast<unsigned>(bw), static_cast<unsigned>(c));
             overlap_add_kernel<4><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, pp, lb, p0, p1, p2, bb[0], bb[1], bb[2],
                                                             bw, bh, bd);
