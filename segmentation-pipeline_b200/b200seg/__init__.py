@@ -233,11 +233,11 @@ def conv3d_tc_wbytes(mode: int, cin_chunks: int, cout: int) -> int:
 
 def instnorm(x: View, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float, slope: float,
              residual: View = NULL_VIEW) -> None:
-    """In-place InstanceNorm3d + activation (+ residual) on a blocked view (three streaming launches)."""
+    """In-place InstanceNorm3d + activation (+ residual) on a blocked view (two streaming launches)."""
     lib = load_library()
     need = int(lib.b200seg_instnorm_scratch_bytes(x))
     scratch = torch.empty(max(need // 4, 1), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
-    _LAUNCHES[0] += 3
+    _LAUNCHES[0] += 2
     _check(lib.b200seg_instnorm(x, _ptr(gamma), _ptr(beta), float(eps), float(slope), residual, _ptr(scratch), need,
                                 _stream()), "instnorm")
 

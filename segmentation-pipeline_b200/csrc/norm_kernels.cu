@@ -1,8 +1,10 @@
 // InstanceNorm3d on blocked activations, in place, fused with the activation and the residual add of Block3d.
-// Statistics are the two-pass form (mean first, then the sum of squared deviations) -- the numerically safe one
-// PyTorch's instance_norm is equivalent to -- reduced with warp shuffles inside a block and, across blocks, through
-// a small scratch array of partial sums that every consumer block re-reduces in a FIXED order (deterministic, no
-// atomics).  Three streaming passes over the tensor: sum, squared deviations, apply.
+// TWO streaming passes over the tensor (round 1: three).  Pass 0: every block reduces its strip of voxels to
+// (mean_b, M2_b) per channel in ONE read, with the shifted-data form -- deviations from the strip's first voxel K,
+// sum d and sum d^2, so that M2_b = sum d^2 - (sum d)^2 / n_b does not cancel -- reduced with warp shuffles.  Pass 1:
+// every block merges the <= 64 block statistics of its (n, channel chunk) in a FIXED order with Chan's pairwise update
+// (deterministic, no atomics; as safe as the mean-then-deviations form), then applies scale / shift, activation and
+// residual.
 #include "common.cuh"
 
 namespace b200seg {
@@ -33,18 +35,30 @@ __device__ __forceinline__ void block_reduce8(float (&v)[8], float* smem /* [8 w
 }
 
 // partial layout: [n][c8][nb][8]
-__device__ __forceinline__ void reduce_partials(const float* part, int nb, float (&out)[8]) {
+// Chan et al. merge of the per-block (mean, M2) in block order; block b holds n_b = min(per, vox - b * per) voxels
+__device__ __forceinline__ void merge_partials(const float* part_mean, const float* part_m2, int nb, long long per,
+                                               long long vox, float (&mean)[8], float (&m2)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = 0.f;
+    for (int j = 0; j < 8; ++j) mean[j] = m2[j] = 0.f;
+    float n = 0.f;
     for (int b = 0; b < nb; ++b) {
+        const long long v0 = b * per;
+        const float nbk = static_cast<float>(min(per, vox - v0));
+        if (nbk <= 0.f) break;
+        const float tot = n + nbk;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) out[j] += __ldg(part + b * 8 + j);
+        for (int j = 0; j < 8; ++j) {
+            const float d = __ldg(part_mean + b * 8 + j) - mean[j];
+            mean[j] += d * (nbk / tot);
+            m2[j] += __ldg(part_m2 + b * 8 + j) + d * d * (n * nbk / tot);
+        }
+        n = tot;
     }
 }
 
 template <typename T, int PASS>
 __global__ void __launch_bounds__(kNormThreads)
-instnorm_kernel(DView x, float* __restrict__ part_sum, float* __restrict__ part_m2, int nb, float inv_count,
+instnorm_kernel(DView x, float* __restrict__ part_mean, float* __restrict__ part_m2, int nb, float inv_count,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float slope,
                 DView residual) {
     __shared__ float red[(kNormThreads / 32) * 8];
@@ -54,32 +68,32 @@ instnorm_kernel(DView x, float* __restrict__ part_sum, float* __restrict__ part_
     const long long v0 = b * per, v1 = min(v0 + per, vox);
     const long long base = n * x.sample_stride + (x.c8_off + cc) * x.chunk_stride;
     const long long pidx = (static_cast<long long>(n) * gridDim.y + cc) * nb;
-    float mean[8];
-    if (PASS >= 1) {
-        reduce_partials(part_sum + pidx * 8, nb, mean);
+    if (PASS == 0) {
+        if (v0 >= v1) return;
+        const Vec8 k = load_vec8<T>(x.data, base + v0);      // shift: the strip's first voxel
+        float s1[8], s2[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mean[j] *= inv_count;
-    }
-    if (PASS == 0 || PASS == 1) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
         for (long long v = v0 + threadIdx.x; v < v1; v += kNormThreads) {
             Vec8 a = load_vec8<T>(x.data, base + v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (PASS == 0) acc[j] += a.v[j];
-                else {
-                    const float d = a.v[j] - mean[j];
-                    acc[j] = fmaf(d, d, acc[j]);
-                }
+                const float d = a.v[j] - k.v[j];
+                s1[j] += d;
+                s2[j] = fmaf(d, d, s2[j]);
             }
         }
-        block_reduce8(acc, red);
-        if (threadIdx.x < 8) (PASS == 0 ? part_sum : part_m2)[(pidx + b) * 8 + threadIdx.x] = acc[threadIdx.x];
+        block_reduce8(s1, red);
+        block_reduce8(s2, red);
+        if (threadIdx.x < 8) {
+            const int j = threadIdx.x;
+            const float nbk = static_cast<float>(v1 - v0);
+            part_mean[(pidx + b) * 8 + j] = k.v[j] + s1[j] / nbk;
+            part_m2[(pidx + b) * 8 + j] = fmaxf(s2[j] - s1[j] * s1[j] / nbk, 0.f);
+        }
     } else {
-        float m2[8], sc[8], sh[8];
-        reduce_partials(part_m2 + pidx * 8, nb, m2);
+        float mean[8], m2[8], sc[8], sh[8];
+        merge_partials(part_mean + pidx * 8, part_m2 + pidx * 8, nb, per, vox, mean, m2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cc * 8 + j;
@@ -153,8 +167,6 @@ extern "C" int b200seg_instnorm(b200seg_view x, const float* gamma, const float*
         instnorm_kernel<T, 0><<<grid, kNormThreads, 0, s>>>(dx, part_sum, part_m2, static_cast<int>(nb), inv_count, \
                                                             gamma, beta, eps, slope, dr);                           \
         instnorm_kernel<T, 1><<<grid, kNormThreads, 0, s>>>(dx, part_sum, part_m2, static_cast<int>(nb), inv_count, \
-                                                            gamma, beta, eps, slope, dr);                           \
-        instnorm_kernel<T, 2><<<grid, kNormThreads, 0, s>>>(dx, part_sum, part_m2, static_cast<int>(nb), inv_count, \
                                                             gamma, beta, eps, slope, dr);                           \
     } while (0)
     if (x.dtype == B200SEG_F32) LAUNCH_NORM(float);

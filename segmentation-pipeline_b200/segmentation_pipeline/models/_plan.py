@@ -222,10 +222,17 @@ def _lower_block(plan: Plan, level: int, name: str, src: Ref, segments, convs, n
         else:
             scale, shift, slope = _epilogue_arrays(cout, b, norms[i], acts[i])
         if inst is not None:
-            if i == 0 and res_conv is not None:
-                plan.ops.append(ConvOp(K3, cur, cur_segments, rw, r_scale, r_shift, r_slope, dst0=res_ref,
-                                       name=f"{name}.res_conv"))
-            plan.ops.append(ConvOp(K3, cur, cur_segments, w, scale, shift, slope, dst0=dst, name=f"{name}.conv{i}"))
+            if i == 0 and res_conv is not None and not last and cout % 8 == 0:
+                # conv0 (raw, + bias) and res_conv read the same tensor: ONE contraction with N = 2 * Cout and two
+                # destinations, exactly as on the BatchNorm branch; the norm kernel then works in place on dst
+                plan.ops.append(ConvOp(K3, cur, cur_segments, torch.cat([w, rw], 0), np.concatenate([scale, r_scale]),
+                                       np.concatenate([shift, r_shift]), np.concatenate([slope, r_slope]), dst0=dst,
+                                       dst1=res_ref, split=cout, name=f"{name}.conv0+res"))
+            else:
+                if i == 0 and res_conv is not None:
+                    plan.ops.append(ConvOp(K3, cur, cur_segments, rw, r_scale, r_shift, r_slope, dst0=res_ref,
+                                           name=f"{name}.res_conv"))
+                plan.ops.append(ConvOp(K3, cur, cur_segments, w, scale, shift, slope, dst0=dst, name=f"{name}.conv{i}"))
             gamma, beta, eps = inst
             plan.ops.append(InstNormOp(dst, gamma, beta, eps, float(_act_slope(acts[i], 1)[0]),
                                        residual=res_ref if (last and res_conv is not None) else None))

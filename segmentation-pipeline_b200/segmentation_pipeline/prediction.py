@@ -106,17 +106,31 @@ class StandardPredict(Predictor):
 
     def predict(self, model, device, subjects, label_attributes=None):
         device = _require_cuda(device)
-        batch = collate_subjects(subjects, image_names=self.image_names, device=device)
         label_attributes = {} if label_attributes is None else label_attributes
         with _lib().on_device(device):
+            # H2D: every subject's volume straight into its slot of the device batch (asynchronous when the host tensor
+            # is pinned) instead of torch.stack on the host + one pageable copy (utils/utils.py:75-85)
+            batch = {}
+            for name in self.image_names:
+                first = subjects[0][name]["data"]
+                stacked = torch.empty((len(subjects), *first.shape), dtype=first.dtype, device=device)
+                for i, subject in enumerate(subjects):
+                    stacked[i].copy_(subject[name]["data"], non_blocking=True)
+                batch[name] = stacked
             if self.sagittal_split:
                 y_pred = reverse_split_and_flip(model(split_and_flip(batch['X']).contiguous()))
             else:
                 y_pred = model(batch["X"])
-        batch['y_pred'] = y_pred
+            batch['y_pred'] = y_pred
+            # D2H: ONE asynchronous copy of the whole batch into pinned memory and one synchronisation, instead of a
+            # blocking .cpu() per subject (prediction.py:97); the per-subject images are views of that buffer
+            y_det = y_pred.detach()
+            y_host = torch.empty(y_det.shape, dtype=y_det.dtype, pin_memory=True)
+            y_host.copy_(y_det, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
         out_subjects = []
         for i, subject in enumerate(subjects):
-            image = _tio.make_label_map(y_pred[i].detach().cpu(), **copy.deepcopy(label_attributes))
+            image = _tio.make_label_map(y_host[i], **copy.deepcopy(label_attributes))
             subject.add_image(image, "y_pred")
             out_subjects.append(_tio.enforce_consistent_affine(subject, "X"))
         return out_subjects, batch
@@ -216,16 +230,27 @@ class PatchPredict(Predictor):
         label_attributes = {} if label_attributes is None else label_attributes
         out_subjects = []
         volumes_on_device = []
-        for subject in subjects:
-            volume = subject["X"]["data"]
-            volume_dev = volume.to(device, non_blocking=True)   # one H2D per subject (async when pinned)
-            volumes_on_device.append(volume_dev)
-            with torch.no_grad():
-                probs, labels = self.predict_volume(model, volume_dev)
-            # D2H through pinned memory (the caching host allocator recycles the block once the caller drops it)
-            probs_host = torch.empty(probs.shape, dtype=probs.dtype, pin_memory=True)
-            probs_host.copy_(probs, non_blocking=True)
-            torch.cuda.current_stream(device).synchronize()
+        pending = []
+        with _lib().on_device(device):
+            main = torch.cuda.current_stream(device)
+            d2h = torch.cuda.Stream(device=device) if len(subjects) > 1 else main
+            for subject in subjects:
+                volume = subject["X"]["data"]
+                volume_dev = volume.to(device, non_blocking=True)   # one H2D per subject (async when pinned)
+                volumes_on_device.append(volume_dev)
+                with torch.no_grad():
+                    probs, labels = self.predict_volume(model, volume_dev)
+                # D2H through pinned memory on a second stream: with several subjects the copy of subject i overlaps
+                # the network of subject i + 1; ONE synchronisation at the end (the reference blocks per patch batch)
+                probs_host = torch.empty(probs.shape, dtype=probs.dtype, pin_memory=True)
+                if d2h is not main:
+                    d2h.wait_stream(main)
+                    probs.record_stream(d2h)
+                with torch.cuda.stream(d2h):
+                    probs_host.copy_(probs, non_blocking=True)
+                pending.append((subject, probs_host, labels))
+            d2h.synchronize()
+        for subject, probs_host, labels in pending:
             image = _tio.make_label_map(probs_host, **copy.deepcopy(label_attributes))
             if labels is not None:
                 # device label map + the identity of the probabilities it was computed from: add_evaluation_labels

@@ -119,6 +119,36 @@ def test_wide_heads_go_through_the_blocked_out_buffer(head):
         assert rel_err(out, ref) <= tol, (head, precision)
 
 
+def test_instance_norm_residual_block_keeps_conv0_res_fusion():
+    """InstanceNorm3d blocks with a residual branch: conv0 and res_conv still run as ONE contraction (two destinations),
+    followed by the in-place norm kernel; vs the oracle (fp32 <= 1e-5, bf16 <= 2e-2)."""
+    from torch import nn
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.models import _engine, set_precision
+    torch.manual_seed(15)
+    model = M.ModularUNet(2, 2, [8, 16], 2, block_params={"residual": True, "normalization_class": nn.InstanceNorm3d,
+                                                          "activation_class": nn.LeakyReLU,
+                                                          "activation_params": {"negative_slope": 0.1}})
+    model.eval()
+    names = [getattr(op, "name", "") for op in _engine.lower(model).ops]
+    assert "down0.conv0+res" in names and "down0.res_conv" not in names
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    cfg = {"depth": 2, "filters": [8, 16], "block": {"residual": True, "norm": "instance", "act": "leaky_relu", "slope": 0.1},
+           "down": "avgpool", "up": "trilinear"}
+    x = torch.randn(2, 2, 16, 16, 8, generator=torch.Generator().manual_seed(16))
+    with torch.no_grad():
+        ref = unet.modular_unet_forward(sd, x, cfg)
+    model.cuda()
+    for precision, tol in (("fp32", 1e-5), ("bf16", 2e-2)):
+        set_precision(precision)
+        try:
+            with torch.no_grad():
+                out = model(x.cuda()).cpu()
+        finally:
+            set_precision("auto")
+        assert rel_err(out, ref) <= tol, precision
+
+
 def test_other_device_than_current(monkeypatch):
     """predict(model, device, ...) with device != the current CUDA device.  Needs two GPUs; on one GPU
     the guard itself is checked: a tensor from another device index is refused loudly."""
