@@ -1395,6 +1395,23 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
                   misc + static_cast<size_t>(n_images) * p.bbuf_bytes + 8 * stage <= budget) ? 1 : 0;
     p.nbuf = p.resident ? n_images
                         : ((misc + 2 * static_cast<size_t>(p.bbuf_bytes) + 4 * stage <= budget) ? 2 : 1);
+    {
+        // streamed weight images: a ring of up to 4 slots when at least 8 A stages still fit -- two issuers share
+        // every streamed image, and a 2-deep ring keeps them in lock step.  B200SEG_TC_NBUF overrides (A/B hook).
+        static const int forced = [] {
+            const char* v = getenv("B200SEG_TC_NBUF");
+            return v ? atoi(v) : 0;
+        }();
+        const int want = forced > 0 ? forced : 4;
+        if (!p.resident && p.nbuf == 2) {
+            for (int nb = want; nb > 2; --nb) {
+                if (nb <= kMaxB && nb <= n_images && misc + static_cast<size_t>(nb) * p.bbuf_bytes + 8 * stage <= budget) {
+                    p.nbuf = nb;
+                    break;
+                }
+            }
+        }
+    }
     B200SEG_CHECK_ARG(misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + 3 * stage <= budget,
                       "conv3d_tc: weight image of %d bytes does not fit shared memory", p.bbuf_bytes);
     long na = static_cast<long>((budget - misc - static_cast<size_t>(p.nbuf) * p.bbuf_bytes) / stage);
@@ -1407,14 +1424,17 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
     // 3 = dual wherever possible, unset = the default rule.
     static const int issuers = [] {
         const char* v = getenv("B200SEG_TC_ISSUERS");
-        return (v && v[0] >= '1' && v[0] <= '3') ? v[0] - '0' : 0;
+        return (v && v[0] >= '1' && v[0] <= '4') ? v[0] - '0' : 0;
     }();
     const long long tiles_all = 1LL * p.tiles_x * p.tiles_y * p.tiles_z * in.n;
     const bool dual_ok = variant == 2 && p.na >= 8 && tiles_all >= 2LL * sms;
+    // Round 1 excluded the 40-channel transposed convolution (streamed weights) from dual issue; with the identity
+    // epilogue and a 4-deep weight ring it now gains 13-17 % from the second issuer (same-box A/B), so the
+    // default is dual wherever the tile count allows.  4 = the round-1 rule (A/B hook).
     const bool dual_rule = issuers == 1 ? false
                          : issuers == 2 ? p.resident != 0
-                         : issuers == 3 ? true
-                                        : (mode != B200SEG_TC_UP || p.resident || g.Cpad >= 80);
+                         : issuers == 4 ? (mode != B200SEG_TC_UP || p.resident || g.Cpad >= 80)
+                                        : true;
     p.dual = (dual_ok && dual_rule) ? 1 : 0;
     const size_t smem = misc + static_cast<size_t>(p.nbuf) * p.bbuf_bytes + static_cast<size_t>(p.na) * stage;
     // ---- launch (persistent)
