@@ -70,6 +70,9 @@ struct TcParams {
     int bbuf_bytes;   // bytes of one B image slot in shared memory
     int maxp;         // planes per MMA
     int n_pass, n_bimg;  // passes and B images per pass
+    int gp;              // chunk pairs ("images") handled per visit: 1, or 2 = "super groups" (one A stage holds two chunk
+                         // pairs, one B slot two consecutive weight images; halves the per-visit issue overhead)
+    int SG, n_simg;      // super groups per parity block (= ceil(G / gp)) and super images per pass (= n_bimg / G * SG)
     int na, nbuf;     // A ring depth, B ring depth
     int resident;     // 1: every weight image has its own slot and is loaded once per CTA (nbuf = n_pass * n_bimg)
     int dual;         // 1: two MMA issuers, one per accumulator set, each with half of the A ring
@@ -235,11 +238,11 @@ __device__ __forceinline__ void issue_plane(uint32_t a16, uint32_t b16, uint32_t
 
 // All planes of one weight image: wait for the plane's halo, issue its steps, release the stage.  The next plane's
 // MMA blocks are fetched from shared memory before blocking on the current plane's data.
-template <int KIND>
+template <int KIND, int KIND2 = -1>
 __device__ __forceinline__ void run_image(bool first_image, int n_planes, int zstep, const PlaneTab* pt,
                                           uint64_t* full_a, uint64_t* empty_a, uint32_t& a_s, uint32_t& a_ph, int na,
                                           uint32_t sA16, uint32_t pbase, uint32_t b16, uint32_t b_lbo,
-                                          uint32_t bstep16, uint32_t tacc, uint32_t stage16) {
+                                          uint32_t bstep16, uint32_t tacc, uint32_t stage16, uint32_t bimg16) {
     PlaneRegs cur = load_plane_regs(pt);
     for (int j = 0; j < n_planes; ++j) {
         const PlaneTab* ptn = pt + zstep;
@@ -265,6 +268,9 @@ __device__ __forceinline__ void run_image(bool first_image, int n_planes, int zs
         } else {
             issue_plane<KIND, 0>(a16, b16, b_lbo, bstep16, tacc, cur);
         }
+        // super group: the stage holds a second chunk pair, the slot a second weight image -- same plane, same blocks
+        if constexpr (KIND2 >= 0)
+            issue_plane<KIND2, 0>(a16 + (kAStageBytes >> 4), b16 + bimg16, b_lbo, bstep16, tacc, cur);
         umma_commit(&empty_a[s]);
         cur = nxt;
         pt = ptn;
@@ -562,49 +568,85 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         tile = bid + tile_it * grid_n;
         return tile_it < my_tiles;
     };
-    const int n_img_round = p.n_pass * p.n_bimg;
-    // one A-plane load request (coordinates of the halo box of input plane zc, chunk pair cc)
-    auto image_loads = [&](int tile, int bi, int& x0, int& y0, int& zc, int& zstep, int& cc, uint32_t& bytes,
-                           const CUtensorMap*& map) {
+    const int n_img_round = p.n_pass * p.n_simg;
+    // A-plane load request of super image si of a tile: everything that is constant over the planes of the image is
+    // computed here, once, so that a stage costs its producer thread a handful of instructions (the thread that feeds
+    // ring 1 also streams the weights and must stay cheap)
+    struct ALoad {
+        int x0, y0, zc, zstep;
+        int cnt, cc0;                 // chunk pairs of the stage, first chunk index (incl. sample offset)
+        uint32_t bytes;               // expected bytes of the stage
+        const CUtensorMap* map_full;  // box of a full chunk pair
+        const CUtensorMap* map_last;  // box of the last pair (a 1-chunk box when the pair is lone)
+    };
+    auto image_loads = [&](int tile, int si, ALoad& a) {
         int t = tile;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int tz = t % p.tiles_z;
         const int n = t / p.tiles_z;
-        x0 = tx * p.tile_sx;
-        y0 = ty * p.tile_sy;
+        a.x0 = tx * p.tile_sx;
+        a.y0 = ty * p.tile_sy;
         const int z0 = tz * p.TZ;
-        const int g = bi % p.G;
-        const bool lone = p.lone_last && g == p.G - 1;
-        bytes = lone ? kChunkBytes : kAStageBytes;
-        cc = n * p.c8_total + p.chunk_base + 2 * g;
-        zstep = 1;
-        map = &maps.m[lone ? 1 : 0];
+        const int outer = si / p.SG;
+        const int sg = si - outer * p.SG;
+        a.zstep = 1;
         if (p.mode == B200SEG_TC_K3T) {
-            zc = z0 - 1;
-            bytes = static_cast<uint32_t>(p.cin_chunks) * kChunkBytes;   // one box with every chunk of the plane
-            map = &maps.m[2];
-        } else if (p.mode == B200SEG_TC_K3) {
-            zc = z0 - 1;
+            a.zc = z0 - 1;
+            a.cnt = 1;
+            a.cc0 = n * p.c8_total + p.chunk_base;
+            a.bytes = static_cast<uint32_t>(p.cin_chunks) * kChunkBytes;   // one box with every chunk of the plane
+            a.map_full = a.map_last = &maps.m[2];
+            return;
+        }
+        const int g0 = p.gp * sg;
+        a.cnt = min(p.gp, p.G - g0);
+        const bool last_lone = p.lone_last && g0 + a.cnt == p.G;
+        a.cc0 = n * p.c8_total + p.chunk_base + 2 * g0;
+        a.bytes = static_cast<uint32_t>(a.cnt * kAStageBytes - (last_lone ? kChunkBytes : 0));
+        if (p.mode == B200SEG_TC_K3) {
+            a.zc = z0 - 1;
+            a.map_full = &maps.m[0];
+            a.map_last = &maps.m[last_lone ? 1 : 0];
         } else if (p.mode == B200SEG_TC_UP) {
-            zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
+            a.zc = z0 / 2 - 1;        // tile origin is in low-res input coordinates; z0 counts OUTPUT planes
+            a.map_full = &maps.m[0];
+            a.map_last = &maps.m[last_lone ? 1 : 0];
         } else {
-            zc = 2 * z0 - 1 + bi / (4 * p.G);
-            zstep = 2;
-            map = &maps.m[(lone ? 4 : 0) + (bi / p.G) % 4];
+            a.zc = 2 * z0 - 1 + outer / 4;
+            a.zstep = 2;
+            a.map_full = &maps.m[outer % 4];
+            a.map_last = &maps.m[(last_lone ? 4 : 0) + outer % 4];
         }
     };
-    auto issue_a = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, uint32_t bytes, int x0, int y0, int zc, int cc) {
-        mbar_arrive_expect_tx(bar, bytes);
-        if (p.mode == B200SEG_TC_DOWN) tma_load_5d(dst, map, bar, 0, x0 - 1, y0 - 1, zc, cc);
-        else tma_load_4d(dst, map, bar, (x0 - 1) * 8, y0 - 1, zc, cc);
+    // one stage = the chunk pairs of input plane zc: one TMA box per pair, one barrier
+    auto issue_a = [&](uint8_t* dst, uint64_t* bar, const ALoad& a, int zc) {
+        mbar_arrive_expect_tx(bar, a.bytes);
+        if (p.mode == B200SEG_TC_DOWN) {
+            if (a.cnt == 2) tma_load_5d(dst, a.map_full, bar, 0, a.x0 - 1, a.y0 - 1, zc, a.cc0);
+            tma_load_5d(dst + (a.cnt - 1) * kAStageBytes, a.map_last, bar, 0, a.x0 - 1, a.y0 - 1, zc,
+                        a.cc0 + 2 * (a.cnt - 1));
+        } else {
+            if (a.cnt == 2) tma_load_4d(dst, a.map_full, bar, (a.x0 - 1) * 8, a.y0 - 1, zc, a.cc0);
+            tma_load_4d(dst + (a.cnt - 1) * kAStageBytes, a.map_last, bar, (a.x0 - 1) * 8, a.y0 - 1, zc,
+                        a.cc0 + 2 * (a.cnt - 1));
+        }
     };
+    // super image idx of the round (pass, outer, sg) = the weight images [first, first + cnt) of wpacked, one barrier
     auto issue_b = [&](int idx, uint32_t slot) {
-        const int g = (idx % p.n_bimg) % p.G;
-        const bool lone = p.lone_last && g == p.G - 1;
-        const uint32_t bytes = (lone ? p.steps_lone : p.steps_full) * 2 * p.NB * 16;
-        mbar_arrive_expect_tx(&full_b[slot], bytes);
-        bulk_load(sB + slot * p.bbuf_bytes, p.wpacked + static_cast<size_t>(idx) * p.bimg_stride, bytes, &full_b[slot]);
+        const int pass = idx / p.n_simg, si = idx - pass * p.n_simg;
+        const int outer = si / p.SG, sg = si - outer * p.SG;
+        const int g0 = p.gp * sg;
+        const int cnt = min(p.gp, p.G - g0);
+        const bool last_lone = p.lone_last && g0 + cnt == p.G;
+        const uint32_t full_bytes = static_cast<uint32_t>(p.steps_full) * 2 * p.NB * 16;
+        const uint32_t lone_bytes = static_cast<uint32_t>(p.steps_lone) * 2 * p.NB * 16;
+        const int first = pass * p.n_bimg + outer * p.G + g0;
+        mbar_arrive_expect_tx(&full_b[slot], (cnt - 1) * full_bytes + (last_lone ? lone_bytes : full_bytes));
+        for (int q = 0; q < cnt; ++q)
+            bulk_load(sB + slot * p.bbuf_bytes + q * p.bimg_stride,
+                      p.wpacked + static_cast<size_t>(first + q) * p.bimg_stride,
+                      (last_lone && q == cnt - 1) ? lone_bytes : full_bytes, &full_b[slot]);
     };
     if (warp == 0) {
         // =============================================================== A producer (ring 0)
@@ -615,14 +657,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int q = 0; q < n_seq; q += dual ? 2 : 1) {
                 int tile, pass;
                 unit_of(q, tile, pass);          // ring 0 units always exist
-                for (int bi = 0; bi < p.n_bimg; ++bi) {
-                    int x0, y0, zc, zstep, cc;
-                    uint32_t bytes;
-                    const CUtensorMap* map;
-                    image_loads(tile, bi, x0, y0, zc, zstep, cc, bytes, map);
-                    for (int j = 0; j < n_img_planes; ++j, zc += zstep) {
+                for (int si = 0; si < p.n_simg; ++si) {
+                    ALoad al;
+                    image_loads(tile, si, al);
+                    int zc = al.zc;
+                    for (int j = 0; j < n_img_planes; ++j, zc += al.zstep) {
                         mbar_wait(&empty_a[s], ph ^ 1);
-                        issue_a(sA + s * p.stage_bytes, map, &full_a[s], bytes, x0, y0, zc, cc);
+                        issue_a(sA + s * p.stage_bytes, &full_a[s], al, zc);
                         if (++s == static_cast<uint32_t>(ring_n)) {
                             s = 0;
                             ph ^= 1;
@@ -636,7 +677,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (!dual) {
                 // =========================================================== B producer (blocking)
                 // resident mode: every image has its own slot, loaded once; otherwise a ring re-streamed per unit
-                const int total = p.resident ? n_img_round : n_seq * p.n_bimg;
+                const int total = p.resident ? n_img_round : n_seq * p.n_simg;
                 uint32_t s = 0, ph = 0;
                 int idx = 0;
                 for (int it = 0; it < total; ++it) {
@@ -652,7 +693,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 // =========================================================== B producer + A producer of ring 1
                 // One thread serves two queues, so it must never block on either: both are polled (test_wait).  Blocking
                 // on a full A ring while issuer 1 waits for a weight image that only this thread can load would deadlock.
-                const int b_total = p.resident ? n_img_round : (n_seq / 2) * p.n_bimg;
+                const int b_total = p.resident ? n_img_round : (n_seq / 2) * p.n_simg;
                 int b_next = 0, b_idx = 0;
                 uint32_t b_s = 0, b_ph = 0;
                 uint64_t* const full_r = full_a + ring_n;
@@ -660,9 +701,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 uint8_t* const sA_r = sA + ring_n * p.stage_bytes;
                 uint32_t s = 0, ph = 0;
                 int q = 1, bi = 0, j = 0, tile = 0, pass = 0;
-                int x0 = 0, y0 = 0, zc = 0, zstep = 1, cc = 0;
-                uint32_t bytes = 0;
-                const CUtensorMap* map = nullptr;
+                int zc = 0;
+                ALoad al{};
                 bool a_done = true;
                 // position the A cursor on the first existing unit of ring 1
                 auto seek = [&]() {
@@ -672,7 +712,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                             a_done = false;
                             bi = 0;
                             j = 0;
-                            image_loads(tile, 0, x0, y0, zc, zstep, cc, bytes, map);
+                            image_loads(tile, 0, al);
+                            zc = al.zc;
                             break;
                         }
                     }
@@ -691,19 +732,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         progress = true;
                     }
                     if (!a_done && mbar_test(&empty_r[s], ph ^ 1)) {
-                        issue_a(sA_r + s * p.stage_bytes, map, &full_r[s], bytes, x0, y0, zc, cc);
+                        issue_a(sA_r + s * p.stage_bytes, &full_r[s], al, zc);
                         if (++s == static_cast<uint32_t>(ring_n)) {
                             s = 0;
                             ph ^= 1;
                         }
-                        zc += zstep;
+                        zc += al.zstep;
                         if (++j == n_img_planes) {
                             j = 0;
-                            if (++bi == p.n_bimg) {
+                            if (++bi == p.n_simg) {
                                 q += 2;
                                 seek();
                             } else {
-                                image_loads(tile, bi, x0, y0, zc, zstep, cc, bytes, map);
+                                image_loads(tile, bi, al);
+                                zc = al.zc;
                             }
                         }
                         progress = true;
@@ -717,7 +759,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int r = warp >> 1;
         if (elect_one()) {
             // everything the loop needs lives in registers: no divisions, no parameter re-loads per MMA
-            const int mode = p.mode, na = ring_n, nbuf = p.nbuf, n_bimg = p.n_bimg, G = p.G;
+            const int mode = p.mode, na = ring_n, nbuf = p.nbuf, n_simg = p.n_simg, G = p.G, gp = p.gp, SG = p.SG;
             const bool lone_last = p.lone_last != 0, resident = p.resident != 0;
             uint32_t a_s = 0, a_ph = 0, b_s = 0, b_ph = 0;
             uint64_t* const full_r = full_a + r * ring_n;
@@ -727,13 +769,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             const uint32_t bbuf16 = static_cast<uint32_t>(p.bbuf_bytes) >> 4;
             const uint32_t b_lbo = static_cast<uint32_t>(p.NB) << 16;   // LBO = NB * 16 bytes
             const uint32_t bstep16 = 2 * p.NB;                          // one step of a B image, in 16-byte units
+            const uint32_t bimg16 = static_cast<uint32_t>(p.bimg_stride) >> 4;   // second image of a super-group slot
             for (int q = dual ? r : 0; q < n_seq; q += dual ? 2 : 1) {
                 int tile, pass;
                 if (!unit_of(q, tile, pass)) {
                     // the partner issuer has a tile in this round, this one has none: release the streamed weight
                     // images it would have consumed, so that the shared ring keeps turning
                     if (!resident) {
-                        for (int bi = 0; bi < n_bimg; ++bi) {
+                        for (int bi = 0; bi < n_simg; ++bi) {
                             mbar_wait(&full_b[b_s], b_ph);
                             mbar_arrive(&empty_b[b_s]);
                             if (++b_s == static_cast<uint32_t>(nbuf)) {
@@ -745,27 +788,31 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     continue;
                 }
                 {
-                    if (resident) b_s = pass * n_bimg;     // image slot = (pass, image)
+                    if (resident) b_s = pass * n_simg;     // image slot = (pass, super image)
                     const uint32_t set = kSets == 2 ? (q & 1) : 0;
                     mbar_wait(&acc_empty[set], ((kSets == 2 ? (q >> 1) : q) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tacc = tmem + set * 256;
-                    int g = 0, gq = 0;   // bi = gq * G + g
-                    for (int bi = 0; bi < n_bimg; ++bi) {
-                        const bool lone = lone_last && g == G - 1 && mode != B200SEG_TC_K3T;
+                    int sg = 0, outer = 0;   // si = outer * SG + sg
+                    for (int si = 0; si < n_simg; ++si) {
+                        const int g0 = gp * sg;
+                        const int cnt = min(gp, G - g0);
+                        const bool last_lone = lone_last && g0 + cnt == G && mode != B200SEG_TC_K3T;
                         int zi0 = 0, zstep = 1, pp = 0;
                         if (mode == B200SEG_TC_DOWN) {
-                            zi0 = gq >> 2;
+                            zi0 = outer >> 2;
                             zstep = 2;
-                            pp = gq & 3;
+                            pp = outer & 3;
                         } else if (mode == B200SEG_TC_UP) {
                             pp = pass;
                         }
-                        if (++g == G) {
-                            g = 0;
-                            ++gq;
+                        if (++sg == SG) {
+                            sg = 0;
+                            ++outer;
                         }
-                        const int kind = mode == B200SEG_TC_K3T ? 4 : (mode == B200SEG_TC_K3 ? 0 : 2) + (lone ? 1 : 0);
+                        // 0 full | 1 lone | 2 full + full | 3 full + lone   (per visit: one or two chunk pairs)
+                        const int combo = cnt == 1 ? (last_lone ? 1 : 0) : (last_lone ? 3 : 2);
+                        const int kind = mode == B200SEG_TC_K3T ? 8 : (mode == B200SEG_TC_K3 ? 0 : 4) + combo;
                         const uint32_t pbase = parity_base(mode, pp);
                         const uint32_t bs = b_s;
                         mbar_wait(&full_b[bs], resident ? 0u : b_ph);   // resident images complete phase 0 once
@@ -776,29 +823,25 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         }
                         const uint32_t b16 = sB16 + bs * bbuf16;
                         const PlaneTab* pt = plane_tab + zi0;
-                        const bool first_image = bi == 0;
+                        const bool first_image = si == 0;
+#define B200SEG_RUN(K, K2)                                                                                             \
+    run_image<K, K2>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16, pbase, b16, b_lbo,     \
+                     bstep16, tacc, stage16, bimg16)
                         switch (kind) {
-                            case kK3Full:
-                                run_image<kK3Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
-                                break;
-                            case kK3Lone:
-                                run_image<kK3Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
-                                break;
-                            case kS2Full:
-                                run_image<kS2Full>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
-                                break;
-                            case kS2Lone:
-                                run_image<kS2Lone>(first_image, n_img_planes, zstep, pt, full_r, empty_r, a_s, a_ph, na, sA16,
-                                                   pbase, b16, b_lbo, bstep16, tacc, stage16);
-                                break;
+                            case 0: B200SEG_RUN(kK3Full, -1); break;
+                            case 1: B200SEG_RUN(kK3Lone, -1); break;
+                            case 2: B200SEG_RUN(kK3Full, kK3Full); break;
+                            case 3: B200SEG_RUN(kK3Full, kK3Lone); break;
+                            case 4: B200SEG_RUN(kS2Full, -1); break;
+                            case 5: B200SEG_RUN(kS2Lone, -1); break;
+                            case 6: B200SEG_RUN(kS2Full, kS2Full); break;
+                            case 7: B200SEG_RUN(kS2Full, kS2Lone); break;
                             default:
                                 run_image_t(G, lone_last, n_img_planes, pt, full_r, empty_r, a_s, a_ph, na, sA16, b16, b_lbo,
                                             bstep16, tacc, stage16);
                                 break;
                         }
+#undef B200SEG_RUN
                         if (!resident) umma_commit(&empty_b[bs]);
                     }
                     umma_commit(&acc_full[set]);
@@ -1380,17 +1423,38 @@ extern "C" int b200seg_conv3d_tc(int32_t mode, b200seg_view in, const void* wpac
         }
     }
     // ---- shared memory: weight image ring (double-buffered when it fits) + A plane ring
-    p.bbuf_bytes = (g.bimg_stride + 127) & ~127;
     const size_t misc = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + sizeof(PlaneTab) * kMaxZin +
                         3 * static_cast<size_t>(g.Cpad) * 4 + 256 +
                         (mode == B200SEG_TC_K3T ? 2 * 128 * static_cast<size_t>(p.tpitch) * 4 : 0);
     const size_t budget = variant == 2 ? 224 * 1024 : 112 * 1024;
     p.cin_chunks = cin_chunks;
-    p.stage_bytes = mode == B200SEG_TC_K3T ? g.G * kAStageBytes : kAStageBytes;
+    // Super groups (gp = 2): one visit of the MMA issuer handles TWO chunk pairs of the plane -- the A stage holds both
+    // halo boxes, the B slot two consecutive weight images.  Every layer whose MMAs are short is bound by the issuing
+    // thread's per-visit work (barrier round trip, ring bookkeeping, descriptor set-up: ~700 cycles for 2-9 MMAs, ncu
+    // profiles/r02_ncu_upsampling0_b8_*), so halving the visits is worth the coarser rings.  Taken when the operand
+    // still fits resident, or as a ring of >= 2 slots, next to >= 8 of the doubled A stages.
+    static const int gp_forced = [] {
+        const char* v = getenv("B200SEG_TC_GP");           // A/B hook: 1 = never, 2 = whenever it fits (default)
+        return (v && (v[0] == '1' || v[0] == '2')) ? v[0] - '0' : 0;
+    }();
+    p.gp = 1;
+    if (mode != B200SEG_TC_K3T && g.G >= 2 && gp_forced != 1) {
+        const size_t bbuf2 = (2 * static_cast<size_t>(g.bimg_stride) + 127) & ~static_cast<size_t>(127);
+        const size_t stage2 = 2 * kAStageBytes;
+        const int sg2 = (g.G + 1) / 2;
+        const int n_img2 = g.n_pass * (g.n_bimg / g.G) * sg2;
+        const bool resident2 = n_img2 <= kMaxB && misc + n_img2 * bbuf2 + 8 * stage2 <= budget;
+        const bool ring2 = misc + 2 * bbuf2 + 8 * stage2 <= budget;
+        if (resident2 || ring2) p.gp = 2;
+    }
+    p.SG = mode == B200SEG_TC_K3T ? 1 : (g.G + p.gp - 1) / p.gp;
+    p.n_simg = mode == B200SEG_TC_K3T ? 1 : (g.n_bimg / g.G) * p.SG;
+    p.bbuf_bytes = (p.gp * g.bimg_stride + 127) & ~127;
+    p.stage_bytes = mode == B200SEG_TC_K3T ? g.G * kAStageBytes : p.gp * kAStageBytes;
     const size_t stage = static_cast<size_t>(p.stage_bytes);
     // weights stay resident (one slot per image, loaded once per CTA) when the whole packed operand fits next to
     // at least 8 A stages; otherwise the images stream through a ring (double-buffered when possible)
-    const int n_images = g.n_pass * g.n_bimg;
+    const int n_images = g.n_pass * p.n_simg;
     p.resident = (n_images <= kMaxB &&
                   misc + static_cast<size_t>(n_images) * p.bbuf_bytes + 8 * stage <= budget) ? 1 : 0;
     p.nbuf = p.resident ? n_images
