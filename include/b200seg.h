@@ -212,6 +212,22 @@ int b200seg_argmax(const float* probs, int32_t c, int64_t voxels, int64_t* label
 int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes, int64_t voxels,
                       int32_t num_classes, int64_t* cm, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ instance evaluation
+ * InstanceSegmentationEvaluator.__call__ (evaluators/instance_segmentation_evaluator.py:103-129): connected components
+ * of `labels > 0` (skimage.morphology.label, connectivity 1 / 2 / 3 = 6 / 18 / 26 neighbours) and the table of voxel
+ * counts per (target component, predicted component) pair.
+ *   ccl3d_roots        union-find over voxel indices; parent[v] = root index (smallest index of the component) or -1
+ *                      for background; the roots are listed (unordered) in `roots`, their number in *n_roots
+ *   ccl3d_relabel      labels[v] = 1 + rank of v's root among `sorted_roots` (ascending) -- the numbering of a raster
+ *                      scan, i.e. skimage's; 0 = background.  The caller sorts the (few) roots between the two calls.
+ *   overlap_histogram  hist[t * (n_pred + 1) + p] += #voxels with target component t and predicted component p */
+int b200seg_ccl3d_roots(const void* mask, int32_t label_bytes, int32_t w, int32_t h, int32_t d, int32_t connectivity,
+                        int32_t* parent, int32_t* roots, int32_t max_roots, int32_t* n_roots, void* stream);
+int b200seg_ccl3d_relabel(const int32_t* parent, int64_t voxels, const int32_t* sorted_roots, int32_t n_roots,
+                          int32_t* labels, void* stream);
+int b200seg_overlap_histogram(const int32_t* target, const int32_t* pred, int64_t voxels, int32_t n_target,
+                              int32_t n_pred, int64_t* hist, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ criterion
  * HybridLogisticDiceLoss.forward (criterions/hybrid_logistic_dice_loss.py:13-43): prediction / target fp32
  * (N, C, voxels) contiguous.  ONE pass produces sums[n*c][4] = {sum p t, sum p^2 | p, sum t^2 | t,

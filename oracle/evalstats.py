@@ -91,3 +91,71 @@ def segmentation_stats(pred: np.ndarray, target: np.ndarray, label_values: Dict[
 def label_volumes(label_map: np.ndarray, label_values: Dict[str, int]) -> Dict[str, int]:
     """label_map_evaluator.py:77-81: ``(data == v).sum()`` per label (int64)."""
     return {name: int((np.asarray(label_map) == v).sum()) for name, v in label_values.items()}
+
+
+# --------------------------------------------------------------------------------------------- instance evaluation
+def connected_components(mask: np.ndarray, connectivity: int = 2):
+    """``skimage.morphology.label(mask, return_num=True, connectivity=connectivity)`` as used at
+    evaluators/instance_segmentation_evaluator.py:107-109.  skimage is not installed here; ``scipy.ndimage.label`` with
+    ``generate_binary_structure(3, connectivity)`` defines the same neighbourhood (voxels within ``connectivity``
+    orthogonal steps) and numbers components in the same raster-scan order."""
+    from scipy import ndimage
+    labels, n = ndimage.label(np.asarray(mask) > 0, structure=ndimage.generate_binary_structure(3, connectivity))
+    return labels.astype(np.int64), int(n)
+
+
+def instance_overlap_histogram(pred: np.ndarray, target: np.ndarray, connectivity: int = 2):
+    """instance_segmentation_evaluator.py:103-124: components of pred > 0 and target > 0, then the (N + 1, M + 1) table
+    of voxel counts per (target component, predicted component) pair (the reference encodes the pair as
+    target + prediction * 10**6 and counts with torch.unique)."""
+    pc, m = connected_components(pred, connectivity)
+    tc, n = connected_components(target, connectivity)
+    hist = np.zeros((n + 1, m + 1), np.int64)
+    np.add.at(hist, (tc.reshape(-1), pc.reshape(-1)), 1)
+    return hist, n, m
+
+
+def msseg_detection_test(overlap_histogram: torch.Tensor, min_recall=0.1, contribution_threshold=0.65,
+                         min_precision=0.3) -> torch.Tensor:
+    """instance_segmentation_evaluator.py:10-72, restated statement by statement (float32 table)."""
+    n = overlap_histogram.shape[0] - 1
+    target_volume = overlap_histogram.sum(dim=1)
+    prediction_volume = overlap_histogram.sum(dim=0)
+    detected = []
+    for i in range(1, n + 1):
+        target_tp = overlap_histogram[i, 1:].sum()
+        recall = target_tp / target_volume[i]
+        if recall < min_recall:
+            detected.append(False)
+            continue
+        predicted_ids = torch.argsort(overlap_histogram[i, 1:], descending=True) + 1
+        contribution_total = 0.0
+        for j in predicted_ids:
+            precision = overlap_histogram[i, j] / prediction_volume[j]
+            if precision < min_precision:
+                detected.append(False)
+                break
+            contribution = overlap_histogram[i, j] / target_tp
+            contribution_total += contribution
+            if contribution_total >= contribution_threshold:
+                detected.append(True)
+                break
+    return torch.tensor(detected)
+
+
+def instance_stats(pred: np.ndarray, target: np.ndarray, connectivity: int = 2) -> Dict[str, float]:
+    """instance_segmentation_evaluator.py:126-160 for one subject."""
+    hist, n, m = instance_overlap_histogram(pred, target, connectivity)
+    h = torch.from_numpy(hist).to(torch.float32)
+    target_detected = msseg_detection_test(h)
+    prediction_detected = msseg_detection_test(h.T)
+    detection_recall = target_detected.sum() / n
+    detection_precision = prediction_detected.sum() / m
+    detection_f1 = 2 * (detection_recall * detection_precision) / (detection_recall + detection_precision)
+    TP, FP, TN, FN = h[1:, 1:].sum(), h[0, 1:].sum(), h[0, 0].sum(), h[1:, 0].sum()
+    s = {'target_components': n, 'predicted_components': m, 'target_detections': target_detected.sum(),
+         'predicted_detections': prediction_detected.sum(), 'detection_recall': detection_recall,
+         'detection_precision': detection_precision, 'detection_f1': detection_f1, 'target_volume': TP + FN,
+         'prediction_volume': TP + FP, 'TP': TP, 'FP': FP, 'TN': TN, 'FN': FN, 'dice': 2 * TP / (2 * TP + FP + FN),
+         'jaccard': TP / (TP + FP + FN), 'precision': TP / (TP + FP), 'recall': TP / (TP + FN)}
+    return {k: (v.item() if isinstance(v, torch.Tensor) else v) for k, v in s.items()}

@@ -40,6 +40,7 @@ SHADOW = frozenset({
     "models",                       # the package __init__ too (same exports + set_precision / get_precision)
     "models.components", "models.modular_unet", "models.nested_residual_unet", "models.ensemble", "models.utils",
     "evaluators.segmentation_evaluator", "evaluators.label_map_evaluator",
+    "evaluators.instance_segmentation_evaluator",     # also drops the reference module's import-time skimage dependency
     "criterions.hybrid_logistic_dice_loss",
 })
 

@@ -74,6 +74,10 @@ _SIGNATURES = {
                                               c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200seg_hybrid_loss_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p,
                                                c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200seg_ccl3d_roots": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                      c_void_p, c_void_p]),
+    "b200seg_ccl3d_relabel": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200seg_overlap_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b200seg_confusion": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -444,3 +448,40 @@ def hybrid_loss_backward(prediction: torch.Tensor, target: torch.Tensor, sums: t
                                                        float(dice_weight), _ptr(class_weights), 1 if square_dice else 0,
                                                        _ptr(grad_loss), _ptr(grad), _stream()), "hybrid_loss_backward")
     return grad
+
+
+def connected_components(mask: torch.Tensor, connectivity: int = 2, max_components: int = 1 << 20):
+    """mask: (W, H, D) uint8 / int32 / int64 on the device (foreground = values > 0) -> (labels int32 (W, H, D) with
+    components numbered 1..N in raster-scan order like skimage.morphology.label, N)."""
+    _require_cuda(mask)
+    assert mask.dim() == 3 and mask.is_contiguous() and mask.dtype in (torch.uint8, torch.int32, torch.int64)
+    w, h, d = mask.shape
+    dev = mask.device
+    parent = torch.empty((w, h, d), dtype=torch.int32, device=dev)
+    roots = torch.empty(max_components, dtype=torch.int32, device=dev)
+    n_roots = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = load_library()
+    _LAUNCHES[0] += 3
+    _check(lib.b200seg_ccl3d_roots(_ptr(mask), mask.element_size(), w, h, d, int(connectivity), _ptr(parent), _ptr(roots),
+                                   max_components, _ptr(n_roots), _stream()), "ccl3d_roots")
+    n = int(n_roots.item())
+    if n > max_components:
+        raise RuntimeError(f"connected_components: {n} components exceed max_components = {max_components}")
+    sorted_roots = torch.sort(roots[:n]).values.contiguous()        # a few hundred integers: plumbing
+    labels = torch.empty((w, h, d), dtype=torch.int32, device=dev)
+    _LAUNCHES[0] += 1
+    _check(lib.b200seg_ccl3d_relabel(_ptr(parent), parent.numel(), _ptr(sorted_roots), n, _ptr(labels), _stream()),
+           "ccl3d_relabel")
+    return labels, n
+
+
+def overlap_histogram(target: torch.Tensor, pred: torch.Tensor, n_target: int, n_pred: int) -> torch.Tensor:
+    """int64 (n_target + 1, n_pred + 1) table of voxel counts per (target component, predicted component) pair."""
+    _require_cuda(target, pred)
+    assert target.dtype == torch.int32 and pred.dtype == torch.int32 and target.is_contiguous() and pred.is_contiguous()
+    assert target.numel() == pred.numel()
+    hist = torch.zeros((n_target + 1, n_pred + 1), dtype=torch.int64, device=target.device)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_overlap_histogram(_ptr(target), _ptr(pred), target.numel(), n_target, n_pred,
+                                                    _ptr(hist), _stream()), "overlap_histogram")
+    return hist

@@ -99,6 +99,48 @@ def test_softmax_and_stochastic_matrix(lib):
     assert rel_err(y.cpu(), unet.stochastic_matrix(x, 3, 1.5)) <= 1e-6
 
 
+# ----------------------------------------------------------------------------------------------- instance evaluation
+def _blob_mask(shape, n_blobs, seed, big=False):
+    rng = np.random.default_rng(seed)
+    zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    m = np.zeros(shape, bool)
+    for _ in range(n_blobs):
+        c = [rng.uniform(0, s) for s in shape]
+        r = rng.uniform(1.0, 6.0 if big else 3.5, 3)
+        m |= ((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2 < 1
+    m |= rng.random(shape) < 0.002                       # isolated voxels and diagonal contacts
+    return m
+
+
+@pytest.mark.parametrize("connectivity", [1, 2, 3])
+@pytest.mark.parametrize("shape,dtype", [((40, 36, 28), torch.uint8), ((17, 50, 33), torch.int64), ((64, 64, 48), torch.int32)])
+def test_connected_components_match_scipy(lib, connectivity, shape, dtype):
+    """Device union-find labelling == scipy.ndimage.label (same partition AND the same raster-scan numbering as
+    skimage.morphology.label, which the reference calls at instance_segmentation_evaluator.py:108-109)."""
+    m = _blob_mask(shape, 25, 70 + connectivity + shape[0])
+    ref, n_ref = evalstats.connected_components(m, connectivity)
+    src = torch.from_numpy(m.astype(np.int64) * 3).to(dtype)          # foreground = any value > 0
+    labels, n = lib.connected_components(dev(src), connectivity)
+    assert n == n_ref and n > 10
+    np.testing.assert_array_equal(labels.cpu().numpy(), ref)
+    # degenerate inputs: empty and full masks
+    z, nz = lib.connected_components(dev(torch.zeros(shape, dtype=dtype)), connectivity)
+    assert nz == 0 and int(z.abs().sum()) == 0
+    o, no = lib.connected_components(dev(torch.ones(shape, dtype=dtype)), connectivity)
+    assert no == 1 and int((o != 1).sum()) == 0
+
+
+def test_overlap_histogram_bit_exact(lib):
+    pm, tm = _blob_mask((48, 40, 36), 30, 81, big=True), _blob_mask((48, 40, 36), 30, 82, big=True)
+    hist_ref, n, m = evalstats.instance_overlap_histogram(pm, tm, 2)
+    pc, m2 = lib.connected_components(dev(torch.from_numpy(pm.astype(np.uint8))), 2)
+    tc, n2 = lib.connected_components(dev(torch.from_numpy(tm.astype(np.uint8))), 2)
+    assert (n2, m2) == (n, m)
+    hist = lib.overlap_histogram(tc, pc, n, m)
+    np.testing.assert_array_equal(hist.cpu().numpy(), hist_ref)
+    assert int(hist.sum()) == pm.size
+
+
 # ----------------------------------------------------------------------------------------------- criterion
 @pytest.mark.parametrize("square_dice,weights", [(True, None), (False, [0.3, 1.0, 2.0]), (True, [1.0, 0.5, 0.25])])
 def test_hybrid_logistic_dice_loss_matches_oracle_and_autograd(lib, square_dice, weights):

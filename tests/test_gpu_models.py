@@ -392,6 +392,32 @@ def test_segmentation_evaluator_with_labels_outside_label_values():
     assert list(vol) == list(evalstats.label_volumes(pred, label_values).values())
 
 
+def test_instance_segmentation_evaluator_matches_oracle():
+    """InstanceSegmentationEvaluator (MSSEG lesion-detection metric): components + overlap table on the device, every
+    statistic equal to the oracle restatement of instance_segmentation_evaluator.py:103-160."""
+    from test_gpu_kernels import _blob_mask
+    from segmentation_pipeline import _tio
+    from segmentation_pipeline.evaluators import InstanceSegmentationEvaluator
+    subjects, want = [], {}
+    for i in range(3):
+        targ = _blob_mask((48, 40, 36), 14, 90 + i, big=True)
+        pred = np.roll(targ, (1, 2, 0), (0, 1, 2)) | _blob_mask((48, 40, 36), 4, 95 + i, big=True)   # shifted + extra lesions
+        if i == 2:
+            pred = targ.copy()                                                                # perfect prediction
+        subjects.append(_tio.Subject(name=f"s{i}", pred=_tio.LabelMap(tensor=torch.from_numpy(pred[None].astype(np.int64))),
+                                     targ=_tio.LabelMap(tensor=torch.from_numpy(targ[None].astype(np.int64)))))
+        want[f"s{i}"] = evalstats.instance_stats(pred, targ, 2)
+    ev = InstanceSegmentationEvaluator("pred", "targ")
+    res = ev(subjects)["subject_stats"]
+    for i in range(3):
+        row = res.iloc[i]
+        for stat in ev.stats_to_output:
+            a, b = float(row[stat]), float(want[f"s{i}"][stat])
+            assert a == b or (np.isnan(a) and np.isnan(b)), (i, stat, a, b)
+    assert float(res.iloc[2]["detection_f1"]) == 1.0 and float(res.iloc[2]["dice"]) == 1.0
+    assert float(res.iloc[0]["target_components"]) > 5
+
+
 def test_slab_mode_single_rank_equals_patch_predict():
     """z-slab driver with the CUDA ops on one rank == PatchPredict.predict_volume, bit for bit."""
     from segmentation_pipeline.distributed import CudaSlabOps, slab_predict
