@@ -220,13 +220,34 @@ int b200seg_confusion(const void* pred, const void* target, int32_t label_bytes,
  *                      for background; the roots are listed (unordered) in `roots`, their number in *n_roots
  *   ccl3d_relabel      labels[v] = 1 + rank of v's root among `sorted_roots` (ascending) -- the numbering of a raster
  *                      scan, i.e. skimage's; 0 = background.  The caller sorts the (few) roots between the two calls.
- *   overlap_histogram  hist[t * (n_pred + 1) + p] += #voxels with target component t and predicted component p */
+ *   overlap_histogram  hist[t * (n_pred + 1) + p] += #voxels with target component t and predicted component p
+ *                      (pred == NULL with n_pred == 0: plain per-label voxel counts)
+ * by_value == 1 labels an INTEGER image the way skimage.measure.label does (background 0, neighbours connect only when
+ * they carry the same value) -- post_processing.py:31 keep_components; by_value == 2 labels the INVERTED mask
+ * (values <= 0), the holes skimage's remove_small_holes measures -- post_processing.py:56.
+ * Post-processing (post_processing.py:5-73 sort_by_size / unsort_by_size / keep_components / remove_holes /
+ * remove_small_components; research/msseg2/competition/ms-inference.py:47-50, research/dmri_hippo/hippo_inference.py:40-44):
+ *   relabel_lut        dst[v] = lut[src[v]] (values outside [0, n_lut) are copied)
+ *   dilate_cross       grey dilation with the 3-D cross, skimage.morphology.dilation's default footprint
+ *   dilate_where       dst = (mask && D != dil_src) ? D : pass_src with D = dilate_cross(dil_src), fused
+ *                      (post_processing.py:44-46 and :62)
+ *   relabel_masked     dst = keep_lut[comp] ? lut[img] : 0 (post_processing.py:42 `sorted_img * keep`)
+ *   label_equals       dst = (src == value);  mask_assign  dst[mask != 0] = value (post_processing.py:69-71) */
 int b200seg_ccl3d_roots(const void* mask, int32_t label_bytes, int32_t w, int32_t h, int32_t d, int32_t connectivity,
-                        int32_t* parent, int32_t* roots, int32_t max_roots, int32_t* n_roots, void* stream);
+                        int32_t by_value, int32_t* parent, int32_t* roots, int32_t max_roots, int32_t* n_roots,
+                        void* stream);
 int b200seg_ccl3d_relabel(const int32_t* parent, int64_t voxels, const int32_t* sorted_roots, int32_t n_roots,
                           int32_t* labels, void* stream);
 int b200seg_overlap_histogram(const int32_t* target, const int32_t* pred, int64_t voxels, int32_t n_target,
                               int32_t n_pred, int64_t* hist, void* stream);
+int b200seg_relabel_lut(const int32_t* src, int64_t voxels, const int32_t* lut, int32_t n_lut, int32_t* dst, void* stream);
+int b200seg_dilate_cross(const int32_t* src, int32_t w, int32_t h, int32_t d, int32_t* dst, void* stream);
+int b200seg_dilate_where(const int32_t* dil_src, const int32_t* mask, const int32_t* pass_src, int32_t w, int32_t h,
+                         int32_t d, int32_t* dst, void* stream);
+int b200seg_relabel_masked(const int32_t* img, const int32_t* lut, int32_t n_lut, const int32_t* comp,
+                           const int32_t* keep_lut, int32_t n_keep, int64_t voxels, int32_t* dst, void* stream);
+int b200seg_label_equals(const int32_t* src, int64_t voxels, int32_t value, int32_t* dst, void* stream);
+int b200seg_mask_assign(int32_t* dst, const int32_t* mask, int64_t voxels, int32_t value, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ criterion
  * HybridLogisticDiceLoss.forward (criterions/hybrid_logistic_dice_loss.py:13-43): prediction / target fp32

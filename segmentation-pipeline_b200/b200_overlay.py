@@ -11,7 +11,7 @@ Why an import hook.  Both trees are regular packages called ``segmentation_pipel
 finder that resolves every ``segmentation_pipeline.*`` module FILE BY FILE:
 
   * the modules of the hot path come from this package (``SHADOW``): ``prediction``, ``models.*``, the two
-    evaluators whose voxel work is the device confusion histogram, and the criterion;
+    evaluators whose voxel work is the device confusion histogram, the criterion, and ``post_processing``;
   * every other module, and every package ``__init__``, is the reference's own file, executed unmodified -- so
     ``segmentation_trainer.py``, the transforms, ``TorchContext``, the data loaders and the ``research/*`` configs see
     exactly the namespace they were written against (``from .evaluators import *``, ``from segmentation_pipeline
@@ -42,6 +42,7 @@ SHADOW = frozenset({
     "evaluators.segmentation_evaluator", "evaluators.label_map_evaluator",
     "evaluators.instance_segmentation_evaluator",     # also drops the reference module's import-time skimage dependency
     "criterions.hybrid_logistic_dice_loss",
+    "post_processing",              # label clean-up after inference; also drops its import-time skimage dependency
 })
 
 

@@ -74,8 +74,15 @@ _SIGNATURES = {
                                               c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200seg_hybrid_loss_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p,
                                                c_int32, c_void_p, c_void_p, c_void_p]),
-    "b200seg_ccl3d_roots": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
-                                      c_void_p, c_void_p]),
+    "b200seg_ccl3d_roots": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                      c_int32, c_void_p, c_void_p]),
+    "b200seg_relabel_lut": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200seg_dilate_cross": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200seg_dilate_where": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200seg_relabel_masked": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int64, c_void_p,
+                                         c_void_p]),
+    "b200seg_label_equals": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "b200seg_mask_assign": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "b200seg_ccl3d_relabel": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200seg_overlap_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b200seg_confusion": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
@@ -450,9 +457,12 @@ def hybrid_loss_backward(prediction: torch.Tensor, target: torch.Tensor, sums: t
     return grad
 
 
-def connected_components(mask: torch.Tensor, connectivity: int = 2, max_components: int = 1 << 20):
+def connected_components(mask: torch.Tensor, connectivity: int = 2, max_components: int = 1 << 20,
+                         by_value: int = 0):
     """mask: (W, H, D) uint8 / int32 / int64 on the device (foreground = values > 0) -> (labels int32 (W, H, D) with
-    components numbered 1..N in raster-scan order like skimage.morphology.label, N)."""
+    components numbered 1..N in raster-scan order like skimage.morphology.label, N).  ``by_value``: label an integer
+    image like skimage.measure.label (background 0, only equal-valued neighbours connect); ``by_value=2``: label the
+    inverted mask (values <= 0)."""
     _require_cuda(mask)
     assert mask.dim() == 3 and mask.is_contiguous() and mask.dtype in (torch.uint8, torch.int32, torch.int64)
     w, h, d = mask.shape
@@ -462,8 +472,8 @@ def connected_components(mask: torch.Tensor, connectivity: int = 2, max_componen
     n_roots = torch.zeros(1, dtype=torch.int32, device=dev)
     lib = load_library()
     _LAUNCHES[0] += 3
-    _check(lib.b200seg_ccl3d_roots(_ptr(mask), mask.element_size(), w, h, d, int(connectivity), _ptr(parent), _ptr(roots),
-                                   max_components, _ptr(n_roots), _stream()), "ccl3d_roots")
+    _check(lib.b200seg_ccl3d_roots(_ptr(mask), mask.element_size(), w, h, d, int(connectivity), int(by_value),
+                                   _ptr(parent), _ptr(roots), max_components, _ptr(n_roots), _stream()), "ccl3d_roots")
     n = int(n_roots.item())
     if n > max_components:
         raise RuntimeError(f"connected_components: {n} components exceed max_components = {max_components}")
@@ -475,13 +485,79 @@ def connected_components(mask: torch.Tensor, connectivity: int = 2, max_componen
     return labels, n
 
 
-def overlap_histogram(target: torch.Tensor, pred: torch.Tensor, n_target: int, n_pred: int) -> torch.Tensor:
-    """int64 (n_target + 1, n_pred + 1) table of voxel counts per (target component, predicted component) pair."""
+def overlap_histogram(target: torch.Tensor, pred: Optional[torch.Tensor], n_target: int, n_pred: int) -> torch.Tensor:
+    """int64 (n_target + 1, n_pred + 1) table of voxel counts per (target component, predicted component) pair;
+    ``pred=None, n_pred=0``: the voxel count of every label 0..n_target."""
     _require_cuda(target, pred)
-    assert target.dtype == torch.int32 and pred.dtype == torch.int32 and target.is_contiguous() and pred.is_contiguous()
-    assert target.numel() == pred.numel()
+    assert target.dtype == torch.int32 and target.is_contiguous()
+    assert pred is None or (pred.dtype == torch.int32 and pred.is_contiguous() and target.numel() == pred.numel())
     hist = torch.zeros((n_target + 1, n_pred + 1), dtype=torch.int64, device=target.device)
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_overlap_histogram(_ptr(target), _ptr(pred), target.numel(), n_target, n_pred,
                                                     _ptr(hist), _stream()), "overlap_histogram")
     return hist
+
+
+def relabel_lut(src: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    """int32 labels -> lut[labels] (int32 lookup table on the device)."""
+    _require_cuda(src, lut)
+    assert src.dtype == torch.int32 and lut.dtype == torch.int32 and src.is_contiguous() and lut.is_contiguous()
+    dst = torch.empty_like(src)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_relabel_lut(_ptr(src), src.numel(), _ptr(lut), lut.numel(), _ptr(dst), _stream()),
+           "relabel_lut")
+    return dst
+
+
+def dilate_cross(src: torch.Tensor) -> torch.Tensor:
+    """Grey dilation of an int32 (W, H, D) volume with the 3-D cross (skimage.morphology.dilation's default)."""
+    _require_cuda(src)
+    assert src.dtype == torch.int32 and src.dim() == 3 and src.is_contiguous()
+    dst = torch.empty_like(src)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_dilate_cross(_ptr(src), *src.shape, _ptr(dst), _stream()), "dilate_cross")
+    return dst
+
+
+def _i32(*tensors):
+    _require_cuda(*tensors)
+    for t in tensors:
+        assert t.dtype == torch.int32 and t.is_contiguous()
+
+
+def dilate_where(dil_src: torch.Tensor, mask: torch.Tensor, pass_src: torch.Tensor) -> torch.Tensor:
+    """where(mask & (D != dil_src), D, pass_src) with D = dilate_cross(dil_src), one kernel."""
+    _i32(dil_src, mask, pass_src)
+    assert dil_src.dim() == 3 and dil_src.shape == mask.shape == pass_src.shape
+    dst = torch.empty_like(dil_src)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_dilate_where(_ptr(dil_src), _ptr(mask), _ptr(pass_src), *dil_src.shape, _ptr(dst),
+                                               _stream()), "dilate_where")
+    return dst
+
+
+def relabel_masked(img: torch.Tensor, lut: torch.Tensor, comp: torch.Tensor, keep_lut: torch.Tensor) -> torch.Tensor:
+    """where(keep_lut[comp], lut[img], 0)."""
+    _i32(img, lut, comp, keep_lut)
+    assert img.shape == comp.shape
+    dst = torch.empty_like(img)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_relabel_masked(_ptr(img), _ptr(lut), lut.numel(), _ptr(comp), _ptr(keep_lut),
+                                                 keep_lut.numel(), img.numel(), _ptr(dst), _stream()), "relabel_masked")
+    return dst
+
+
+def label_equals(src: torch.Tensor, value: int) -> torch.Tensor:
+    _i32(src)
+    dst = torch.empty_like(src)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_label_equals(_ptr(src), src.numel(), int(value), _ptr(dst), _stream()), "label_equals")
+    return dst
+
+
+def mask_assign(dst: torch.Tensor, mask: torch.Tensor, value: int) -> torch.Tensor:
+    _i32(dst, mask)
+    assert dst.shape == mask.shape
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_mask_assign(_ptr(dst), _ptr(mask), dst.numel(), int(value), _stream()), "mask_assign")
+    return dst

@@ -54,14 +54,19 @@ __device__ __forceinline__ void ccl_union(int* parent, int a, int b) {
 
 template <typename L>
 __global__ void __launch_bounds__(kCclThreads)
-ccl_init_kernel(const L* __restrict__ src, long long vox, int* __restrict__ parent) {
+ccl_init_kernel(const L* __restrict__ src, long long vox, int* __restrict__ parent, int by_value) {
     long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
     if (v >= vox) return;
-    parent[v] = src[v] > 0 ? static_cast<int>(v) : -1;
+    // binary mode: foreground = values > 0 (the evaluator's `data > 0`); by-value mode: skimage.measure.label of an
+    // integer image -- background 0, two voxels are connected when they are neighbours AND carry the same value
+    // mode 2: the INVERTED mask (values <= 0) -- the holes remove_small_holes looks for (post_processing.py:56)
+    const bool fg = by_value == 1 ? src[v] != 0 : (by_value == 2 ? !(src[v] > 0) : src[v] > 0);
+    parent[v] = fg ? static_cast<int>(v) : -1;
 }
 
+template <typename L>
 __global__ void __launch_bounds__(kCclThreads)
-ccl_merge_kernel(int* __restrict__ parent, int w, int h, int d, int connectivity) {
+ccl_merge_kernel(const L* __restrict__ src, int* __restrict__ parent, int w, int h, int d, int connectivity, int by_value) {
     long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
     const long long vox = 1LL * w * h * d;
     if (v >= vox || reinterpret_cast<const volatile int*>(parent)[v] < 0) return;
@@ -78,7 +83,9 @@ ccl_merge_kernel(int* __restrict__ parent, int w, int h, int d, int connectivity
                 const int ni = i + di, nj = j + dj, nk = k + dk;
                 if (ni < 0 || nj < 0 || nj >= h || nk < 0 || nk >= d) continue;
                 const long long n = (1LL * ni * h + nj) * d + nk;
-                if (reinterpret_cast<const volatile int*>(parent)[n] >= 0) ccl_union(parent, static_cast<int>(v), static_cast<int>(n));
+                if (reinterpret_cast<const volatile int*>(parent)[n] < 0) continue;
+                if (by_value == 1 && src[n] != src[v]) continue;
+                ccl_union(parent, static_cast<int>(v), static_cast<int>(n));
             }
 }
 
@@ -115,7 +122,87 @@ ccl_relabel_kernel(const int* __restrict__ parent, long long vox, const int* __r
     labels[v] = lo + 1;
 }
 
-// hist[t * m1 + p] += 1 per voxel; lanes of a warp that hold the same pair are grouped (label maps are piecewise
+// dst[v] = lut[src[v]]  (sort_by_size / unsort_by_size of post_processing.py:5-26 as one gather)
+__global__ void __launch_bounds__(kCclThreads)
+relabel_lut_kernel(const int* __restrict__ src, long long vox, const int* __restrict__ lut, int n_lut, int* __restrict__ dst) {
+    long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
+    if (v >= vox) return;
+    const int x = src[v];
+    dst[v] = (x >= 0 && x < n_lut) ? __ldg(lut + x) : x;
+}
+
+// grey dilation with the 3-D cross (skimage.morphology.dilation default footprint, connectivity 1); border voxels see
+// their in-volume neighbours only (scipy's 'reflect' mode mirrors the border voxel itself, which changes nothing)
+__global__ void __launch_bounds__(kCclThreads)
+dilate_cross_kernel(const int* __restrict__ src, int w, int h, int d, int* __restrict__ dst) {
+    long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
+    const long long vox = 1LL * w * h * d;
+    if (v >= vox) return;
+    const int k = static_cast<int>(v % d);
+    const int j = static_cast<int>((v / d) % h);
+    const int i = static_cast<int>(v / (1LL * d * h));
+    int m = src[v];
+    if (k > 0) m = max(m, __ldg(src + v - 1));
+    if (k < d - 1) m = max(m, __ldg(src + v + 1));
+    if (j > 0) m = max(m, __ldg(src + v - d));
+    if (j < h - 1) m = max(m, __ldg(src + v + d));
+    if (i > 0) m = max(m, __ldg(src + v - 1LL * d * h));
+    if (i < w - 1) m = max(m, __ldg(src + v + 1LL * d * h));
+    dst[v] = m;
+}
+
+// out[v] = (mask[v] && D != dil_src[v]) ? D : pass_src[v], D = cross dilation of dil_src at v.  One kernel for
+// `img[small_holes] = dilation(img)[small_holes]` (post_processing.py:62; dil_src = pass_src = img) and for
+// `change = (dilated != to_dilate) & remove; sorted_img[change] = dilated[change]` (post_processing.py:44-46).
+__global__ void __launch_bounds__(kCclThreads)
+dilate_where_kernel(const int* __restrict__ dil_src, const int* __restrict__ mask, const int* __restrict__ pass_src,
+                    int w, int h, int d, int* __restrict__ dst) {
+    long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
+    const long long vox = 1LL * w * h * d;
+    if (v >= vox) return;
+    int out = pass_src[v];
+    if (mask[v] != 0) {
+        const int k = static_cast<int>(v % d);
+        const int j = static_cast<int>((v / d) % h);
+        const int i = static_cast<int>(v / (1LL * d * h));
+        const int c = dil_src[v];
+        int m = c;
+        if (k > 0) m = max(m, __ldg(dil_src + v - 1));
+        if (k < d - 1) m = max(m, __ldg(dil_src + v + 1));
+        if (j > 0) m = max(m, __ldg(dil_src + v - d));
+        if (j < h - 1) m = max(m, __ldg(dil_src + v + d));
+        if (i > 0) m = max(m, __ldg(dil_src + v - 1LL * d * h));
+        if (i < w - 1) m = max(m, __ldg(dil_src + v + 1LL * d * h));
+        if (m != c) out = m;
+    }
+    dst[v] = out;
+}
+
+// dst[v] = keep_lut[comp[v]] ? lut[img[v]] : 0   (`to_dilate = sorted_img * keep`, post_processing.py:42)
+__global__ void __launch_bounds__(kCclThreads)
+relabel_masked_kernel(const int* __restrict__ img, const int* __restrict__ lut, int n_lut, const int* __restrict__ comp,
+                      const int* __restrict__ keep_lut, int n_keep, long long vox, int* __restrict__ dst) {
+    long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
+    if (v >= vox) return;
+    const int c = comp[v];
+    const bool keep = c >= 0 && c < n_keep && __ldg(keep_lut + c) != 0;
+    const int x = img[v];
+    dst[v] = keep ? ((x >= 0 && x < n_lut) ? __ldg(lut + x) : x) : 0;
+}
+
+// dst[v] = src[v] == value   /   dst[v] = mask[v] ? value : dst[v]   (post_processing.py:69,71)
+__global__ void __launch_bounds__(kCclThreads)
+label_equals_kernel(const int* __restrict__ src, long long vox, int value, int* __restrict__ dst) {
+    long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
+    if (v < vox) dst[v] = src[v] == value ? 1 : 0;
+}
+__global__ void __launch_bounds__(kCclThreads)
+mask_assign_kernel(int* __restrict__ dst, const int* __restrict__ mask, long long vox, int value) {
+    long long v = blockIdx.x * 1LL * kCclThreads + threadIdx.x;
+    if (v < vox && mask[v] != 0) dst[v] = value;
+}
+
+// hist[t * m1 + p] += 1 per voxel (pred may be null: plain label counts); lanes of a warp that hold the same pair are grouped (label maps are piecewise
 // constant, the background pair dominates), one int64 atomic per distinct pair per warp
 __global__ void __launch_bounds__(kCclThreads)
 overlap_histogram_kernel(const int* __restrict__ target, const int* __restrict__ pred, long long vox, int m1,
@@ -126,7 +213,7 @@ overlap_histogram_kernel(const int* __restrict__ target, const int* __restrict__
     for (long long v0 = base - lane; v0 < vox; v0 += stride) {           // warp-uniform trip count
         const long long v = v0 + lane;
         const bool ok = v < vox;
-        const long long key = ok ? static_cast<long long>(__ldg(target + v)) * m1 + __ldg(pred + v) : -1;
+        const long long key = ok ? static_cast<long long>(__ldg(target + v)) * m1 + (pred != nullptr ? __ldg(pred + v) : 0) : -1;
         const unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const unsigned peers = __match_any_sync(active, key);
@@ -140,8 +227,8 @@ overlap_histogram_kernel(const int* __restrict__ target, const int* __restrict__
 using namespace b200seg;
 
 extern "C" int b200seg_ccl3d_roots(const void* mask, int32_t label_bytes, int32_t w, int32_t h, int32_t d,
-                                   int32_t connectivity, int32_t* parent, int32_t* roots, int32_t max_roots,
-                                   int32_t* n_roots, void* stream) {
+                                   int32_t connectivity, int32_t by_value, int32_t* parent, int32_t* roots,
+                                   int32_t max_roots, int32_t* n_roots, void* stream) {
     B200SEG_CHECK_ARG(mask && parent && roots && n_roots && w > 0 && h > 0 && d > 0, "ccl3d_roots: bad arguments");
     B200SEG_CHECK_ARG(label_bytes == 1 || label_bytes == 4 || label_bytes == 8, "ccl3d_roots: label_bytes must be 1, 4 or 8");
     B200SEG_CHECK_ARG(connectivity >= 1 && connectivity <= 3, "ccl3d_roots: connectivity %d not in [1,3]", connectivity);
@@ -150,10 +237,16 @@ extern "C" int b200seg_ccl3d_roots(const void* mask, int32_t label_bytes, int32_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const unsigned blocks = static_cast<unsigned>((vox + kCclThreads - 1) / kCclThreads);
     B200SEG_CHECK_CUDA(cudaMemsetAsync(n_roots, 0, sizeof(int32_t), s));
-    if (label_bytes == 1) ccl_init_kernel<uint8_t><<<blocks, kCclThreads, 0, s>>>(static_cast<const uint8_t*>(mask), vox, parent);
-    else if (label_bytes == 4) ccl_init_kernel<int><<<blocks, kCclThreads, 0, s>>>(static_cast<const int*>(mask), vox, parent);
-    else ccl_init_kernel<long long><<<blocks, kCclThreads, 0, s>>>(static_cast<const long long*>(mask), vox, parent);
-    ccl_merge_kernel<<<blocks, kCclThreads, 0, s>>>(parent, w, h, d, connectivity);
+#define B200SEG_CCL(T)                                                                                                \
+    do {                                                                                                              \
+        ccl_init_kernel<T><<<blocks, kCclThreads, 0, s>>>(static_cast<const T*>(mask), vox, parent, by_value);         \
+        ccl_merge_kernel<T><<<blocks, kCclThreads, 0, s>>>(static_cast<const T*>(mask), parent, w, h, d, connectivity,  \
+                                                           by_value);                                                  \
+    } while (0)
+    if (label_bytes == 1) B200SEG_CCL(uint8_t);
+    else if (label_bytes == 4) B200SEG_CCL(int);
+    else B200SEG_CCL(long long);
+#undef B200SEG_CCL
     ccl_flatten_kernel<<<blocks, kCclThreads, 0, s>>>(parent, vox, roots, max_roots, n_roots);
     return check_launch("ccl3d_roots");
 }
@@ -168,7 +261,8 @@ extern "C" int b200seg_ccl3d_relabel(const int32_t* parent, int64_t voxels, cons
 
 extern "C" int b200seg_overlap_histogram(const int32_t* target, const int32_t* pred, int64_t voxels, int32_t n_target,
                                          int32_t n_pred, int64_t* hist, void* stream) {
-    B200SEG_CHECK_ARG(target && pred && hist && voxels > 0 && n_target >= 0 && n_pred >= 0, "overlap_histogram: bad arguments");
+    B200SEG_CHECK_ARG(target && hist && voxels > 0 && n_target >= 0 && n_pred >= 0, "overlap_histogram: bad arguments");
+    B200SEG_CHECK_ARG(pred != nullptr || n_pred == 0, "overlap_histogram: pred may be null only with n_pred == 0");
     int dev = 0, sms = 148;
     B200SEG_CHECK_CUDA(cudaGetDevice(&dev));
     B200SEG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -177,4 +271,55 @@ extern "C" int b200seg_overlap_histogram(const int32_t* target, const int32_t* p
     overlap_histogram_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         target, pred, voxels, n_pred + 1, reinterpret_cast<unsigned long long*>(hist));
     return check_launch("overlap_histogram");
+}
+
+extern "C" int b200seg_relabel_lut(const int32_t* src, int64_t voxels, const int32_t* lut, int32_t n_lut, int32_t* dst,
+                                   void* stream) {
+    B200SEG_CHECK_ARG(src && dst && lut && voxels > 0 && n_lut > 0, "relabel_lut: bad arguments");
+    const unsigned blocks = static_cast<unsigned>((voxels + kCclThreads - 1) / kCclThreads);
+    relabel_lut_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, voxels, lut, n_lut, dst);
+    return check_launch("relabel_lut");
+}
+
+extern "C" int b200seg_dilate_cross(const int32_t* src, int32_t w, int32_t h, int32_t d, int32_t* dst, void* stream) {
+    B200SEG_CHECK_ARG(src && dst && src != dst && w > 0 && h > 0 && d > 0, "dilate_cross: bad arguments");
+    const long long vox = 1LL * w * h * d;
+    const unsigned blocks = static_cast<unsigned>((vox + kCclThreads - 1) / kCclThreads);
+    dilate_cross_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, w, h, d, dst);
+    return check_launch("dilate_cross");
+}
+
+extern "C" int b200seg_dilate_where(const int32_t* dil_src, const int32_t* mask, const int32_t* pass_src, int32_t w,
+                                    int32_t h, int32_t d, int32_t* dst, void* stream) {
+    B200SEG_CHECK_ARG(dil_src && mask && pass_src && dst && dst != dil_src && w > 0 && h > 0 && d > 0,
+                      "dilate_where: bad arguments");
+    const long long vox = 1LL * w * h * d;
+    const unsigned blocks = static_cast<unsigned>((vox + kCclThreads - 1) / kCclThreads);
+    dilate_where_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(dil_src, mask, pass_src, w, h, d, dst);
+    return check_launch("dilate_where");
+}
+
+extern "C" int b200seg_relabel_masked(const int32_t* img, const int32_t* lut, int32_t n_lut, const int32_t* comp,
+                                      const int32_t* keep_lut, int32_t n_keep, int64_t voxels, int32_t* dst,
+                                      void* stream) {
+    B200SEG_CHECK_ARG(img && lut && comp && keep_lut && dst && voxels > 0 && n_lut > 0 && n_keep > 0,
+                      "relabel_masked: bad arguments");
+    const unsigned blocks = static_cast<unsigned>((voxels + kCclThreads - 1) / kCclThreads);
+    relabel_masked_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(img, lut, n_lut, comp, keep_lut,
+                                                                                         n_keep, voxels, dst);
+    return check_launch("relabel_masked");
+}
+
+extern "C" int b200seg_label_equals(const int32_t* src, int64_t voxels, int32_t value, int32_t* dst, void* stream) {
+    B200SEG_CHECK_ARG(src && dst && voxels > 0, "label_equals: bad arguments");
+    const unsigned blocks = static_cast<unsigned>((voxels + kCclThreads - 1) / kCclThreads);
+    label_equals_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, voxels, value, dst);
+    return check_launch("label_equals");
+}
+
+extern "C" int b200seg_mask_assign(int32_t* dst, const int32_t* mask, int64_t voxels, int32_t value, void* stream) {
+    B200SEG_CHECK_ARG(dst && mask && voxels > 0, "mask_assign: bad arguments");
+    const unsigned blocks = static_cast<unsigned>((voxels + kCclThreads - 1) / kCclThreads);
+    mask_assign_kernel<<<blocks, kCclThreads, 0, static_cast<cudaStream_t>(stream)>>>(dst, mask, voxels, value);
+    return check_launch("mask_assign");
 }

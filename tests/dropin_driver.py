@@ -57,7 +57,7 @@ def main():
                            for k, v in sorted(finder.resolved.items())
                            if k.split(".")[-1] in ("segmentation_pipeline", "segmentation_trainer", "prediction",
                                                    "modular_unet", "segmentation_evaluator", "custom_label_transforms",
-                                                   "subject_folder", "torch_context", "data_loader_factory")}}
+                                                   "subject_folder", "torch_context", "data_loader_factory", "post_processing")}}
 
     # ------------------------------------------------------------------ synthetic dataset behind the reference's SubjectFolder
     tmp = tempfile.mkdtemp(prefix="b200_dropin_")

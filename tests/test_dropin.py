@@ -48,6 +48,7 @@ def test_unmodified_trainer_reaches_b200_predictor():
     assert served["segmentation_pipeline.prediction"] == "b200"
     assert served["segmentation_pipeline.models.modular_unet"] == "b200"
     assert served["segmentation_pipeline.evaluators.segmentation_evaluator"] == "b200"
+    assert served["segmentation_pipeline.post_processing"] == "b200"               # remove_holes & co on the device
     # the training step ran (stub predictor + the reference's criterion), the validation branch called our predictor,
     # and on a CPU device that is an error, not a silent fallback
     err = res["error"]
