@@ -519,7 +519,7 @@ def dilate_cross(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def _i32(*tensors):
+def _require_i32(*tensors):
     _require_cuda(*tensors)
     for t in tensors:
         assert t.dtype == torch.int32 and t.is_contiguous()
@@ -527,7 +527,7 @@ def _i32(*tensors):
 
 def dilate_where(dil_src: torch.Tensor, mask: torch.Tensor, pass_src: torch.Tensor) -> torch.Tensor:
     """where(mask & (D != dil_src), D, pass_src) with D = dilate_cross(dil_src), one kernel."""
-    _i32(dil_src, mask, pass_src)
+    _require_i32(dil_src, mask, pass_src)
     assert dil_src.dim() == 3 and dil_src.shape == mask.shape == pass_src.shape
     dst = torch.empty_like(dil_src)
     _LAUNCHES[0] += 1
@@ -538,7 +538,7 @@ def dilate_where(dil_src: torch.Tensor, mask: torch.Tensor, pass_src: torch.Tens
 
 def relabel_masked(img: torch.Tensor, lut: torch.Tensor, comp: torch.Tensor, keep_lut: torch.Tensor) -> torch.Tensor:
     """where(keep_lut[comp], lut[img], 0)."""
-    _i32(img, lut, comp, keep_lut)
+    _require_i32(img, lut, comp, keep_lut)
     assert img.shape == comp.shape
     dst = torch.empty_like(img)
     _LAUNCHES[0] += 1
@@ -548,7 +548,7 @@ def relabel_masked(img: torch.Tensor, lut: torch.Tensor, comp: torch.Tensor, kee
 
 
 def label_equals(src: torch.Tensor, value: int) -> torch.Tensor:
-    _i32(src)
+    _require_i32(src)
     dst = torch.empty_like(src)
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_label_equals(_ptr(src), src.numel(), int(value), _ptr(dst), _stream()), "label_equals")
@@ -556,7 +556,7 @@ def label_equals(src: torch.Tensor, value: int) -> torch.Tensor:
 
 
 def mask_assign(dst: torch.Tensor, mask: torch.Tensor, value: int) -> torch.Tensor:
-    _i32(dst, mask)
+    _require_i32(dst, mask)
     assert dst.shape == mask.shape
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_mask_assign(_ptr(dst), _ptr(mask), dst.numel(), int(value), _stream()), "mask_assign")

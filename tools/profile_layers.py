@@ -17,9 +17,11 @@ def main():
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     only = sys.argv[3] if len(sys.argv) > 3 else None     # run just the ops whose name contains this (for ncu)
-    set_precision("bf16")
+    only = None if only in (None, "", "-") else only
+    precision = sys.argv[4] if len(sys.argv) > 4 else "bf16"      # "fp32": the CUDA-core precision path
+    set_precision(precision)
     model = bench.build_model().cuda()
-    compiled = _engine.compiled_for(model, "bf16", torch.device("cuda"))
+    compiled = _engine.compiled_for(model, precision, torch.device("cuda"))
     if only:
         compiled.calls = [c for c in compiled.calls if only in getattr(c, "name", "")]
         compiled.plan.buffers.setdefault("out", (1, 0))
@@ -43,14 +45,15 @@ def main():
         if isinstance(call, _engine._ConvCall):
             lvl = compiled.plan.buffers[call.src.buf][1]
             ez, ey, ex = z >> lvl, y >> lvl, xx >> lvl
-            taps = 27 if call.mode in (0, 3) else (64 if call.mode == 1 else 8)
-            if call.mode == 1:
+            mode = call.mode if call.tc else (2 if call.transposed else (1 if call.stride == 2 else 0))
+            taps = 27 if mode in (0, 3) else (64 if mode == 1 else 8)
+            if mode == 1:
                 ez, ey, ex = ez // 2, ey // 2, ex // 2
-            if call.mode == 2:
+            if mode == 2:
                 ez, ey, ex = ez * 2, ey * 2, ex * 2
             flop = 2.0 * n * ez * ey * ex * taps * call.src.c * call.cout
             total_flop += flop
-            print(f"{call.name:28s} {['k3','down','up','k3t'][call.mode]:5s} {call.src.c:4d} {call.cout:4d} "
+            print(f"{call.name:28s} {['k3','down','up','k3t'][mode]:5s} {call.src.c:4d} {call.cout:4d} "
                   f"{f'{ez}x{ey}x{ex}':>12s} {ms:8.3f} {flop / ms / 1e9:8.1f}")
         else:
             print(f"{type(call).__name__:28s} {'':5s} {'':4s} {'':4s} {'':>12s} {ms:8.3f}")
