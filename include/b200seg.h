@@ -176,6 +176,15 @@ int b200seg_grid_extract(const float* volume, int32_t c, int32_t w, int32_t h, i
  * patches: fp32 [count][C][p0][p1][p2]; locations_host: HOST int32 [count][6]. */
 int b200seg_overlap_add(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,
                         const int32_t* locations_host, int32_t count, void* stream);
+/* 'hann' mode (the weighted overlap-add of newer torchio GridAggregators, reached through the same
+ * `overlap_mode` argument of PatchPredict, prediction.py:115,134): window_patches multiplies the `count` patches in
+ * place by the separable window ((w0[i] * w1[j]) * w2[k]) before b200seg_overlap_add; divide_separable divides the
+ * accumulator by the summed windows ((s0[i] * s1[j]) * s2[k]) -- separable because the patch grid is a product grid --
+ * before b200seg_finalize is called without counts. */
+int b200seg_window_patches(float* patches, int32_t count, int32_t c, int32_t p0, int32_t p1, int32_t p2, const float* w0,
+                           const float* w1, const float* w2, void* stream);
+int b200seg_divide_separable(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* s0, const float* s1,
+                             const float* s2, void* stream);
 /* 'crop' mode: assign the centre crop of each patch (GridAggregator.crop_batch). */
 int b200seg_overlap_crop(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,
                          const int32_t* locations_host, int32_t count, const int32_t border[3],

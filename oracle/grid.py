@@ -137,6 +137,33 @@ def aggregate_crop(patches: np.ndarray, locations: np.ndarray, spatial_shape: Se
     return out
 
 
+def hann_window_3d(patch_size: Triple) -> np.ndarray:
+    """torchio's ``GridAggregator._get_hann_window`` (torchio >= 0.19, data/inference/aggregator.py; restated from the
+    upstream source, torchio is not in this image): per axis ``torch.hann_window(size + 2, periodic=False)[1:-1]``,
+    multiplied up axis by axis in float32."""
+    window = np.ones((1, 1, 1), dtype=np.float32)
+    for axis, size in enumerate(to_triple(patch_size)):
+        n = np.arange(size + 2, dtype=np.float64)
+        w1d = (0.5 - 0.5 * np.cos(2.0 * np.pi * n / (size + 1))).astype(np.float32)[1:-1]
+        shape = [1, 1, 1]
+        shape[axis] = size
+        window = window * w1d.reshape(shape)
+    return window.astype(np.float32)
+
+
+def aggregate_hann(patches: np.ndarray, locations: np.ndarray, spatial_shape: Sequence[int]
+                   ) -> Tuple[np.ndarray, np.ndarray]:
+    """``GridAggregator.add_batch`` in ``'hann'`` mode: ``output += patch * window``, ``avgmask += window`` per patch
+    in order; returns (sum, mask).  ``get_output_tensor`` divides them like the average mode."""
+    window = hann_window_3d(patches.shape[2:])
+    out = np.zeros((patches.shape[1], *spatial_shape), dtype=patches.dtype)
+    mask = np.zeros_like(out)
+    for patch, (i0, j0, k0, i1, j1, k1) in zip(patches, locations):
+        out[:, i0:i1, j0:j1, k0:k1] += patch * window
+        mask[:, i0:i1, j0:j1, k0:k1] += window
+    return out, mask
+
+
 def finalize(out: np.ndarray, cnt: Optional[np.ndarray], patch_overlap: Triple, volume_padded: bool) -> np.ndarray:
     """``GridAggregator.get_output_tensor``: ``true_divide(out, cnt)`` in average mode, then crop the
     ``overlap // 2`` border if the sampler padded the volume."""
@@ -167,4 +194,7 @@ def sliding_window(volume: np.ndarray, model_fn, patch_size: Triple, patch_overl
     if overlap_mode == "crop":
         out = aggregate_crop(y, locations, spatial, patch_overlap, padding_mode is not None)
         return finalize(out, None, patch_overlap, padding_mode is not None)
-    raise ValueError(f'Overlap mode must be "crop" or "average" but "{overlap_mode}" was passed')
+    if overlap_mode == "hann":
+        out, mask = aggregate_hann(y, locations, spatial)
+        return finalize(out, mask, patch_overlap, padding_mode is not None)
+    raise ValueError(f'Overlap mode must be "crop", "average" or "hann" but "{overlap_mode}" was passed')

@@ -76,6 +76,10 @@ _SIGNATURES = {
                                                c_int32, c_void_p, c_void_p, c_void_p]),
     "b200seg_ccl3d_roots": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                       c_int32, c_void_p, c_void_p]),
+    "b200seg_window_patches": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
+    "b200seg_divide_separable": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                           c_void_p]),
     "b200seg_relabel_lut": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200seg_dilate_cross": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200seg_dilate_where": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -353,6 +357,30 @@ def overlap_add(out: torch.Tensor, patches: torch.Tensor, locations: Sequence[Se
     _LAUNCHES[0] += (len(locations) + 63) // 64
     _check(load_library().b200seg_overlap_add(_ptr(out), c, pw, ph, pd, _ptr(patches), _i32(flat), len(locations),
                                               _stream()), "overlap_add")
+
+
+def window_patches(patches: torch.Tensor, windows: Sequence[torch.Tensor], count: Optional[int] = None) -> None:
+    """patches (B, C, p0, p1, p2) fp32 *= outer product of the three per-axis fp32 windows, in place ('hann' mode)."""
+    _require_cuda(patches, *windows)
+    assert patches.dtype == torch.float32 and patches.is_contiguous() and patches.dim() == 5
+    b, c, p0, p1, p2 = patches.shape
+    for w, size in zip(windows, (p0, p1, p2)):
+        assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == size
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_window_patches(_ptr(patches), b if count is None else count, c, p0, p1, p2,
+                                                 _ptr(windows[0]), _ptr(windows[1]), _ptr(windows[2]), _stream()),
+           "window_patches")
+
+
+def divide_separable(out: torch.Tensor, sums: Sequence[torch.Tensor]) -> None:
+    """out (C, PW, PH, PD) fp32 /= outer product of the three per-axis fp32 vectors, in place ('hann' mode)."""
+    _require_cuda(out, *sums)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.dim() == 4
+    for v, size in zip(sums, out.shape[1:]):
+        assert v.dtype == torch.float32 and v.is_contiguous() and v.numel() == size
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_divide_separable(_ptr(out), *out.shape, _ptr(sums[0]), _ptr(sums[1]), _ptr(sums[2]),
+                                                   _stream()), "divide_separable")
 
 
 def overlap_crop(out: torch.Tensor, patches: torch.Tensor, locations: Sequence[Sequence[int]],

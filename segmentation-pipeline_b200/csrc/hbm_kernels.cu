@@ -515,6 +515,40 @@ overlap_add_rows_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, 
     }
 }
 
+// 'hann' mode (torchio >= 0.19 GridAggregator): every patch is multiplied by the separable Hann window before the
+// overlap-add and the sum is divided by the summed windows.  The window product is built the way torchio builds its
+// 3-D window, ((w0[i] * w1[j]) * w2[k]), so the weighted values carry the same rounding.
+__global__ void __launch_bounds__(kThreads)
+window_patches_kernel(float* __restrict__ patches, int p0, int p1, int p2, const float* __restrict__ w0,
+                      const float* __restrict__ w1, const float* __restrict__ w2, long long total4) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total4) return;
+    const int k = static_cast<int>(t % (p2 / 4)) * 4;
+    long long r = t / (p2 / 4);
+    const int j = static_cast<int>(r % p1);
+    const int i = static_cast<int>((r / p1) % p0);
+    const float wij = __ldg(w0 + i) * __ldg(w1 + j);
+    float4 v = reinterpret_cast<float4*>(patches)[t];
+    v.x *= wij * __ldg(w2 + k);
+    v.y *= wij * __ldg(w2 + k + 1);
+    v.z *= wij * __ldg(w2 + k + 2);
+    v.w *= wij * __ldg(w2 + k + 3);
+    reinterpret_cast<float4*>(patches)[t] = v;
+}
+
+// out[c][i][j][k] /= (s0[i] * s1[j]) * s2[k]: the summed windows of a product grid are separable
+__global__ void __launch_bounds__(kThreads)
+divide_separable_kernel(float* __restrict__ out, int PW, int PH, int PD, const float* __restrict__ s0,
+                        const float* __restrict__ s1, const float* __restrict__ s2, long long total) {
+    long long t = blockIdx.x * 1LL * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const int k = static_cast<int>(t % PD);
+    long long r = t / PD;
+    const int j = static_cast<int>(r % PH);
+    const int i = static_cast<int>((r / PH) % PW);
+    out[t] = out[t] / ((__ldg(s0 + i) * __ldg(s1 + j)) * __ldg(s2 + k));
+}
+
 // 'crop' mode: every patch assigns the centre crop of itself; patches are processed in order, later wins.
 __global__ void __launch_bounds__(kThreads)
 overlap_crop_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, const float* __restrict__ patches,
@@ -1015,6 +1049,27 @@ int b200seg_overlap_add(float* out, int32_t c, int32_t pw, int32_t ph, int32_t p
         if (rc) return rc;
     }
     return B200SEG_OK;
+}
+
+int b200seg_window_patches(float* patches, int32_t count, int32_t c, int32_t p0, int32_t p1, int32_t p2, const float* w0,
+                           const float* w1, const float* w2, void* stream) {
+    B200SEG_CHECK_ARG(patches && w0 && w1 && w2 && count > 0 && c > 0 && p0 > 0 && p1 > 0 && p2 > 0,
+                      "window_patches: bad arguments");
+    B200SEG_CHECK_ARG(p2 % 4 == 0 && (reinterpret_cast<uintptr_t>(patches) & 15) == 0,
+                      "window_patches: the last patch axis must be a multiple of 4 and the buffer 16-byte aligned");
+    const long long total4 = 1LL * count * c * p0 * p1 * (p2 / 4);
+    window_patches_kernel<<<blocks_for(total4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(patches, p0, p1, p2, w0,
+                                                                                                 w1, w2, total4);
+    return check_launch("window_patches");
+}
+
+int b200seg_divide_separable(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* s0, const float* s1,
+                             const float* s2, void* stream) {
+    B200SEG_CHECK_ARG(out && s0 && s1 && s2 && c > 0 && pw > 0 && ph > 0 && pd > 0, "divide_separable: bad arguments");
+    const long long total = 1LL * c * pw * ph * pd;
+    divide_separable_kernel<<<blocks_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(out, pw, ph, pd, s0, s1,
+                                                                                                  s2, total);
+    return check_launch("divide_separable");
 }
 
 int b200seg_overlap_crop(float* out, int32_t c, int32_t pw, int32_t ph, int32_t pd, const float* patches,

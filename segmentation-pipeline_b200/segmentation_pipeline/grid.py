@@ -66,6 +66,24 @@ class PatchGrid:
             counts.append(c)
         return counts
 
+    def hann_windows(self):
+        """Per-axis window of torchio's 'hann' aggregation: ``torch.hann_window(size + 2, periodic=False)[1:-1]`` (the
+        two zero end points dropped), fp32.  The 3-D window is their outer product."""
+        import torch
+        return [torch.hann_window(p + 2, periodic=False)[1:-1].contiguous() for p in self.patch_size]
+
+    def axis_window_sums(self):
+        """Summed window per index along each axis (fp32, patches added in ascending start order); the 3-D sum of
+        windows over the product grid is the outer product of the three."""
+        import torch
+        sums = []
+        for size, patch, starts, win in zip(self.padded_shape, self.patch_size, self.axis_starts, self.hann_windows()):
+            acc = torch.zeros(size, dtype=torch.float32)
+            for s0 in starts:
+                acc[s0:s0 + patch] += win
+            sums.append(acc)
+        return sums
+
     @property
     def pad_mode_code(self) -> int:
         """0 none, 1 'edge' (clamp), 2 constant -- the modes b200seg_grid_extract implements."""

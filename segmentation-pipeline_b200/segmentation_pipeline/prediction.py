@@ -167,8 +167,8 @@ class PatchPredict(Predictor):
 
     def _predict_volume(self, model, volume, want_probs, want_labels):
         lib = _lib()
-        if self.overlap_mode not in ("average", "crop"):
-            raise ValueError(f'Overlap mode must be "crop" or "average" but "{self.overlap_mode}" was passed')
+        if self.overlap_mode not in ("average", "crop", "hann"):
+            raise ValueError(f'Overlap mode must be "crop", "average" or "hann" but "{self.overlap_mode}" was passed')
         if not volume.is_cuda:
             raise RuntimeError("predict_volume expects the volume on the CUDA device")
         in_dtype = volume.dtype          # 'auto' precision follows the caller's dtype (a bf16 volume -> bf16 path)
@@ -192,6 +192,7 @@ class PatchPredict(Predictor):
             fit = max(int(0.25 * free // max(per_patch, 1)), 1)
             batch_size = max(batch_size, min(DEVICE_BATCH[0], fit, len(grid.locations)))
         out = None
+        windows = [w.to(device) for w in grid.hann_windows()] if self.overlap_mode == "hann" else None
         for locations in grid.batches(batch_size):
             b = len(locations)
             if native:
@@ -213,11 +214,19 @@ class PatchPredict(Predictor):
                 out = torch.zeros((y.shape[1], *grid.padded_shape), dtype=torch.float32, device=device)
             if self.overlap_mode == "average":
                 lib.overlap_add(out, y, locations)
+            elif self.overlap_mode == "hann":
+                # weighted overlap-add: patch * window, then the same owner-computes gather
+                if p2 % 4:
+                    raise NotImplementedError("'hann' aggregation needs a patch size whose last axis is a multiple of 4")
+                lib.window_patches(y, windows, count=b)
+                lib.overlap_add(out, y, locations)
             else:
                 lib.overlap_crop(out, y, locations, [o // 2 for o in grid.patch_overlap], grid.volume_padded)
         counts = None
         if self.overlap_mode == "average":
             counts = [torch.tensor(c, dtype=torch.int32, device=device) for c in grid.axis_counts()]
+        elif self.overlap_mode == "hann":
+            lib.divide_separable(out, [v.to(device) for v in grid.axis_window_sums()])
         w, h, d = grid.spatial_shape
         probs = torch.empty((out.shape[0], w, h, d), dtype=torch.float32, device=device) if want_probs else None
         labels = torch.empty((w, h, d), dtype=torch.uint8, device=device) \

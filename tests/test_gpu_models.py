@@ -264,7 +264,8 @@ def _small_model():
 
 
 @pytest.mark.parametrize("device_batch", [0, 48])     # literal patch_batch_size (ragged batches) / regrouped on the device
-@pytest.mark.parametrize("padding_mode,overlap_mode", [(None, "average"), ("edge", "average"), ("edge", "crop")])
+@pytest.mark.parametrize("padding_mode,overlap_mode", [(None, "average"), ("edge", "average"), ("edge", "crop"),
+                                                       (None, "hann"), ("edge", "hann")])
 def test_patch_predict_matches_oracle_sliding_window(padding_mode, overlap_mode, device_batch, monkeypatch):
     from segmentation_pipeline import _tio, prediction
     from segmentation_pipeline.models import set_precision

@@ -128,3 +128,27 @@ def test_sliding_window_matches_brute_force_vectors():
                                    case["patch"], case["overlap"], case["padding_mode"], case["overlap_mode"],
                                    patch_batch_size=3)
         np.testing.assert_array_equal(res[0], np.array(case["output"], np.float32))
+
+
+@pytest.mark.parametrize("padding_mode", [None, "edge", 0.0])
+def test_hann_mode_is_a_partition_of_unity_and_separable(padding_mode):
+    """'hann' aggregation (newer torchio): an identity model reproduces the volume; the summed 3-D windows of the
+    product grid equal the outer product of the per-axis sums the device path divides by."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "segmentation-pipeline_b200"))
+    from segmentation_pipeline.grid import PatchGrid
+    rng = np.random.default_rng(4)
+    vol = rng.normal(size=(2, 20, 24, 32)).astype(np.float32)
+    out = grid.sliding_window(vol, lambda p: p, (8, 12, 16), (4, 4, 8), padding_mode, "hann", 5)
+    assert out.shape == vol.shape and np.abs(out - vol).max() <= 2e-6
+    pg = PatchGrid(vol.shape[1:], (8, 12, 16), (4, 4, 8), padding_mode)
+    ones = np.ones((len(pg.locations), 1, 8, 12, 16), dtype=np.float32)
+    _, mask = grid.aggregate_hann(ones, np.array(pg.locations), pg.padded_shape)
+    s0, s1, s2 = (v.numpy() for v in pg.axis_window_sums())
+    sep = (s0[:, None, None] * s1[None, :, None]) * s2[None, None, :]
+    assert np.abs(mask[0] - sep).max() <= 1e-6 * sep.max()
+    assert mask.min() > 0
+    w = grid.hann_window_3d((8, 12, 16))
+    ws = pg.hann_windows()
+    w3 = ((ws[0][:, None, None] * ws[1][None, :, None]) * ws[2][None, None, :]).numpy()
+    assert np.abs(w - w3).max() <= 3e-7
