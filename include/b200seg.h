@@ -271,6 +271,35 @@ int b200seg_hybrid_loss_backward(const float* prediction, const float* target, c
                                  int64_t voxels, float dice_weight, const float* class_weights, int32_t square_dice,
                                  const float* grad_loss, float* grad_prediction, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ training step
+ * The device side of the reference's trainer step (segmentation_trainer.py:162-180: model.train(), forward, loss,
+ * backward; BatchNorm3d with batch statistics, components.py:53).  fp32 blocked views only.  Forward convolutions and
+ * data gradients are b200seg_conv3d_direct launches (a dgrad is a convolution with re-arranged weights); these entry
+ * points add the rest.  All reductions are deterministic (per-block partials summed in a fixed order).
+ *   train_scratch_bytes  size of the double scratch the reductions need for `channels` channels
+ *   channel_moments      mean[c], var[c] (biased) over (N, Z, Y, X)               -- nn.BatchNorm3d training statistics
+ *   affine_act           dst = act(scale[c] * src + shift[c]) (+ residual)        -- BN apply + activation + res add
+ *   bn_backward          g = dy * act'(scale*z+shift); sum_g[c] = sum g (= d beta), sum_gx[c] = sum g*xhat (= d gamma),
+ *                        dz = scale[c] * (g - sum_g/M - xhat * sum_gx/M) with xhat = (z - mean) * rstd; has_norm == 0:
+ *                        dz = g (activation only; sum_g is then the bias gradient)
+ *   softmax_backward     dlogits = p * (dp - sum_c dp_c p_c) (softmax != 0) or dp, fp32 NCDHW -> blocked view
+ *   wgrad                grad[tap][a_ch][b_ch] = sum_{n,pos} A[a_ch](pos) * B[b_ch](stride*pos + tap - pad), zero outside
+ *                        B; tap = (tz*k + ty)*k + tx, rows padded to multiples of 8.  3x3x3 layers: A = dz, B = x,
+ *                        stride 1, pad 1; BlurConv3d: A = dz, B = x, k 4, stride 2, pad 1; BlurConvTranspose3d: A = x,
+ *                        B = dy, k 4, stride 2, pad 1.  scratch: wgrad_scratch_floats() floats. */
+int64_t b200seg_train_scratch_bytes(int32_t channels);
+int b200seg_channel_moments(b200seg_view x, void* scratch, float* mean, float* var, void* stream);
+int b200seg_affine_act(b200seg_view src, const float* scale, const float* shift, const float* slope,
+                       b200seg_view residual, b200seg_view dst, void* stream);
+int b200seg_bn_backward(b200seg_view dy, b200seg_view z, const float* scale, const float* shift, const float* slope,
+                        const float* mean, const float* rstd, int32_t has_norm, void* scratch, float* sum_g,
+                        float* sum_gx, b200seg_view dz, void* stream);
+int b200seg_softmax_backward(const float* probs, const float* dprobs, int32_t n, int32_t c, int32_t softmax,
+                             b200seg_view dst, void* stream);
+int64_t b200seg_wgrad_scratch_floats(int32_t a_channels, int32_t b_channels, int32_t ksize);
+int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int32_t stride, int32_t pad, float* scratch,
+                  float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,11 +102,18 @@ def _activation(x, act: Optional[str], slope: float = 0.01):
     raise ValueError(act)
 
 
-def _norm(x, sd, prefix, norm: Optional[str]):
+def batch_norm_train(x, sd: SD, prefix: str, eps: float = BN_EPS, momentum: float = 0.1):
+    """nn.BatchNorm3d in TRAINING mode (models/components.py:53 under ``model.train()``,
+    segmentation_trainer.py:162): batch statistics; ``sd``'s running_mean / running_var are updated in place."""
+    return F.batch_norm(x, sd[prefix + "running_mean"], sd[prefix + "running_var"], sd.get(prefix + "weight"),
+                        sd.get(prefix + "bias"), training=True, momentum=momentum, eps=eps)
+
+
+def _norm(x, sd, prefix, norm: Optional[str], training: bool = False):
     if norm is None or norm == "none":
         return x
     if norm == "batch":
-        return batch_norm_eval(x, sd, prefix)
+        return batch_norm_train(x, sd, prefix) if training else batch_norm_eval(x, sd, prefix)
     if norm == "instance":
         # nn.InstanceNorm3d defaults: affine=False, track_running_stats=False
         return F.instance_norm(x, weight=sd.get(prefix + "weight"), bias=sd.get(prefix + "bias"), eps=BN_EPS)
@@ -127,7 +134,7 @@ def block3d(x, sd: SD, prefix: str, cfg: dict):
             x = ws_conv3d(x, w, padding=1)
         else:
             x = F.conv3d(_q(x), _q(w), b, padding=1)
-        x = _norm(x, sd, f"{prefix}layers.norm{i}.", cfg.get("norm", "batch"))
+        x = _norm(x, sd, f"{prefix}layers.norm{i}.", cfg.get("norm", "batch"), cfg.get("bn_training", False))
         x = _activation(x, cfg.get("act", "relu"), cfg.get("slope", 0.01))
         if not (residual and i == n - 1):
             x = _q(x)          # stored activation (the last one is stored after the residual add)

@@ -76,6 +76,14 @@ _SIGNATURES = {
                                                c_int32, c_void_p, c_void_p, c_void_p]),
     "b200seg_ccl3d_roots": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                       c_int32, c_void_p, c_void_p]),
+    "b200seg_train_scratch_bytes": (c_int64, [c_int32]),
+    "b200seg_channel_moments": (c_int32, [View, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200seg_affine_act": (c_int32, [View, c_void_p, c_void_p, c_void_p, View, View, c_void_p]),
+    "b200seg_bn_backward": (c_int32, [View, View, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                      c_void_p, c_void_p, View, c_void_p]),
+    "b200seg_softmax_backward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, View, c_void_p]),
+    "b200seg_wgrad_scratch_floats": (c_int64, [c_int32, c_int32, c_int32]),
+    "b200seg_wgrad": (c_int32, [View, View, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200seg_window_patches": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                          c_void_p, c_void_p]),
     "b200seg_divide_separable": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
@@ -589,3 +597,60 @@ def mask_assign(dst: torch.Tensor, mask: torch.Tensor, value: int) -> torch.Tens
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_mask_assign(_ptr(dst), _ptr(mask), dst.numel(), int(value), _stream()), "mask_assign")
     return dst
+
+
+# ------------------------------------------------------------------------------------------------- training step
+def _train_scratch(channels: int, device) -> torch.Tensor:
+    return torch.empty(load_library().b200seg_train_scratch_bytes(int(channels)) // 8, dtype=torch.float64, device=device)
+
+
+def channel_moments(x: View, channels: int, device):
+    """(mean, biased var) fp32 vectors of length round_up(channels, 8) over (N, Z, Y, X) of a blocked fp32 view."""
+    cpad = (channels + 7) // 8 * 8
+    mean = torch.empty(cpad, dtype=torch.float32, device=device)
+    var = torch.empty(cpad, dtype=torch.float32, device=device)
+    scratch = _train_scratch(channels, device)
+    _LAUNCHES[0] += 2
+    _check(load_library().b200seg_channel_moments(x, _ptr(scratch), _ptr(mean), _ptr(var), _stream()), "channel_moments")
+    return mean, var
+
+
+def affine_act(src: View, scale: torch.Tensor, shift: torch.Tensor, slope: torch.Tensor, dst: View,
+               residual: View = NULL_VIEW) -> None:
+    _require_cuda(scale, shift, slope)
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_affine_act(src, _ptr(scale), _ptr(shift), _ptr(slope), residual, dst, _stream()),
+           "affine_act")
+
+
+def bn_backward(dy: View, z: View, scale, shift, slope, mean, rstd, has_norm: bool, dz: View, channels: int, device):
+    """-> (sum_g, sum_gx) fp32 vectors (d beta, d gamma); writes dz."""
+    _require_cuda(scale, shift, slope, mean, rstd)
+    cpad = (channels + 7) // 8 * 8
+    sum_g = torch.empty(cpad, dtype=torch.float32, device=device)
+    sum_gx = torch.empty(cpad, dtype=torch.float32, device=device)
+    scratch = _train_scratch(channels, device)
+    _LAUNCHES[0] += 3
+    _check(load_library().b200seg_bn_backward(dy, z, _ptr(scale), _ptr(shift), _ptr(slope), _ptr(mean), _ptr(rstd),
+                                              1 if has_norm else 0, _ptr(scratch), _ptr(sum_g), _ptr(sum_gx), dz,
+                                              _stream()), "bn_backward")
+    return sum_g, sum_gx
+
+
+def softmax_backward(probs: torch.Tensor, dprobs: torch.Tensor, softmax: bool, dst: View) -> None:
+    _require_cuda(probs, dprobs)
+    assert probs.dtype == torch.float32 and dprobs.dtype == torch.float32 and probs.shape == dprobs.shape
+    assert probs.is_contiguous() and dprobs.is_contiguous()
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_softmax_backward(_ptr(probs), _ptr(dprobs), probs.shape[0], probs.shape[1],
+                                                   1 if softmax else 0, dst, _stream()), "softmax_backward")
+
+
+def wgrad(a: View, b: View, ksize: int, stride: int, pad: int, device) -> torch.Tensor:
+    """-> fp32 (k^3, round_up(a.c, 8), round_up(b.c, 8)): sum over positions of A[a](pos) * B[b](stride*pos + tap - pad)."""
+    lib = load_library()
+    scratch = torch.empty(lib.b200seg_wgrad_scratch_floats(a.c, b.c, ksize), dtype=torch.float32, device=device)
+    grad = torch.empty((ksize ** 3, (a.c + 7) // 8 * 8, (b.c + 7) // 8 * 8), dtype=torch.float32, device=device)
+    _LAUNCHES[0] += 2
+    _check(lib.b200seg_wgrad(a, b, ksize, stride, pad, _ptr(scratch), _ptr(grad), _stream()), "wgrad")
+    return grad

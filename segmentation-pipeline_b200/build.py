@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200seg.so")
-SOURCES = ["common.cu", "hbm_kernels.cu", "norm_kernels.cu", "loss_kernels.cu", "ccl_kernels.cu", "conv_direct.cu", "conv_tc.cu"]
+SOURCES = ["common.cu", "hbm_kernels.cu", "norm_kernels.cu", "loss_kernels.cu", "ccl_kernels.cu", "train_kernels.cu", "conv_direct.cu", "conv_tc.cu"]
 HEADERS = ["common.cuh", "ptx_sm100.cuh", os.path.join("..", "..", "include", "b200seg.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -1,0 +1,424 @@
+// Training-step kernels (fp32, blocked activations) -- the device side of the reference's trainer step,
+// segmentation_trainer.py:162-180: model.train() forward (BatchNorm3d with BATCH statistics), loss, backward.
+// The forward convolutions and the data gradients (dgrad) are b200seg_conv3d_direct launches (a dgrad IS a convolution
+// with re-arranged weights: flipped taps for the 3x3x3 layers, the transposed geometry for the strided ones and vice
+// versa); this file holds what is new for training:
+//   wgrad            G[tap][a][b] = sum over (n, pos) of A[a](pos) * B[b](stride * pos + tap - pad)
+//   channel_moments  per-channel mean / biased variance over (N, Z, Y, X)            (BatchNorm3d training statistics)
+//   affine_act       act(scale * z + shift) (+ residual)                             (BN apply + activation + res add)
+//   bn_backward_*    the two reductions and the data gradient of BN + activation
+//   softmax_backward dlogits = p * (dp - sum_c dp_c p_c), NCDHW -> blocked
+// All reductions are two-stage with per-block partials summed in a fixed order (deterministic, no atomics); the
+// per-channel sums are carried in double.
+#include "common.cuh"
+
+namespace b200seg {
+
+constexpr int kTrThreads = 256;
+
+__device__ __forceinline__ Vec8 ldv(const DView& v, long long idx) { return load_vec8<float>(v.data, idx); }
+
+// ------------------------------------------------------------------------------------------- two-sum reductions
+// MODE 0: (x, x^2) of view a.   MODE 1: (g, g * xhat) with g = dy * act'(scale * z + shift), xhat = (z - mean) * rstd;
+// a = dy, b = z.
+struct ReduceParams {
+    const float* scale;
+    const float* shift;
+    const float* slope;
+    const float* mean;
+    const float* rstd;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTrThreads)
+chan_reduce_partial_kernel(DView a, DView b, ReduceParams p, double* __restrict__ partial, int nblk) {
+    __shared__ double red[kTrThreads / 32][16];
+    const int cc = blockIdx.y, blk = blockIdx.x;
+    const long long total = 1LL * a.n * a.chunk_stride;
+    const long long per = (total + nblk - 1) / nblk;
+    const long long t0 = blk * per, t1 = min(t0 + per, total);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    float sc[8], sh[8], sl[8], mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = __ldg(p.scale + cc * 8 + j);
+            sh[j] = __ldg(p.shift + cc * 8 + j);
+            sl[j] = __ldg(p.slope + cc * 8 + j);
+            mu[j] = __ldg(p.mean + cc * 8 + j);
+            rs[j] = __ldg(p.rstd + cc * 8 + j);
+        }
+    }
+    for (long long t = t0 + threadIdx.x; t < t1; t += kTrThreads) {
+        const long long n = t / a.chunk_stride, v = t - n * a.chunk_stride;
+        const Vec8 x = ldv(a, n * a.sample_stride + (a.c8_off + cc) * a.chunk_stride + v);
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += x.v[j];
+                s2[j] = fmaf(x.v[j], x.v[j], s2[j]);
+            }
+        } else {
+            const Vec8 z = ldv(b, n * b.sample_stride + (b.c8_off + cc) * b.chunk_stride + v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float y = fmaf(z.v[j], sc[j], sh[j]);
+                const float g = y > 0.f ? x.v[j] : x.v[j] * sl[j];
+                s1[j] += g;
+                s2[j] = fmaf(g, (z.v[j] - mu[j]) * rs[j], s2[j]);
+            }
+        }
+    }
+    double d[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        d[j] = s1[j];
+        d[8 + j] = s2[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) red[warp][j] = d[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double s = 0.0;
+        for (int w = 0; w < kTrThreads / 32; ++w) s += red[w][threadIdx.x];
+        partial[(static_cast<long long>(cc) * nblk + blk) * 16 + threadIdx.x] = s;
+    }
+}
+
+// moments != 0: out0 = s1 / count (mean), out1 = s2 / count - mean^2 (biased variance, >= 0); else the raw sums
+__global__ void chan_reduce_finish_kernel(const double* __restrict__ partial, int nblk, int channels, double count,
+                                          int moments, float* __restrict__ out0, float* __restrict__ out1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const int cc = c / 8, j = c % 8;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        s1 += partial[(static_cast<long long>(cc) * nblk + b) * 16 + j];
+        s2 += partial[(static_cast<long long>(cc) * nblk + b) * 16 + 8 + j];
+    }
+    if (moments) {
+        const double mean = s1 / count;
+        double var = s2 / count - mean * mean;
+        out0[c] = static_cast<float>(mean);
+        out1[c] = static_cast<float>(var > 0.0 ? var : 0.0);
+    } else {
+        out0[c] = static_cast<float>(s1);
+        out1[c] = static_cast<float>(s2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- elementwise
+__global__ void __launch_bounds__(kTrThreads)
+affine_act_kernel(DView src, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ slope, DView residual, DView dst, int c8n, long long total) {
+    const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long v = t % src.chunk_stride;
+    const long long r = t / src.chunk_stride;
+    const int cc = static_cast<int>(r % c8n);
+    const long long n = r / c8n;
+    Vec8 a = ldv(src, n * src.sample_stride + (src.c8_off + cc) * src.chunk_stride + v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float y = fmaf(a.v[j], __ldg(scale + cc * 8 + j), __ldg(shift + cc * 8 + j));
+        a.v[j] = y > 0.f ? y : y * __ldg(slope + cc * 8 + j);
+    }
+    if (residual.data != nullptr) {
+        const Vec8 q = ldv(residual, n * residual.sample_stride + (residual.c8_off + cc) * residual.chunk_stride + v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a.v[j] += q.v[j];
+    }
+    store_vec8<float>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, a);
+}
+
+// dz = has_norm ? scale * (g - c1 - xhat * c2) : g,   g = dy * act'(scale * z + shift); c1 = sum g / M, c2 = sum g xhat / M
+__global__ void __launch_bounds__(kTrThreads)
+bn_backward_apply_kernel(DView dy, DView z, ReduceParams p, const float* __restrict__ sum_g,
+                         const float* __restrict__ sum_gx, float inv_count, int has_norm, DView dst, int c8n,
+                         long long total) {
+    const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long v = t % dy.chunk_stride;
+    const long long r = t / dy.chunk_stride;
+    const int cc = static_cast<int>(r % c8n);
+    const long long n = r / c8n;
+    const Vec8 d = ldv(dy, n * dy.sample_stride + (dy.c8_off + cc) * dy.chunk_stride + v);
+    const Vec8 zz = ldv(z, n * z.sample_stride + (z.c8_off + cc) * z.chunk_stride + v);
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cc * 8 + j;
+        const float sc = __ldg(p.scale + c);
+        const float y = fmaf(zz.v[j], sc, __ldg(p.shift + c));
+        const float g = y > 0.f ? d.v[j] : d.v[j] * __ldg(p.slope + c);
+        if (has_norm) {
+            const float xh = (zz.v[j] - __ldg(p.mean + c)) * __ldg(p.rstd + c);
+            o.v[j] = sc * (g - __ldg(sum_g + c) * inv_count - xh * (__ldg(sum_gx + c) * inv_count));
+        } else {
+            o.v[j] = g;
+        }
+    }
+    store_vec8<float>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, o);
+}
+
+// probs / dprobs: fp32 NCDHW [N][C][vox]; dst: blocked view with C channels (padding channels written as 0)
+__global__ void __launch_bounds__(kTrThreads)
+softmax_backward_kernel(const float* __restrict__ probs, const float* __restrict__ dprobs, int C, long long vox,
+                        int softmax, DView dst, long long total) {
+    const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long n = t / vox, v = t - n * vox;
+    const float* pp = probs + n * C * vox + v;
+    const float* dp = dprobs + n * C * vox + v;
+    float dot = 0.f;
+    if (softmax)
+        for (int c = 0; c < C; ++c) dot = fmaf(__ldg(dp + c * vox), __ldg(pp + c * vox), dot);
+    const int c8n = (C + 7) / 8;
+    for (int cc = 0; cc < c8n; ++cc) {
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cc * 8 + j;
+            float val = 0.f;
+            if (c < C) val = softmax ? __ldg(pp + c * vox) * (__ldg(dp + c * vox) - dot) : __ldg(dp + c * vox);
+            o.v[j] = val;
+        }
+        store_vec8<float>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- wgrad
+// One block = the K*K in-plane taps of one tz (one warp per tap) for one (A chunk, B chunk) pair; lanes = 32
+// consecutive positions of the flattened (y, x) plane of the A grid, so both operand loads of a warp are contiguous
+// 1 KB segments (A) / contiguous up to row wraps (B); the K*K warps of a block read the same A vectors and
+// neighbouring B vectors, which L1 serves.  Each thread carries the 8 x 8 outer-product accumulator of its tap.
+struct WgradGeom {
+    int stride, pad;
+    int pz, py, px;        // A (position) grid
+    int plane_blocks;      // ceil(py * px / 32)
+    long long items;       // n * pz * plane_blocks
+    int cb8n;              // B chunks
+    float inv_px;
+};
+
+template <int K>
+__global__ void __launch_bounds__(K * K * 32)
+wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int ty = warp / K, tx = warp % K, tz = blockIdx.z;
+    const int ca = blockIdx.y / g.cb8n, cb = blockIdx.y % g.cb8n;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int plane = g.py * g.px;
+    for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const int pb = static_cast<int>(item % g.plane_blocks);
+        const long long r = item / g.plane_blocks;
+        const int z = static_cast<int>(r % g.pz);
+        const int n = static_cast<int>(r / g.pz);
+        const int bz = g.stride * z + tz - g.pad;
+        if (bz < 0 || bz >= B.z) continue;       // block-uniform
+        const int p = pb * 32 + lane;
+        if (p >= plane) continue;
+        int y = __float2int_rd((p + 0.5f) * g.inv_px);
+        if (y * g.px > p) --y;
+        if ((y + 1) * g.px <= p) ++y;
+        const int x = p - y * g.px;
+        const int by = g.stride * y + ty - g.pad, bx = g.stride * x + tx - g.pad;
+        if (by < 0 || by >= B.y || bx < 0 || bx >= B.x) continue;
+        const Vec8 a = ldv(A, vox_index(A, n, ca, z, y, x));
+        const Vec8 b = ldv(B, vox_index(B, n, cb, bz, by, bx));
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a.v[i], b.v[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+    if (lane == 0) {
+        const int tap = (tz * K + ty) * K + tx;
+        float* dst = partial + ((static_cast<long long>(blockIdx.x) * (K * K * K) + tap) * gridDim.y + blockIdx.y) * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[i * 8 + j] = acc[i][j];
+    }
+}
+
+// G[tap][ca * 8 + i][cb * 8 + j] = sum over slices, in slice order
+__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int slices, int taps, int pairs, int cb8n,
+                                    float* __restrict__ grad, long long total) {
+    const long long t = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int e = static_cast<int>(t % 64);
+    const long long r = t / 64;
+    const int pair = static_cast<int>(r % pairs);
+    const int tap = static_cast<int>(r / pairs);
+    float s = 0.f;
+    for (int sl = 0; sl < slices; ++sl) s += partial[((static_cast<long long>(sl) * taps + tap) * pairs + pair) * 64 + e];
+    const int ca = pair / cb8n, cb = pair % cb8n;
+    const int ca8n = pairs / cb8n;
+    grad[(static_cast<long long>(tap) * ca8n * 8 + ca * 8 + e / 8) * (cb8n * 8) + cb * 8 + e % 8] = s;
+}
+
+static int check_f32_view(const b200seg_view& v, const char* name) {
+    int rc = validate_view(v, name);
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(v.dtype == B200SEG_F32, "%s: the training kernels take fp32 views", name);
+    return B200SEG_OK;
+}
+
+static bool same_extent(const b200seg_view& a, const b200seg_view& b) {
+    return a.n == b.n && a.z == b.z && a.y == b.y && a.x == b.x && (a.c + 7) / 8 == (b.c + 7) / 8;
+}
+
+static int reduce_blocks(const b200seg_view& v) {
+    const long long total = 1LL * v.n * v.z * v.y * v.x;
+    long long nblk = (total + 4 * kTrThreads - 1) / (4 * kTrThreads);
+    return static_cast<int>(nblk < 1 ? 1 : (nblk > 256 ? 256 : nblk));
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+extern "C" int64_t b200seg_train_scratch_bytes(int32_t channels) {
+    // doubles: [c8][256 blocks][16]
+    return static_cast<int64_t>((channels + 7) / 8) * 256 * 16 * 8;
+}
+
+extern "C" int b200seg_channel_moments(b200seg_view x, void* scratch, float* mean, float* var, void* stream) {
+    int rc = check_f32_view(x, "channel_moments x");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(scratch && mean && var, "channel_moments: null argument");
+    const int c8n = (x.c + 7) / 8, nblk = reduce_blocks(x);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DView dx = make_dview(x);
+    ReduceParams p{};
+    chan_reduce_partial_kernel<0><<<dim3(nblk, c8n), kTrThreads, 0, s>>>(dx, dx, p, static_cast<double*>(scratch), nblk);
+    const double count = 1.0 * x.n * x.z * x.y * x.x;
+    chan_reduce_finish_kernel<<<(c8n * 8 + 127) / 128, 128, 0, s>>>(static_cast<const double*>(scratch), nblk, c8n * 8, count,
+                                                                   1, mean, var);
+    return check_launch("channel_moments");
+}
+
+extern "C" int b200seg_affine_act(b200seg_view src, const float* scale, const float* shift, const float* slope,
+                                  b200seg_view residual, b200seg_view dst, void* stream) {
+    int rc = check_f32_view(src, "affine_act src");
+    if (rc) return rc;
+    rc = check_f32_view(dst, "affine_act dst");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(scale && shift && slope && same_extent(src, dst), "affine_act: bad arguments");
+    DView dr = null_dview();
+    if (residual.data != nullptr) {
+        rc = check_f32_view(residual, "affine_act residual");
+        if (rc) return rc;
+        B200SEG_CHECK_ARG(same_extent(src, residual), "affine_act: residual extent differs");
+        dr = make_dview(residual);
+    }
+    const int c8n = (src.c + 7) / 8;
+    const long long total = 1LL * src.n * c8n * src.z * src.y * src.x;
+    const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
+    affine_act_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(make_dview(src), scale, shift, slope, dr,
+                                                                                   make_dview(dst), c8n, total);
+    return check_launch("affine_act");
+}
+
+extern "C" int b200seg_bn_backward(b200seg_view dy, b200seg_view z, const float* scale, const float* shift,
+                                   const float* slope, const float* mean, const float* rstd, int32_t has_norm,
+                                   void* scratch, float* sum_g, float* sum_gx, b200seg_view dz, void* stream) {
+    int rc = check_f32_view(dy, "bn_backward dy");
+    if (rc) return rc;
+    rc = check_f32_view(z, "bn_backward z");
+    if (rc) return rc;
+    rc = check_f32_view(dz, "bn_backward dz");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(scale && shift && slope && mean && rstd && scratch && sum_g && sum_gx, "bn_backward: null argument");
+    B200SEG_CHECK_ARG(same_extent(dy, z) && same_extent(dy, dz), "bn_backward: extents differ");
+    const int c8n = (dy.c + 7) / 8, nblk = reduce_blocks(dy);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ReduceParams p{scale, shift, slope, mean, rstd};
+    DView ddy = make_dview(dy), dzv = make_dview(z);
+    chan_reduce_partial_kernel<1><<<dim3(nblk, c8n), kTrThreads, 0, s>>>(ddy, dzv, p, static_cast<double*>(scratch), nblk);
+    chan_reduce_finish_kernel<<<(c8n * 8 + 127) / 128, 128, 0, s>>>(static_cast<const double*>(scratch), nblk, c8n * 8, 1.0, 0,
+                                                                   sum_g, sum_gx);
+    const double count = 1.0 * dy.n * dy.z * dy.y * dy.x;
+    const long long total = 1LL * dy.n * c8n * dy.z * dy.y * dy.x;
+    const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
+    bn_backward_apply_kernel<<<blocks, kTrThreads, 0, s>>>(ddy, dzv, p, sum_g, sum_gx, static_cast<float>(1.0 / count),
+                                                           has_norm, make_dview(dz), c8n, total);
+    return check_launch("bn_backward");
+}
+
+extern "C" int b200seg_softmax_backward(const float* probs, const float* dprobs, int32_t n, int32_t c, int32_t softmax,
+                                        b200seg_view dst, void* stream) {
+    int rc = check_f32_view(dst, "softmax_backward dst");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(probs && dprobs && n == dst.n && c == dst.c, "softmax_backward: bad arguments");
+    const long long vox = 1LL * dst.z * dst.y * dst.x, total = vox * n;
+    const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
+    softmax_backward_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(probs, dprobs, c, vox, softmax,
+                                                                                         make_dview(dst), total);
+    return check_launch("softmax_backward");
+}
+
+extern "C" int64_t b200seg_wgrad_scratch_floats(int32_t a_channels, int32_t b_channels, int32_t ksize) {
+    // at most 1024 slices are ever used
+    const int64_t pairs = static_cast<int64_t>((a_channels + 7) / 8) * ((b_channels + 7) / 8);
+    int64_t slices = (6 * 148 + pairs * ksize - 1) / (pairs * ksize);
+    if (slices < 1) slices = 1;
+    return slices * ksize * ksize * ksize * pairs * 64;
+}
+
+extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int32_t stride, int32_t pad, float* scratch,
+                             float* grad, void* stream) {
+    int rc = check_f32_view(a, "wgrad a");
+    if (rc) return rc;
+    rc = check_f32_view(b, "wgrad b");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG((ksize == 3 || ksize == 4) && stride >= 1 && stride <= 2 && pad >= 0 && scratch && grad && a.n == b.n,
+                      "wgrad: bad arguments");
+    const int ca8n = (a.c + 7) / 8, cb8n = (b.c + 7) / 8, pairs = ca8n * cb8n;
+    WgradGeom g;
+    g.stride = stride;
+    g.pad = pad;
+    g.pz = a.z;
+    g.py = a.y;
+    g.px = a.x;
+    g.plane_blocks = (a.y * a.x + 31) / 32;
+    g.items = 1LL * a.n * a.z * g.plane_blocks;
+    g.cb8n = cb8n;
+    g.inv_px = 1.0f / static_cast<float>(a.x);
+    long long slices = (6 * 148 + 1LL * pairs * ksize - 1) / (1LL * pairs * ksize);
+    if (slices < 1) slices = 1;
+    if (slices > g.items) slices = g.items;
+    B200SEG_CHECK_ARG(pairs <= 65535, "wgrad: too many channel chunk pairs");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid(static_cast<unsigned>(slices), pairs, ksize);
+    if (ksize == 3)
+        wgrad_partial_kernel<3><<<grid, 9 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
+    else
+        wgrad_partial_kernel<4><<<grid, 16 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
+    rc = check_launch("wgrad (partial)");
+    if (rc) return rc;
+    const int taps = ksize * ksize * ksize;
+    const long long total = 1LL * taps * pairs * 64;
+    wgrad_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(scratch, static_cast<int>(slices), taps,
+                                                                                   pairs, cb8n, grad, total);
+    return check_launch("wgrad (finish)");
+}

@@ -338,17 +338,21 @@ def compiled_for(module: nn.Module, precision: str, device: torch.device) -> Com
 
 
 def forward_native(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """The ``forward`` of every mirrored module.  Inference only: the training step (autograd, batch-statistic
-    BatchNorm, Dropout3d) is a later tier and raises instead of silently computing
-    something else."""
+    """The ``forward`` of every mirrored module.  ``model.eval()``: the inference plan.  ``model.train()``: a
+    ``ModularUNet`` runs the device training step (``_train.py``: batch-statistic BatchNorm, autograd); every other
+    module with BatchNorm / Dropout raises instead of silently computing something else."""
     from .components import StochasticMatrix
+    from .modular_unet import ModularUNet
     if not x.is_cuda:
         raise RuntimeError("segmentation_pipeline.models (b200) runs on CUDA tensors only: there is no CPU "
                            "fallback on the product path (the CPU oracle lives under oracle/ for tests)")
+    if module.training and isinstance(module, ModularUNet):
+        from . import _train
+        return _train.forward_train(module, x)
     if module.training and any(isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.Dropout3d))
                                for m in module.modules()):
-        raise NotImplementedError("training-mode forward (batch statistics / dropout / autograd) is not part of "
-                                  "the inference hot path; call model.eval()")
+        raise NotImplementedError("training-mode forward (batch statistics / dropout / autograd) of this module is not "
+                                  "lowered (ModularUNet is); call model.eval()")
     lib = _b200seg()
     # the caller's current device may be another GPU: launch on the stream of the device that holds x
     with lib.on_device(x):

@@ -1,0 +1,215 @@
+"""Training step on the device (reference segmentation_trainer.py:162-180): forward in
+training mode (BatchNorm3d batch statistics), HybridLogisticDiceLoss, backward, SGD step -- against PyTorch autograd
+over the CPU oracle (oracle/unet.py with ``bn_training``) on the same weights and inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernels_vs_torch_inputs(seed, n=2, c=12, ext=(6, 10, 9)):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, c, *ext, generator=g)
+
+
+def _blocked(lib, t):
+    n, c = t.shape[:2]
+    buf = lib.Blocked(n, (c + 7) // 8, *t.shape[2:], torch.float32, t.device)
+    lib.pack_ncdhw(t.contiguous(), buf.view(c))
+    return buf
+
+
+def _unblocked(lib, buf, c):
+    out = torch.empty((buf.n, c, buf.z, buf.y, buf.x), dtype=torch.float32, device=buf.tensor.device)
+    lib.unpack_ncdhw(buf.view(c), out)
+    return out
+
+
+def test_channel_moments_and_affine_act():
+    import b200seg as lib
+    x = (_kernels_vs_torch_inputs(0) * 3 + 1.5).cuda()
+    buf = _blocked(lib, x)
+    mean, var = lib.channel_moments(buf.view(12), 12, x.device)
+    assert torch.allclose(mean[:12], x.mean(dim=(0, 2, 3, 4)), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(var[:12], x.var(dim=(0, 2, 3, 4), unbiased=False), rtol=1e-5, atol=1e-6)
+    scale = torch.randn(16).cuda()
+    shift = torch.randn(16).cuda()
+    slope = torch.full((16,), 0.1).cuda()
+    res = _kernels_vs_torch_inputs(1).cuda()
+    dst = lib.Blocked(2, 2, 6, 10, 9, torch.float32, x.device)
+    res_buf = _blocked(lib, res)           # keep the buffers alive: a View is a raw pointer
+    lib.affine_act(buf.view(12), scale, shift, slope, dst.view(12), residual=res_buf.view(12))
+    want = torch.nn.functional.leaky_relu(x * scale[:12].view(1, -1, 1, 1, 1) + shift[:12].view(1, -1, 1, 1, 1), 0.1) + res
+    assert torch.allclose(_unblocked(lib, dst, 12), want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("slope,has_norm", [(0.0, True), (0.2, True), (1.0, True), (0.0, False)])
+def test_bn_backward_matches_autograd(slope, has_norm):
+    import b200seg as lib
+    z = _kernels_vs_torch_inputs(2).cuda().requires_grad_(True)
+    dy = _kernels_vs_torch_inputs(3).cuda()
+    gamma = (torch.rand(12) + 0.5).cuda().requires_grad_(True)
+    beta = torch.randn(12).cuda().requires_grad_(True)
+    eps = 1e-5
+    if has_norm:
+        y = torch.nn.functional.batch_norm(z, None, None, gamma, beta, training=True, eps=eps)
+    else:
+        y = z
+    a = torch.nn.functional.leaky_relu(y, slope) if slope != 1.0 else y
+    a.backward(dy)
+    mean = torch.zeros(16).cuda()
+    rstd = torch.ones(16).cuda()
+    scale = torch.ones(16).cuda()
+    shift = torch.zeros(16).cuda()
+    if has_norm:
+        mean[:12] = z.detach().mean(dim=(0, 2, 3, 4))
+        rstd[:12] = torch.rsqrt(z.detach().var(dim=(0, 2, 3, 4), unbiased=False) + eps)
+        scale[:12] = gamma.detach() * rstd[:12]
+        shift[:12] = beta.detach() - mean[:12] * scale[:12]
+    dz = lib.Blocked(2, 2, 6, 10, 9, torch.float32, z.device)
+    dy_buf, z_buf = _blocked(lib, dy), _blocked(lib, z.detach())
+    sum_g, sum_gx = lib.bn_backward(dy_buf.view(12), z_buf.view(12), scale, shift,
+                                    torch.full((16,), slope).cuda(), mean, rstd, has_norm, dz.view(12), 12, z.device)
+    assert torch.allclose(_unblocked(lib, dz, 12), z.grad, rtol=1e-4, atol=1e-5)
+    if has_norm:
+        assert torch.allclose(sum_g[:12], beta.grad, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(sum_gx[:12], gamma.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("softmax", [True, False])
+def test_softmax_backward(softmax):
+    import b200seg as lib
+    logits = _kernels_vs_torch_inputs(4, c=3).cuda().requires_grad_(True)
+    dp = _kernels_vs_torch_inputs(5, c=3).cuda()
+    p = torch.softmax(logits, dim=1) if softmax else logits * 1.0
+    p.backward(dp)
+    dst = lib.Blocked(2, 1, 6, 10, 9, torch.float32, dp.device)
+    lib.softmax_backward(p.detach().contiguous(), dp, softmax, dst.view(3))
+    assert torch.allclose(_unblocked(lib, dst, 3), logits.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["k3", "down", "up"])
+@pytest.mark.parametrize("cin,cout,ext", [(2, 16, (8, 8, 8)), (16, 24, (4, 6, 10)), (40, 40, (12, 12, 12))])
+def test_wgrad_and_dgrad_match_autograd(kind, cin, cout, ext):
+    """Weight and data gradients of the three convolution geometries vs torch.autograd (float64 on the CPU)."""
+    import b200seg as lib
+    from segmentation_pipeline.models import _train
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    n = 2
+    x = torch.randn(n, cin, *ext, generator=g, dtype=torch.float64, requires_grad=True)
+    runner = _train._Runner({}, torch.device("cuda"))
+    if kind == "k3":
+        w = torch.randn(cout, cin, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv3d(x, w, padding=1)
+    elif kind == "down":
+        w = torch.randn(cout, cin, 4, 4, 4, generator=g, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv3d(x, w, stride=2, padding=1)
+    else:
+        w = torch.randn(cin, cout, 4, 4, 4, generator=g, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv_transpose3d(x, w, stride=2, padding=1)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    xb = _blocked(lib, x.detach().float().cuda())
+    dyb = _blocked(lib, dy.float().cuda())
+    wf = w.detach().float().cuda()
+    dx = lib.Blocked(n, (cin + 7) // 8, *ext, torch.float32, torch.device("cuda"))
+    if kind == "k3":
+        gw = runner._wgrad_conv(dyb.view(cout), xb.view(cin), cout, cin)
+        runner.conv(dyb.view(cout), _train._pack(wf.flip(2, 3, 4).permute(2, 3, 4, 0, 1)), cin, dx.view(cin))
+    elif kind == "down":
+        gw = lib.wgrad(dyb.view(cout), xb.view(cin), 4, 2, 1, torch.device("cuda"))[:, :cout, :cin] \
+            .permute(1, 2, 0).reshape(cout, cin, 4, 4, 4)
+        runner.conv(dyb.view(cout), _train._pack(wf.permute(2, 3, 4, 0, 1)), cin, dx.view(cin), ksize=4, stride=2, pad=1,
+                    transposed=True)
+    else:
+        gw = lib.wgrad(xb.view(cin), dyb.view(cout), 4, 2, 1, torch.device("cuda"))[:, :cin, :cout] \
+            .permute(1, 2, 0).reshape(cin, cout, 4, 4, 4)
+        runner.conv(dyb.view(cout), _train._pack(wf.permute(2, 3, 4, 1, 0)), cin, dx.view(cin), ksize=4, stride=2, pad=1)
+    scale = float(w.grad.abs().max())
+    assert float((gw.cpu().double() - w.grad).abs().max()) <= 2e-5 * scale
+    scale = float(x.grad.abs().max())
+    assert float((_unblocked(lib, dx, cin).cpu().double() - x.grad).abs().max()) <= 2e-5 * scale
+
+
+def _msseg_like(filters, depth, residual=True, act=None):
+    from segmentation_pipeline import models as M
+    block_params = {"residual": residual}
+    if act is not None:
+        block_params.update(activation_class=torch.nn.LeakyReLU, activation_params={"negative_slope": act})
+    return M.ModularUNet(2, 2, filters, depth, block_params=block_params,
+                         downsample_class=M.BlurConv3d,
+                         downsample_params={"kernel_size": 3, "stride": 2, "padding": 1},
+                         upsample_class=M.BlurConvTranspose3d,
+                         upsample_params={"kernel_size": 3, "stride": 2, "padding": 1, "output_padding": 0})
+
+
+@pytest.mark.parametrize("filters,depth,residual,act", [([8, 16], 2, True, None), ([8, 8, 16], 3, False, 0.1)])
+def test_training_step_matches_cpu_autograd(filters, depth, residual, act):
+    """One trainer iteration (segmentation_trainer.py:162-180) on a small msseg2-style ModularUNet: probabilities,
+    loss, EVERY parameter gradient, BatchNorm running statistics and the weights after the SGD step, vs autograd over
+    the CPU oracle."""
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    torch.manual_seed(5)
+    model = _msseg_like(filters, depth, residual, act)
+    g = torch.Generator().manual_seed(6)
+    for p in model.parameters():
+        if p.dim() == 1:
+            p.data.add_(0.1 * torch.randn(p.shape, generator=g))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.randn(3, 2, 16, 16, 16, generator=g)
+    labels = (torch.rand(3, 16, 16, 16, generator=g) < 0.3).long()
+    target = torch.nn.functional.one_hot(labels, 2).movedim(-1, 1).float()
+
+    # ---- CPU oracle: autograd through the functional restatement with batch-statistic BatchNorm
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "kernel" not in k)
+              for k, v in sd0.items()}
+    cfg = {"depth": depth, "filters": filters, "down": "blur", "up": "blur",
+           "block": {"residual": residual, "bn_training": True, "act": "relu" if act is None else "leaky_relu",
+                     "slope": act or 0.0}}
+    ref_probs = unet.modular_unet_forward(ref_sd, x, cfg)
+    ref_loss = unet.hybrid_logistic_dice_loss(ref_probs, target, logistic_class_weights=[1, 100])["loss"]
+    ref_loss.backward()
+
+    # ---- device
+    model.cuda().train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.95)
+    criterion = HybridLogisticDiceLoss(logistic_class_weights=[1, 100])
+    probs = model(x.cuda())
+    assert probs.requires_grad
+    loss = criterion(probs, target.cuda())["loss"]
+    opt.zero_grad()
+    loss.backward()
+    assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
+    checked = 0
+    for name, p in model.named_parameters():
+        want = ref_sd[name].grad
+        if want is None:                       # the never-applied blur-conv biases (components.py:119)
+            assert p.grad is None, name
+            continue
+        scale = float(want.abs().max()) + 1e-12
+        err = float((p.grad.cpu() - want).abs().max())
+        assert err <= 2e-4 * scale + 1e-9, (name, err, scale)
+        checked += 1
+    assert checked >= 10
+    for name, buf in model.named_buffers():
+        if "running" in name:
+            assert torch.allclose(buf.cpu(), ref_sd[name], rtol=1e-5, atol=1e-6), name
+        if "num_batches_tracked" in name:
+            assert int(buf) == 1
+    opt.step()
+    ref_params = [ref_sd[n] for n, _ in model.named_parameters()]
+    ref_opt = torch.optim.SGD([p for p in ref_params if p.grad is not None], lr=1e-3, momentum=0.95)
+    ref_opt.step()
+    for (name, p), want in zip(model.named_parameters(), ref_params):
+        assert torch.allclose(p.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7), name
+
+
+def test_training_mode_unsupported_configuration_raises():
+    from segmentation_pipeline import models as M
+    model = M.ModularUNet(1, 2, [8, 8], 2).cuda().train()        # AvgPool3d / trilinear Upsample: not lowered for training
+    with pytest.raises(NotImplementedError):
+        model(torch.randn(1, 1, 8, 8, 8).cuda())
