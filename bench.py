@@ -567,6 +567,70 @@ def run_cohort_section(world: int, rank: int, device, steps: int = 3, warmup: in
             "collective": "all_reduce(SUM) of the 2x2 int64 confusion matrix"}
 
 
+# ------------------------------------------------------------------------------------------------- training (config 5)
+TRAIN_BATCH = 4
+TRAIN_WORKLOAD = ("config5: one trainer iteration (segmentation_trainer.py:162-180) of the msseg2 ModularUNet in training mode "
+                  "(BatchNorm3d batch statistics), batch 4 x (2, 96^3) per GPU (research/msseg2/msseg2.py:94,153), fp32, "
+                  "HybridLogisticDiceLoss([1, 100]), backward, SGD(lr 1e-3, momentum 0.95); N > 1: "
+                  "DistributedDataParallel gradient all-reduce over NCCL")
+
+
+def run_train_section(world: int, rank: int, local: int, device, steps: int = 3, warmup: int = 1) -> dict:
+    """BASELINE config 5: forward + loss + backward + optimizer step, every activation
+    kernel from libb200seg (fp32 CUDA-core convolutions, wgrad, BatchNorm forward / backward)."""
+    import torch.distributed as dist
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    from segmentation_pipeline.models import set_precision
+    set_precision("auto")
+    net = build_model().to(device).train()
+    model = net
+    if world > 1:
+        # the blur convolutions' bias parameters are never used by the reference's forward (components.py:119)
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.95)
+    criterion = HybridLogisticDiceLoss(logistic_class_weights=[1, 100])
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(TRAIN_BATCH, 2, PATCH, PATCH, PATCH, generator=g).to(device)
+    labels = (torch.rand(TRAIN_BATCH, PATCH, PATCH, PATCH, generator=g) < 0.05).long()
+    y = torch.nn.functional.one_hot(labels, 2).movedim(-1, 1).float().to(device)
+    losses = []
+
+    def step():
+        out = criterion(model(x), y)
+        opt.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        losses.append(out["loss"].detach())
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    set_precision("bf16")
+    patches = world * TRAIN_BATCH
+    return {"workload": TRAIN_WORKLOAD, "n_gpus": world, "dtype": "f32", "scaling": "weak", "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "patches_per_s": patches / (ms * 1e-3),
+            "value": patches * PATCH ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxel/s (patch voxels trained)",
+            "tflops": 3 * FLOP_PER_PATCH * patches / (ms * 1e-3) / 1e12,
+            "tflops_basis": "3 x the forward FLOPs (forward + dgrad + wgrad)",
+            "loss": [float(v) for v in losses],
+            "peak_mem_gib": torch.cuda.max_memory_allocated(device) / 2 ** 30,
+            "collective": "DistributedDataParallel bucketed all-reduce of the fp32 gradients (NCCL)" if world > 1 else None}
+
+
 def run_gpu_arm(args) -> None:
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -681,6 +745,7 @@ def run_gpu_arm(args) -> None:
     set_precision("bf16")
     slab = run_slab_section(world, rank, device) if (world > 1 or args.slab) else None
     cohort4 = run_cohort_section(world, rank, device)
+    train5 = run_train_section(world, rank, local, device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -721,6 +786,7 @@ def run_gpu_arm(args) -> None:
     if slab is not None:
         line["slab"] = slab
     line["cohort_config4"] = cohort4
+    line["train_config5"] = train5
     if world == 1:
         line["config1"] = run_config1_section(device)
         set_precision("bf16")

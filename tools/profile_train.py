@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Times one trainer iteration (segmentation_trainer.py:162-180) of the msseg2 network on the device:
+model.train() forward, HybridLogisticDiceLoss, backward, SGD step.  Usage: profile_train.py [batch] [patch] [steps]."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "segmentation-pipeline_b200")]
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss  # noqa: E402
+
+
+def main():
+    batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    patch = int(sys.argv[2]) if len(sys.argv) > 2 else 96
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    model = bench.build_model().cuda().train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.95)
+    criterion = HybridLogisticDiceLoss(logistic_class_weights=[1, 100])
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 2, patch, patch, patch, generator=g).cuda()
+    labels = (torch.rand(batch, patch, patch, patch, generator=g) < 0.05).long()
+    y = torch.nn.functional.one_hot(labels, 2).movedim(-1, 1).float().cuda()
+    times = {"forward": 0.0, "loss": 0.0, "backward": 0.0, "step": 0.0}
+    for it in range(steps + 1):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        marks[0].record()
+        probs = model(x)
+        marks[1].record()
+        loss = criterion(probs, y)["loss"]
+        marks[2].record()
+        opt.zero_grad()
+        loss.backward()
+        marks[3].record()
+        opt.step()
+        marks[4].record()
+        torch.cuda.synchronize()
+        if it:                                   # first iteration = warm-up
+            for k, (a, b) in zip(times, zip(marks[:-1], marks[1:])):
+                times[k] += a.elapsed_time(b) / steps
+        print(f"iter {it}: loss {float(loss):.6f}  peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
+    total = sum(times.values())
+    flop = 3 * 668.74e9 * batch * (patch / 96) ** 3
+    print({k: round(v, 1) for k, v in times.items()}, f"total {total:.1f} ms/step; {flop / total / 1e9:.1f} TFLOP/s (3 x forward FLOPs)")
+
+
+if __name__ == "__main__":
+    main()
