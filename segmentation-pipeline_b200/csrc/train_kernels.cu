@@ -205,15 +205,17 @@ struct WgradGeom {
     int stride, pad;
     int pz, py, px;        // A (position) grid
     int plane_blocks;      // ceil(py * px / 32)
-    long long items;       // n * pz * plane_blocks
+    int items;             // n * pz * plane_blocks
     int cb8n;              // B chunks
     float inv_px;
 };
 
-template <int K>
-__global__ void __launch_bounds__(K * K * 32)
+template <int K, int H>
+__global__ void __launch_bounds__(K * K * 32 * H, (K == 3 && H == 1) ? 2 : 1)
 wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial) {
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // H groups of K*K tap-warps: group h takes every H-th trip over the plane and writes its own partial slice
+    const int half = threadIdx.x / (K * K * 32);
+    const int warp = (threadIdx.x / 32) % (K * K), lane = threadIdx.x % 32;
     const int ty = warp / K, tx = warp % K, tz = blockIdx.z;
     const int ca = blockIdx.y / g.cb8n, cb = blockIdx.y % g.cb8n;
     float acc[8][8];
@@ -222,27 +224,59 @@ wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     const int plane = g.py * g.px;
-    for (long long item = blockIdx.x; item < g.items; item += gridDim.x) {
-        const int pb = static_cast<int>(item % g.plane_blocks);
-        const long long r = item / g.plane_blocks;
-        const int z = static_cast<int>(r % g.pz);
-        const int n = static_cast<int>(r / g.pz);
+    // A block owns a contiguous range of (n, z) rows of the position grid and walks each plane 2 x 32 positions per
+    // trip: both operand pairs are loaded before the first FMA (latency), and (y, x) of a lane advance incrementally
+    // (first version: a division and 64-bit index math per item cost twice the FMAs -- ncu: 33 % of the instructions
+    // were FFMA, issue slots 32 % busy).
+    constexpr int U = 2;
+    const int rows = A.n * g.pz;
+    const int per = (rows + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * per, r1 = min(r0 + per, rows);
+    for (int r = r0; r < r1; ++r) {
+        const int n = r / g.pz, z = r - n * g.pz;
         const int bz = g.stride * z + tz - g.pad;
-        if (bz < 0 || bz >= B.z) continue;       // block-uniform
-        const int p = pb * 32 + lane;
-        if (p >= plane) continue;
-        int y = __float2int_rd((p + 0.5f) * g.inv_px);
-        if (y * g.px > p) --y;
-        if ((y + 1) * g.px <= p) ++y;
-        const int x = p - y * g.px;
-        const int by = g.stride * y + ty - g.pad, bx = g.stride * x + tx - g.pad;
-        if (by < 0 || by >= B.y || bx < 0 || bx >= B.x) continue;
-        const Vec8 a = ldv(A, vox_index(A, n, ca, z, y, x));
-        const Vec8 b = ldv(B, vox_index(B, n, cb, bz, by, bx));
+        if (bz < 0 || bz >= B.z) continue;                       // block-uniform
+        const float4* arow = reinterpret_cast<const float4*>(A.data) + 2 * vox_index(A, n, ca, z, 0, 0);
+        const float4* bplane = reinterpret_cast<const float4*>(B.data) + 2 * vox_index(B, n, cb, bz, 0, 0);
+        int py[U], px[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int u = 0; u < U; ++u) {
+            const int p = (half * U + u) * 32 + lane;
+            py[u] = p / g.px;
+            px[u] = p - py[u] * g.px;
+        }
+        for (int p0 = half * 32 * U; p0 < plane; p0 += 32 * U * H) {
+            Vec8 a[U], b[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a.v[i], b.v[j], acc[i][j]);
+            for (int u = 0; u < U; ++u) {
+                const int p = p0 + u * 32 + lane;
+                const int by = g.stride * py[u] + ty - g.pad, bx = g.stride * px[u] + tx - g.pad;
+                const bool ok = p < plane && by >= 0 && by < B.y && bx >= 0 && bx < B.x;
+                if (ok) {
+                    const float4* ap = arow + 2 * p;
+                    const float4* bp = bplane + 2 * (by * B.x + bx);
+                    const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+                    a[u].v[0] = a0.x; a[u].v[1] = a0.y; a[u].v[2] = a0.z; a[u].v[3] = a0.w;
+                    a[u].v[4] = a1.x; a[u].v[5] = a1.y; a[u].v[6] = a1.z; a[u].v[7] = a1.w;
+                    b[u].v[0] = b0.x; b[u].v[1] = b0.y; b[u].v[2] = b0.z; b[u].v[3] = b0.w;
+                    b[u].v[4] = b1.x; b[u].v[5] = b1.y; b[u].v[6] = b1.z; b[u].v[7] = b1.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[u].v[i] = b[u].v[i] = 0.f;
+                }
+                px[u] += 32 * U * H;
+                while (px[u] >= g.px) {
+                    px[u] -= g.px;
+                    ++py[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[u].v[i], b[u].v[j], acc[i][j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -252,7 +286,7 @@ wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial)
             for (int o = 16; o > 0; o >>= 1) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
     if (lane == 0) {
         const int tap = (tz * K + ty) * K + tx;
-        float* dst = partial + ((static_cast<long long>(blockIdx.x) * (K * K * K) + tap) * gridDim.y + blockIdx.y) * 64;
+        float* dst = partial + ((static_cast<long long>(blockIdx.x * H + half) * (K * K * K) + tap) * gridDim.y + blockIdx.y) * 64;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -401,24 +435,26 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
     g.py = a.y;
     g.px = a.x;
     g.plane_blocks = (a.y * a.x + 31) / 32;
-    g.items = 1LL * a.n * a.z * g.plane_blocks;
+    B200SEG_CHECK_ARG(1LL * a.n * a.z * g.plane_blocks < (1LL << 30), "wgrad: tensor too large");
+    g.items = a.n * a.z * g.plane_blocks;
     g.cb8n = cb8n;
     g.inv_px = 1.0f / static_cast<float>(a.x);
     long long slices = (6 * 148 + 1LL * pairs * ksize - 1) / (1LL * pairs * ksize);
     if (slices < 1) slices = 1;
-    if (slices > g.items) slices = g.items;
+    if (slices > 1LL * a.n * a.z) slices = 1LL * a.n * a.z;      // a block owns whole (n, z) rows
     B200SEG_CHECK_ARG(pairs <= 65535, "wgrad: too many channel chunk pairs");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     dim3 grid(static_cast<unsigned>(slices), pairs, ksize);
+    const int halves = 1;      // (two tap-warp groups per block measured slower for K = 3: 14.0 vs 15.5 TFLOP/s)
     if (ksize == 3)
-        wgrad_partial_kernel<3><<<grid, 9 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
+        wgrad_partial_kernel<3, 1><<<grid, 9 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
     else
-        wgrad_partial_kernel<4><<<grid, 16 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
+        wgrad_partial_kernel<4, 1><<<grid, 16 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
     rc = check_launch("wgrad (partial)");
     if (rc) return rc;
     const int taps = ksize * ksize * ksize;
     const long long total = 1LL * taps * pairs * 64;
-    wgrad_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(scratch, static_cast<int>(slices), taps,
+    wgrad_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(scratch, static_cast<int>(slices) * halves, taps,
                                                                                    pairs, cb8n, grad, total);
     return check_launch("wgrad (finish)");
 }
