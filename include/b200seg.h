@@ -286,8 +286,13 @@ int b200seg_hybrid_loss_backward(const float* prediction, const float* target, c
  *   wgrad                grad[tap][a_ch][b_ch] = sum_{n,pos} A[a_ch](pos) * B[b_ch](stride*pos + tap - pad), zero outside
  *                        B; tap = (tz*k + ty)*k + tx, rows padded to multiples of 8.  3x3x3 layers: A = dz, B = x,
  *                        stride 1, pad 1; BlurConv3d: A = dz, B = x, k 4, stride 2, pad 1; BlurConvTranspose3d: A = x,
- *                        B = dy, k 4, stride 2, pad 1.  scratch: wgrad_scratch_floats() floats. */
+ *                        B = dy, k 4, stride 2, pad 1.  scratch: wgrad_scratch_floats() floats.
+ *   avgpool2_backward / upsample_trilinear2_backward   adjoints of nn.AvgPool3d(2) (dx = dy(v/2)/8 + add) and of
+ *                        nn.Upsample(scale_factor=2, 'trilinear', align_corners=True) (modular_unet.py:38-41), the
+ *                        latter as a deterministic gather with the forward kernel's coefficients */
 int64_t b200seg_train_scratch_bytes(int32_t channels);
+int b200seg_avgpool2_backward(b200seg_view dy, b200seg_view add, b200seg_view dx, void* stream);
+int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_view dx, void* stream);
 int b200seg_channel_moments(b200seg_view x, void* scratch, float* mean, float* var, void* stream);
 int b200seg_affine_act(b200seg_view src, const float* scale, const float* shift, const float* slope,
                        b200seg_view residual, b200seg_view dst, void* stream);

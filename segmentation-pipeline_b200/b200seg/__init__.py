@@ -84,6 +84,8 @@ _SIGNATURES = {
     "b200seg_softmax_backward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, View, c_void_p]),
     "b200seg_wgrad_scratch_floats": (c_int64, [c_int32, c_int32, c_int32]),
     "b200seg_wgrad": (c_int32, [View, View, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200seg_avgpool2_backward": (c_int32, [View, View, View, c_void_p]),
+    "b200seg_upsample_trilinear2_backward": (c_int32, [View, View, c_void_p]),
     "b200seg_window_patches": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                          c_void_p, c_void_p]),
     "b200seg_divide_separable": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
@@ -654,3 +656,13 @@ def wgrad(a: View, b: View, ksize: int, stride: int, pad: int, device) -> torch.
     _LAUNCHES[0] += 2
     _check(lib.b200seg_wgrad(a, b, ksize, stride, pad, _ptr(scratch), _ptr(grad), _stream()), "wgrad")
     return grad
+
+
+def avgpool2_backward(dy: View, dx: View, add: View = NULL_VIEW) -> None:
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_avgpool2_backward(dy, add, dx, _stream()), "avgpool2_backward")
+
+
+def upsample_trilinear2_backward(dy: View, dx: View) -> None:
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_upsample_trilinear2_backward(dy, dx, _stream()), "upsample_trilinear2_backward")

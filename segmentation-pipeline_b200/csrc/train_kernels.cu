@@ -196,6 +196,107 @@ softmax_backward_kernel(const float* __restrict__ probs, const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------- pooling / upsampling adjoints
+// nn.AvgPool3d(2) backward: dx(v) = dy(v / 2) / 8 (+ add(v): the skip connection's gradient)
+__global__ void __launch_bounds__(kTrThreads)
+avgpool2_backward_kernel(DView dy, DView add, DView dx, int c8n, long long total) {
+    const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
+    if (t >= total) return;
+    const int x = static_cast<int>(t % dx.x);
+    long long r = t / dx.x;
+    const int y = static_cast<int>(r % dx.y);
+    r /= dx.y;
+    const int z = static_cast<int>(r % dx.z);
+    r /= dx.z;
+    const int cc = static_cast<int>(r % c8n);
+    const int n = static_cast<int>(r / c8n);
+    Vec8 o;
+    if ((z >> 1) < dy.z && (y >> 1) < dy.y && (x >> 1) < dy.x) {
+        o = ldv(dy, vox_index(dy, n, cc, z >> 1, y >> 1, x >> 1));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = o.v[j] / 8.0f;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+    }
+    if (add.data != nullptr) {
+        const Vec8 q = ldv(add, vox_index(add, n, cc, z, y, x));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] += q.v[j];
+    }
+    store_vec8<float>(dx.data, vox_index(dx, n, cc, z, y, x), o);
+}
+
+// Same interpolation coefficients as upsample_trilinear2_kernel (hbm_kernels.cu): align_corners = True
+__device__ __forceinline__ void tr_lin_coeff(int dst, int in_size, int out_size, int& i0, int& i1, float& l0, float& l1) {
+    const float scale = out_size > 1 ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.f;
+    const float src = scale * static_cast<float>(dst);
+    i0 = static_cast<int>(src);
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - static_cast<float>(i0);
+    l0 = 1.f - l1;
+}
+
+constexpr int kMaxAdj = 8;
+// outputs o of one axis that read input index i, with their weights: w = [i0(o) == i] l0 + [i1(o) == i] l1
+__device__ __forceinline__ int adjoint_taps(int i, int in_size, int out_size, int (&o_idx)[kMaxAdj], float (&w)[kMaxAdj]) {
+    int count = 0;
+    const float inv = in_size > 1 ? static_cast<float>(out_size - 1) / static_cast<float>(in_size - 1) : 0.f;
+    int lo = static_cast<int>(floorf((i - 1) * inv)) - 1, hi = static_cast<int>(ceilf((i + 1) * inv)) + 1;
+    if (in_size == 1) {
+        lo = 0;
+        hi = out_size - 1;
+    }
+    lo = max(lo, 0);
+    hi = min(hi, out_size - 1);
+    for (int o = lo; o <= hi; ++o) {
+        int i0, i1;
+        float l0, l1;
+        tr_lin_coeff(o, in_size, out_size, i0, i1, l0, l1);
+        const float ww = (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+        if (ww != 0.f && count < kMaxAdj) {
+            o_idx[count] = o;
+            w[count] = ww;
+            ++count;
+        }
+    }
+    return count;
+}
+
+// adjoint of nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True): dx(i) = sum_o W(o, i) dy(o), as a gather
+__global__ void __launch_bounds__(kTrThreads)
+upsample_trilinear2_backward_kernel(DView dy, DView dx, int c8n, long long total) {
+    const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
+    if (t >= total) return;
+    const int x = static_cast<int>(t % dx.x);
+    long long r = t / dx.x;
+    const int y = static_cast<int>(r % dx.y);
+    r /= dx.y;
+    const int z = static_cast<int>(r % dx.z);
+    r /= dx.z;
+    const int cc = static_cast<int>(r % c8n);
+    const int n = static_cast<int>(r / c8n);
+    int oz[kMaxAdj], oy[kMaxAdj], ox[kMaxAdj];
+    float wz[kMaxAdj], wy[kMaxAdj], wx[kMaxAdj];
+    const int nz = adjoint_taps(z, dx.z, dy.z, oz, wz);
+    const int ny = adjoint_taps(y, dx.y, dy.y, oy, wy);
+    const int nx = adjoint_taps(x, dx.x, dy.x, ox, wx);
+    Vec8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    for (int a = 0; a < nz; ++a)
+        for (int b = 0; b < ny; ++b) {
+            const float wzy = wz[a] * wy[b];
+            for (int c = 0; c < nx; ++c) {
+                const Vec8 v = ldv(dy, vox_index(dy, n, cc, oz[a], oy[b], ox[c]));
+                const float ww = wzy * wx[c];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(ww, v.v[j], acc.v[j]);
+            }
+        }
+    store_vec8<float>(dx.data, vox_index(dx, n, cc, z, y, x), acc);
+}
+
 // ------------------------------------------------------------------------------------------- wgrad
 // One block = the K*K in-plane taps of one tz (one warp per tap) for one (A chunk, B chunk) pair; lanes = 32
 // consecutive positions of the flattened (y, x) plane of the A grid, so both operand loads of a warp are contiguous
@@ -457,4 +558,41 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
     wgrad_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(scratch, static_cast<int>(slices) * halves, taps,
                                                                                    pairs, cb8n, grad, total);
     return check_launch("wgrad (finish)");
+}
+
+extern "C" int b200seg_avgpool2_backward(b200seg_view dy, b200seg_view add, b200seg_view dx, void* stream) {
+    int rc = check_f32_view(dy, "avgpool2_backward dy");
+    if (rc) return rc;
+    rc = check_f32_view(dx, "avgpool2_backward dx");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(dy.n == dx.n && (dy.c + 7) / 8 == (dx.c + 7) / 8 && dy.z == dx.z / 2 && dy.y == dx.y / 2 && dy.x == dx.x / 2,
+                      "avgpool2_backward: dy must be the pooled extent of dx");
+    DView dadd = null_dview();
+    if (add.data != nullptr) {
+        rc = check_f32_view(add, "avgpool2_backward add");
+        if (rc) return rc;
+        B200SEG_CHECK_ARG(same_extent(add, dx), "avgpool2_backward: add extent differs");
+        dadd = make_dview(add);
+    }
+    const int c8n = (dx.c + 7) / 8;
+    const long long total = 1LL * dx.n * c8n * dx.z * dx.y * dx.x;
+    const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
+    avgpool2_backward_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(make_dview(dy), dadd, make_dview(dx),
+                                                                                          c8n, total);
+    return check_launch("avgpool2_backward");
+}
+
+extern "C" int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_view dx, void* stream) {
+    int rc = check_f32_view(dy, "upsample_trilinear2_backward dy");
+    if (rc) return rc;
+    rc = check_f32_view(dx, "upsample_trilinear2_backward dx");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(dy.n == dx.n && (dy.c + 7) / 8 == (dx.c + 7) / 8 && dy.z == 2 * dx.z && dy.y == 2 * dx.y && dy.x == 2 * dx.x,
+                      "upsample_trilinear2_backward: dy must be twice the extent of dx");
+    const int c8n = (dx.c + 7) / 8;
+    const long long total = 1LL * dx.n * c8n * dx.z * dx.y * dx.x;
+    const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
+    upsample_trilinear2_backward_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(make_dview(dy),
+                                                                                                     make_dview(dx), c8n, total);
+    return check_launch("upsample_trilinear2_backward");
 }

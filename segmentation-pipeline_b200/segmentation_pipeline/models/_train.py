@@ -23,8 +23,9 @@ derivatives by itself; everything that touches activations is a libb200seg kerne
 
 Supported module space (anything else raises ``NotImplementedError`` -- never a silent ATen fallback): ``ModularUNet``
 with ``Block3d`` blocks (``nn.Conv3d`` / ``WSConv3d`` 3x3x3 convolutions, ``BatchNorm3d`` or no norm, ``ReLU`` /
-``LeakyReLU`` / no activation, optional residual, ``dropout_p == 0``), ``BlurConv3d`` down- and ``BlurConvTranspose3d``
-up-sampling (the msseg2 configuration, ``research/msseg2/msseg2.py:84-93``), 3x3x3 ``out_conv``, ``Softmax(dim=1)`` or
+``LeakyReLU`` / no activation, optional residual, ``dropout_p == 0``), ``AvgPool3d(2)`` or ``BlurConv3d`` down- and
+trilinear ``Upsample(2)`` or ``BlurConvTranspose3d`` up-sampling (the class defaults, ``modular_unet.py:38-41``, and the
+msseg2 configuration, ``research/msseg2/msseg2.py:84-93``), 3x3x3 ``out_conv``, ``Softmax(dim=1)`` or
 ``Identity`` hypothesis, channel counts that are multiples of 8 wherever tensors are concatenated.  fp32 only."""
 from __future__ import annotations
 
@@ -47,6 +48,12 @@ def _pad8(c: int) -> int:
 
 class Unsupported(NotImplementedError):
     pass
+
+
+def _triple(value):
+    if isinstance(value, (tuple, list)):
+        return tuple(int(v) if float(v) == int(v) else float(v) for v in value)
+    return (int(value) if float(value) == int(value) else float(value),) * 3
 
 
 # ------------------------------------------------------------------------------------------------- module -> spec
@@ -135,20 +142,34 @@ def build_spec(model):
     spec = {"depth": model.depth, "down": [], "downs": [], "up": [], "ups": []}
     for block in model.down_blocks:
         spec["down"].append(_block_spec(block, params))
-    for down in model.downsampling:
+    for i, down in enumerate(model.downsampling):
+        width = spec["down"][i]["cout"]
+        if isinstance(down, nn.AvgPool3d):
+            if _triple(down.kernel_size) != (2, 2, 2) or _triple(down.stride) != (2, 2, 2) or _triple(down.padding) != (0, 0, 0) \
+                    or down.ceil_mode:
+                raise Unsupported("training: only AvgPool3d(kernel_size=2, stride=2) is lowered")
+            spec["downs"].append({"w": None, "cin": width, "cout": width})
+            continue
         if not isinstance(down, BlurConv3d) or down.kernel_size != (3, 3, 3) or down.stride != (2, 2, 2) or \
                 down.padding != (1, 1, 1):
             raise Unsupported(f"training: downsampling {type(down).__name__} is not lowered "
-                              f"(BlurConv3d(kernel_size=3, stride=2, padding=1) is)")
+                              f"(AvgPool3d(2) and BlurConv3d(kernel_size=3, stride=2, padding=1) are)")
         params.append(_blurred(down))
         spec["downs"].append({"w": len(params) - 1, "cin": down.in_channels, "cout": down.out_channels})
     for block in model.up_blocks:
         spec["up"].append(_block_spec(block, params))
-    for up in model.upsampling:
+    for i, up in enumerate(model.upsampling):
+        if isinstance(up, nn.Upsample):
+            if up.mode != "trilinear" or not up.align_corners or up.size is not None or \
+                    _triple(up.scale_factor) != (2, 2, 2):
+                raise Unsupported("training: only Upsample(scale_factor=2, mode='trilinear', align_corners=True) is lowered")
+            width = spec["down"][i + 1]["cout"]
+            spec["ups"].append({"w": None, "cin": width, "cout": width})
+            continue
         if not isinstance(up, BlurConvTranspose3d) or up.kernel_size != (3, 3, 3) or up.stride != (2, 2, 2) or \
                 up.padding != (1, 1, 1) or up.output_padding != (0, 0, 0):
-            raise Unsupported(f"training: upsampling {type(up).__name__} is not lowered "
-                              f"(BlurConvTranspose3d(kernel_size=3, stride=2, padding=1, output_padding=0) is)")
+            raise Unsupported(f"training: upsampling {type(up).__name__} is not lowered (trilinear Upsample(2) and "
+                              f"BlurConvTranspose3d(kernel_size=3, stride=2, padding=1, output_padding=0) are)")
         params.append(_blurred(up))
         spec["ups"].append({"w": len(params) - 1, "cin": up.in_channels, "cout": up.out_channels})
     wi, bi = _effective_conv_weight(model.out_conv, params)
@@ -293,8 +314,12 @@ class _Runner:
                 out = self.block_forward(("down", i), b, params, cur, n, exts[i], cat, up_c // 8)
                 d = spec["downs"][i]
                 nxt = self.buffer(n, d["cout"], exts[i + 1])
-                wb = params[d["w"]].detach()
-                self.conv(out, _pack(wb.permute(2, 3, 4, 1, 0)), d["cout"], nxt.view(d["cout"]), ksize=4, stride=2, pad=1)
+                if d["w"] is None:
+                    lib.avgpool2(out, nxt.view(d["cout"]))                          # nn.AvgPool3d(2), modular_unet.py:40-41
+                else:
+                    wb = params[d["w"]].detach()
+                    self.conv(out, _pack(wb.permute(2, 3, 4, 1, 0)), d["cout"], nxt.view(d["cout"]), ksize=4, stride=2,
+                              pad=1)
                 self.saved[("downs", i)] = {"in": out, "out_buf": nxt}
                 cur = nxt.view(d["cout"])
             else:
@@ -303,10 +328,13 @@ class _Runner:
                 self.saved["bottom"] = bottom
         for i in reversed(range(depth - 1)):
             u = spec["ups"][i]
-            wt = params[u["w"]].detach()
             cat = cats[i]
-            self.conv(cur, _pack(wt.permute(2, 3, 4, 0, 1)), u["cout"], cat.view(u["cout"], 0), ksize=4, stride=2, pad=1,
-                      transposed=True)
+            if u["w"] is None:
+                lib.upsample_trilinear2(cur, cat.view(u["cout"], 0))                # nn.Upsample, modular_unet.py:38-39
+            else:
+                wt = params[u["w"]].detach()
+                self.conv(cur, _pack(wt.permute(2, 3, 4, 0, 1)), u["cout"], cat.view(u["cout"], 0), ksize=4, stride=2,
+                          pad=1, transposed=True)
             self.saved[("ups", i)] = {"in": cur}
             b = spec["up"][i]
             outb = self.buffer(n, b["cout"], exts[i])
@@ -409,12 +437,15 @@ class _Runner:
             dskips[i] = (dcat, u["cout"] // 8, spec["down"][i]["cout"])
             du = dcat.view(u["cout"], 0)
             up_in = self.saved.pop(("ups", i))["in"]
-            # BlurConvTranspose3d: weight (cin, cout, 4, 4, 4) -- wgrad with A = x, B = dy
-            g = lib.wgrad(up_in, du, 4, 2, 1, self.device)                     # [tap][cin_pad][cout_pad]
-            grads[u["w"]] = g[:, :u["cin"], :u["cout"]].permute(1, 2, 0).reshape(u["cin"], u["cout"], 4, 4, 4)
-            wt = params[u["w"]].detach()
             dnext = self.buffer(n, u["cin"], exts[i + 1])
-            self.conv(du, _pack(wt.permute(2, 3, 4, 1, 0)), u["cin"], dnext.view(u["cin"]), ksize=4, stride=2, pad=1)
+            if u["w"] is None:
+                lib.upsample_trilinear2_backward(du, dnext.view(u["cin"]))
+            else:
+                # BlurConvTranspose3d: weight (cin, cout, 4, 4, 4) -- wgrad with A = x, B = dy
+                g = lib.wgrad(up_in, du, 4, 2, 1, self.device)                 # [tap][cin_pad][cout_pad]
+                grads[u["w"]] = g[:, :u["cin"], :u["cout"]].permute(1, 2, 0).reshape(u["cin"], u["cout"], 4, 4, 4)
+                wt = params[u["w"]].detach()
+                self.conv(du, _pack(wt.permute(2, 3, 4, 1, 0)), u["cin"], dnext.view(u["cin"]), ksize=4, stride=2, pad=1)
             dcur_buf, dcur = dnext, dnext.view(u["cin"])
         for i in reversed(range(depth)):                   # down blocks, deepest first
             b = spec["down"][i]
@@ -423,16 +454,19 @@ class _Runner:
                 break
             d = spec["downs"][i - 1]
             sv = self.saved.pop(("downs", i - 1))
-            # BlurConv3d: weight (cout, cin, 4, 4, 4) -- wgrad with A = dz (coarse grid), B = x
-            g = lib.wgrad(dsrc.view(d["cout"]), sv["in"], 4, 2, 1, self.device)      # [tap][cout_pad][cin_pad]
-            grads[d["w"]] = g[:, :d["cout"], :d["cin"]].permute(1, 2, 0).reshape(d["cout"], d["cin"], 4, 4, 4)
-            wb = params[d["w"]].detach()
             dcat, off, skip_c = dskips.pop(i - 1)
             dout = self.buffer(n, d["cin"], exts[i - 1])
-            # adjoint of the strided conv = the transposed geometry; the skip connection's gradient rides in as the
-            # residual of the epilogue
-            self.conv(dsrc.view(d["cout"]), _pack(wb.permute(2, 3, 4, 0, 1)), d["cin"], dout.view(d["cin"]), ksize=4,
-                      stride=2, pad=1, transposed=True, residual=dcat.view(skip_c, off))
+            if d["w"] is None:
+                lib.avgpool2_backward(dsrc.view(d["cout"]), dout.view(d["cin"]), add=dcat.view(skip_c, off))
+            else:
+                # BlurConv3d: weight (cout, cin, 4, 4, 4) -- wgrad with A = dz (coarse grid), B = x
+                g = lib.wgrad(dsrc.view(d["cout"]), sv["in"], 4, 2, 1, self.device)      # [tap][cout_pad][cin_pad]
+                grads[d["w"]] = g[:, :d["cout"], :d["cin"]].permute(1, 2, 0).reshape(d["cout"], d["cin"], 4, 4, 4)
+                wb = params[d["w"]].detach()
+                # adjoint of the strided conv = the transposed geometry; the skip connection's gradient rides in as
+                # the residual of the epilogue
+                self.conv(dsrc.view(d["cout"]), _pack(wb.permute(2, 3, 4, 0, 1)), d["cin"], dout.view(d["cin"]), ksize=4,
+                          stride=2, pad=1, transposed=True, residual=dcat.view(skip_c, off))
             dcur_buf, dcur = dout, dout.view(d["cin"])
         self.saved.clear()
         return grads

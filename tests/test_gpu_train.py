@@ -208,8 +208,57 @@ def test_training_step_matches_cpu_autograd(filters, depth, residual, act):
         assert torch.allclose(p.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7), name
 
 
+def test_default_modular_unet_training_step_matches_cpu_autograd():
+    """The class defaults (AvgPool3d(2) down, trilinear Upsample(2, align_corners=True) up, no residual) -- the
+    BASELINE config-1 network -- through one training step."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    torch.manual_seed(8)
+    filters, depth = [8, 16, 24], 3
+    model = M.ModularUNet(1, 3, filters, depth)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 1, 16, 24, 8, generator=g)
+    target = torch.nn.functional.one_hot(torch.randint(0, 3, (2, 16, 24, 8), generator=g), 3).movedim(-1, 1).float()
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    cfg = {"depth": depth, "filters": filters, "down": "avgpool", "up": "trilinear",
+           "block": {"residual": False, "bn_training": True}}
+    ref_probs = unet.modular_unet_forward(ref_sd, x, cfg)
+    unet.hybrid_logistic_dice_loss(ref_probs, target)["loss"].backward()
+    model.cuda().train()
+    probs = model(x.cuda())
+    HybridLogisticDiceLoss()(probs, target.cuda())["loss"].backward()
+    assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5
+    for name, p in model.named_parameters():
+        want = ref_sd[name].grad
+        scale = float(want.abs().max()) + 1e-12
+        assert float((p.grad.cpu() - want).abs().max()) <= 2e-4 * scale + 1e-9, name
+
+
+def test_pool_and_upsample_adjoints_match_autograd():
+    import b200seg as lib
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 12, 4, 6, 10, generator=g, dtype=torch.float64, requires_grad=True)
+    up = torch.nn.functional.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    dy = torch.randn(up.shape, generator=g, dtype=torch.float64)
+    up.backward(dy)
+    dy_buf = _blocked(lib, dy.float().cuda())
+    dx = lib.Blocked(2, 2, 4, 6, 10, torch.float32, torch.device("cuda"))
+    lib.upsample_trilinear2_backward(dy_buf.view(12), dx.view(12))
+    assert float((_unblocked(lib, dx, 12).cpu().double() - x.grad).abs().max()) <= 1e-5 * float(x.grad.abs().max())
+    big = torch.randn(2, 12, 8, 12, 20, generator=g, dtype=torch.float64, requires_grad=True)
+    pooled = torch.nn.functional.avg_pool3d(big, 2, 2)
+    dp = torch.randn(pooled.shape, generator=g, dtype=torch.float64)
+    add = torch.randn(big.shape, generator=g, dtype=torch.float64)
+    pooled.backward(dp)
+    dp_buf, add_buf = _blocked(lib, dp.float().cuda()), _blocked(lib, add.float().cuda())
+    dbig = lib.Blocked(2, 2, 8, 12, 20, torch.float32, torch.device("cuda"))
+    lib.avgpool2_backward(dp_buf.view(12), dbig.view(12), add=add_buf.view(12))
+    assert float((_unblocked(lib, dbig, 12).cpu().double() - (big.grad + add)).abs().max()) <= 1e-6
+
+
 def test_training_mode_unsupported_configuration_raises():
     from segmentation_pipeline import models as M
-    model = M.ModularUNet(1, 2, [8, 8], 2).cuda().train()        # AvgPool3d / trilinear Upsample: not lowered for training
+    model = M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.2}).cuda().train()    # Dropout3d: not lowered
     with pytest.raises(NotImplementedError):
         model(torch.randn(1, 1, 8, 8, 8).cuda())
