@@ -93,10 +93,13 @@ def main():
     model = sp.ModularUNet(2, 3, [8, 16], 2, block_params={"residual": True})
     model.eval()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd0 = {k: v.clone() for k, v in sd.items()}
     device = torch.device(args.device)
 
     class StubTrainPredictor(sp.prediction.Predictor):
-        """Stands in for the training-mode forward (f3, not built): returns tensors the criterion can consume."""
+        """CPU-only wiring run: stands in for the training-mode forward (which needs the GPU): returns tensors the
+        criterion can consume.  On the GPU the trainer gets the real thing -- StandardPredict(['X', 'y']) over the model
+        in training mode, as research/msseg2/msseg2.py:138 configures it."""
         def predict(self, model, device, subjects, label_attributes=None):
             y = torch.stack([s["y"]["data"] for s in subjects]).float().to(device)
             return subjects, {"y": y, "y_pred": (y * 0 + 1.0 / y.shape[1]).requires_grad_(True)}
@@ -127,10 +130,14 @@ def main():
             logs.append(log_dict)
 
     dummy = torch.nn.Parameter(torch.zeros(1))
+    on_gpu = device.type == "cuda"
+    if on_gpu:
+        model.to(device)
     context = types.SimpleNamespace(
-        dataset=dataset, model=model.to(device) if device.type == "cuda" else model, device=device,
+        dataset=dataset, model=model, device=device,
         criterion=criterion,
-        optimizer=torch.optim.SGD([dummy], lr=0.1))
+        optimizer=torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.95) if on_gpu
+        else torch.optim.SGD([dummy], lr=0.1))
     sampler = torch.utils.data.SequentialSampler
     evaluator = sp.SegmentationEvaluator("y_pred_eval", "y_eval", stats_to_output=("TP", "FP", "TN", "FN", "dice"))
     trainer = sp.SegmentationTrainer(
@@ -139,7 +146,7 @@ def main():
         one_time_evaluators=[], training_evaluators=[],
         validation_evaluators=[sp.ScheduledEvaluation(evaluator, "seg", cohorts=["validation"])],
         max_iterations_with_no_improvement=10,
-        train_predictor=StubTrainPredictor(),
+        train_predictor=sp.StandardPredict(image_names=["X", "y"]) if on_gpu else StubTrainPredictor(),
         validation_predictor=sp.PatchPredict(patch_batch_size=5, patch_size=(16, 16, 16), patch_overlap=(8, 8, 4),
                                              padding_mode="edge", overlap_mode="average"),
         train_dataloader_factory=sp.StandardDataLoader(sampler=sampler),
@@ -167,6 +174,26 @@ def main():
     # ------------------------------------------------------------------ the same thing on the CPU oracle
     from oracle import evalstats, grid as ogrid, unet
     cfg = {"depth": 2, "filters": [8, 16], "block": {"residual": True}, "down": "avgpool", "up": "trilinear"}
+    # the training step of the iteration (segmentation_trainer.py:162-180) on the first training subject: autograd
+    # through the oracle with batch-statistic BatchNorm, then the first SGD step (momentum buffer = gradient)
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    x0, labels0 = synth("s0")
+    remapped = torch.where(labels0 == 1, 2, torch.where(labels0 == 2, 1, labels0))
+    y0 = torch.nn.functional.one_hot(remapped[0], 3).movedim(-1, 0)[None].float()
+    train_cfg = dict(cfg, block=dict(cfg["block"], bn_training=True))
+    ref_loss = unet.hybrid_logistic_dice_loss(unet.modular_unet_forward(ref_sd, x0[None], train_cfg), y0)["loss"]
+    ref_loss.backward()
+    with torch.no_grad():
+        for v in ref_sd.values():
+            if v.grad is not None:
+                v -= 1e-3 * v.grad
+    sd = {k: v.detach() for k, v in ref_sd.items()}
+    out["oracle_train_loss"] = float(ref_loss)
+    out["train_step_max_abs_weight_diff"] = max(
+        float((v.detach().cpu().float() - sd[k].float()).abs().max()) for k, v in model.state_dict().items()
+        if "num_batches_tracked" not in k)
+    out["weights_moved"] = max(float((v.detach().cpu() - sd0[k]).abs().max()) for k, v in model.state_dict().items()
+                               if v.is_floating_point())
     expected = {}
     for n in ("s2", "s3"):
         vol, labels = synth(n)

@@ -1,5 +1,6 @@
-"""Drop-in proof on the GPU: the unmodified reference ``SegmentationTrainer`` runs one iteration whose validation
-branch (segmentation_trainer.py:196-242) goes through the b200 ``PatchPredict`` -> history-inverse
+"""Drop-in proof on the GPU: the unmodified reference ``SegmentationTrainer`` runs one iteration whose training step
+(segmentation_trainer.py:162-180) goes through the b200 model in training mode (device forward / backward) and whose
+validation branch (segmentation_trainer.py:196-242) goes through the b200 ``PatchPredict`` -> history-inverse
 ``add_evaluation_labels`` (label swap undone, argmax on the device) -> ``SegmentationEvaluator`` (device confusion
 histogram); the per-subject TP / FP / TN / FN / Dice the trainer logged are compared with the CPU oracle."""
 import pytest
@@ -34,9 +35,12 @@ def test_reference_trainer_validation_branch_on_gpu(precision):
                                       "served_from": res["served_from"], "subject_stats": stats["data"],
                                       "oracle": res["oracle"], "model_score": res["model_score"]}))
     assert "model_forward_evaluation" in res["timer_keys"] and "evaluation.seg.validation" in res["timer_keys"]
-    # the training step of the same iteration used the b200 criterion (device kernels + autograd) via the reference's name
+    # the training step of the same iteration (segmentation_trainer.py:162-180) ran on the device too: the model in
+    # training mode behind StandardPredict(['X', 'y']), the b200 criterion, backward through the device autograd
+    # function, the reference's optimizer step -- loss and updated weights (incl. BatchNorm running statistics) match an
+    # autograd step over the CPU oracle
     assert res["criterion_module"].endswith("from b200")
-    # uniform prediction 1/3 against a one-hot target: logistic = -log(1/3)/3 per channel on average
-    import math
-    assert abs(res["train_loss"]["logistic_loss"] - math.log(3.0) / 3.0) < 1e-4
+    assert abs(res["train_loss"]["loss"] - res["oracle_train_loss"]) <= 1e-5 * max(1.0, abs(res["oracle_train_loss"]))
     assert res["train_grad_abs_sum"] is not None and res["train_grad_abs_sum"] > 0
+    assert res["weights_moved"] > 1e-6
+    assert res["train_step_max_abs_weight_diff"] <= 1e-6
