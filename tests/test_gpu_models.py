@@ -207,11 +207,16 @@ def test_unsupported_and_training_mode_raise():
     with pytest.raises(NotImplementedError):
         model(torch.zeros(1, 1, 8, 8, 8).cuda())     # Tanh is not lowered: loud error, no silent ATen path
     meta, sd, x, y = load_case("models_modular_default")
-    model = build_model(meta).cuda().train()
-    with pytest.raises(NotImplementedError):
-        model(x.cuda())
+    model = build_model(meta).cuda()
     with pytest.raises(RuntimeError):
         model.eval()(x)           # CPU tensor
+    # training mode: ModularUNet is lowered (tests/test_gpu_train.py); what is not raises instead of falling back
+    nested = M.NestedResUNet(1, 2, 8).cuda().train()
+    with pytest.raises(NotImplementedError):
+        nested(torch.zeros(1, 1, 16, 16, 16).cuda())
+    dropout = M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.1}).cuda().train()
+    with pytest.raises(NotImplementedError):
+        dropout(torch.zeros(1, 1, 8, 8, 8).cuda())
 
 
 def test_components_forward():
