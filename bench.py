@@ -576,12 +576,22 @@ TRAIN_WORKLOAD = ("config5: one trainer iteration (segmentation_trainer.py:162-1
 
 
 def run_train_section(world: int, rank: int, local: int, device, steps: int = 3, warmup: int = 1) -> dict:
-    """BASELINE config 5: forward + loss + backward + optimizer step, every activation
-    kernel from libb200seg (fp32 CUDA-core convolutions, wgrad, BatchNorm forward / backward)."""
+    """BASELINE config 5 in both precisions of the training step: 'fp32' (the reference's arithmetic: CUDA-core
+    convolutions) and 'bf16' (mixed precision: forward and dgrad on the tcgen05 engine, fp32 statistics / wgrad /
+    parameters)."""
+    out = {"workload": TRAIN_WORKLOAD}
+    for precision in ("fp32", "bf16"):
+        out[precision] = _run_train(world, rank, local, device, precision, steps, warmup)
+    return out
+
+
+def _run_train(world: int, rank: int, local: int, device, precision: str, steps: int, warmup: int) -> dict:
+    """Forward + loss + backward + optimizer step; every activation kernel from libb200seg."""
     import torch.distributed as dist
     from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
     from segmentation_pipeline.models import set_precision
-    set_precision("auto")
+    set_precision(precision)
+    torch.cuda.reset_peak_memory_stats(device)
     net = build_model().to(device).train()
     model = net
     if world > 1:
@@ -621,7 +631,8 @@ def run_train_section(world: int, rank: int, local: int, device, steps: int = 3,
     ms = float(ms.item())
     set_precision("bf16")
     patches = world * TRAIN_BATCH
-    return {"workload": TRAIN_WORKLOAD, "n_gpus": world, "dtype": "f32", "scaling": "weak", "steps": steps, "warmup": warmup,
+    return {"n_gpus": world, "dtype": "f32" if precision == "fp32" else "bf16 activations / fp32 accumulation, statistics and weights",
+            "scaling": "weak", "steps": steps, "warmup": warmup,
             "ms_per_step": ms, "patches_per_s": patches / (ms * 1e-3),
             "value": patches * PATCH ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxel/s (patch voxels trained)",
             "tflops": 3 * FLOP_PER_PATCH * patches / (ms * 1e-3) / 1e12,

@@ -273,8 +273,9 @@ int b200seg_hybrid_loss_backward(const float* prediction, const float* target, c
 
 /* ------------------------------------------------------------------------------------------------ training step
  * The device side of the reference's trainer step (segmentation_trainer.py:162-180: model.train(), forward, loss,
- * backward; BatchNorm3d with batch statistics, components.py:53).  fp32 blocked views only.  Forward convolutions and
- * data gradients are b200seg_conv3d_direct launches (a dgrad is a convolution with re-arranged weights); these entry
+ * backward; BatchNorm3d with batch statistics, components.py:53).  fp32 blocked views (the precision path) or bf16 ones
+ * (mixed precision: bf16 storage, fp32 arithmetic; all views of a call share one dtype).  Forward convolutions and
+ * data gradients are b200seg_conv3d_direct (fp32) / b200seg_conv3d_tc (bf16) launches (a dgrad is a convolution with re-arranged weights); these entry
  * points add the rest.  All reductions are deterministic (per-block partials summed in a fixed order).
  *   train_scratch_bytes  size of the double scratch the reductions need for `channels` channels
  *   channel_moments      mean[c], var[c] (biased) over (N, Z, Y, X)               -- nn.BatchNorm3d training statistics

@@ -10,13 +10,27 @@
 //   softmax_backward dlogits = p * (dp - sum_c dp_c p_c), NCDHW -> blocked
 // All reductions are two-stage with per-block partials summed in a fixed order (deterministic, no atomics); the
 // per-channel sums are carried in double.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200seg {
 
 constexpr int kTrThreads = 256;
 
-__device__ __forceinline__ Vec8 ldv(const DView& v, long long idx) { return load_vec8<float>(v.data, idx); }
+template <typename T>
+__device__ __forceinline__ Vec8 ldv(const DView& v, long long idx) { return load_vec8<T>(v.data, idx); }
+
+#define TRAIN_DISPATCH(dtype, ...)        \
+    do {                                   \
+        if ((dtype) == B200SEG_F32) {      \
+            using T = float;               \
+            __VA_ARGS__;                   \
+        } else {                           \
+            using T = __nv_bfloat16;       \
+            __VA_ARGS__;                   \
+        }                                  \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------- two-sum reductions
 // MODE 0: (x, x^2) of view a.   MODE 1: (g, g * xhat) with g = dy * act'(scale * z + shift), xhat = (z - mean) * rstd;
@@ -29,7 +43,7 @@ struct ReduceParams {
     const float* rstd;
 };
 
-template <int MODE>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kTrThreads)
 chan_reduce_partial_kernel(DView a, DView b, ReduceParams p, double* __restrict__ partial, int nblk) {
     __shared__ double red[kTrThreads / 32][16];
@@ -53,7 +67,7 @@ chan_reduce_partial_kernel(DView a, DView b, ReduceParams p, double* __restrict_
     }
     for (long long t = t0 + threadIdx.x; t < t1; t += kTrThreads) {
         const long long n = t / a.chunk_stride, v = t - n * a.chunk_stride;
-        const Vec8 x = ldv(a, n * a.sample_stride + (a.c8_off + cc) * a.chunk_stride + v);
+        const Vec8 x = ldv<T>(a, n * a.sample_stride + (a.c8_off + cc) * a.chunk_stride + v);
         if (MODE == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -61,7 +75,7 @@ chan_reduce_partial_kernel(DView a, DView b, ReduceParams p, double* __restrict_
                 s2[j] = fmaf(x.v[j], x.v[j], s2[j]);
             }
         } else {
-            const Vec8 z = ldv(b, n * b.sample_stride + (b.c8_off + cc) * b.chunk_stride + v);
+            const Vec8 z = ldv<T>(b, n * b.sample_stride + (b.c8_off + cc) * b.chunk_stride + v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float y = fmaf(z.v[j], sc[j], sh[j]);
@@ -117,6 +131,7 @@ __global__ void chan_reduce_finish_kernel(const double* __restrict__ partial, in
 }
 
 // ------------------------------------------------------------------------------------------- elementwise
+template <typename T>
 __global__ void __launch_bounds__(kTrThreads)
 affine_act_kernel(DView src, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ slope, DView residual, DView dst, int c8n, long long total) {
@@ -126,21 +141,22 @@ affine_act_kernel(DView src, const float* __restrict__ scale, const float* __res
     const long long r = t / src.chunk_stride;
     const int cc = static_cast<int>(r % c8n);
     const long long n = r / c8n;
-    Vec8 a = ldv(src, n * src.sample_stride + (src.c8_off + cc) * src.chunk_stride + v);
+    Vec8 a = ldv<T>(src, n * src.sample_stride + (src.c8_off + cc) * src.chunk_stride + v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float y = fmaf(a.v[j], __ldg(scale + cc * 8 + j), __ldg(shift + cc * 8 + j));
         a.v[j] = y > 0.f ? y : y * __ldg(slope + cc * 8 + j);
     }
     if (residual.data != nullptr) {
-        const Vec8 q = ldv(residual, n * residual.sample_stride + (residual.c8_off + cc) * residual.chunk_stride + v);
+        const Vec8 q = ldv<T>(residual, n * residual.sample_stride + (residual.c8_off + cc) * residual.chunk_stride + v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a.v[j] += q.v[j];
     }
-    store_vec8<float>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, a);
+    store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, a);
 }
 
 // dz = has_norm ? scale * (g - c1 - xhat * c2) : g,   g = dy * act'(scale * z + shift); c1 = sum g / M, c2 = sum g xhat / M
+template <typename T>
 __global__ void __launch_bounds__(kTrThreads)
 bn_backward_apply_kernel(DView dy, DView z, ReduceParams p, const float* __restrict__ sum_g,
                          const float* __restrict__ sum_gx, float inv_count, int has_norm, DView dst, int c8n,
@@ -151,8 +167,8 @@ bn_backward_apply_kernel(DView dy, DView z, ReduceParams p, const float* __restr
     const long long r = t / dy.chunk_stride;
     const int cc = static_cast<int>(r % c8n);
     const long long n = r / c8n;
-    const Vec8 d = ldv(dy, n * dy.sample_stride + (dy.c8_off + cc) * dy.chunk_stride + v);
-    const Vec8 zz = ldv(z, n * z.sample_stride + (z.c8_off + cc) * z.chunk_stride + v);
+    const Vec8 d = ldv<T>(dy, n * dy.sample_stride + (dy.c8_off + cc) * dy.chunk_stride + v);
+    const Vec8 zz = ldv<T>(z, n * z.sample_stride + (z.c8_off + cc) * z.chunk_stride + v);
     Vec8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -167,10 +183,11 @@ bn_backward_apply_kernel(DView dy, DView z, ReduceParams p, const float* __restr
             o.v[j] = g;
         }
     }
-    store_vec8<float>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, o);
+    store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, o);
 }
 
 // probs / dprobs: fp32 NCDHW [N][C][vox]; dst: blocked view with C channels (padding channels written as 0)
+template <typename T>
 __global__ void __launch_bounds__(kTrThreads)
 softmax_backward_kernel(const float* __restrict__ probs, const float* __restrict__ dprobs, int C, long long vox,
                         int softmax, DView dst, long long total) {
@@ -192,12 +209,13 @@ softmax_backward_kernel(const float* __restrict__ probs, const float* __restrict
             if (c < C) val = softmax ? __ldg(pp + c * vox) * (__ldg(dp + c * vox) - dot) : __ldg(dp + c * vox);
             o.v[j] = val;
         }
-        store_vec8<float>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, o);
+        store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, o);
     }
 }
 
 // ------------------------------------------------------------------------------------------- pooling / upsampling adjoints
 // nn.AvgPool3d(2) backward: dx(v) = dy(v / 2) / 8 (+ add(v): the skip connection's gradient)
+template <typename T>
 __global__ void __launch_bounds__(kTrThreads)
 avgpool2_backward_kernel(DView dy, DView add, DView dx, int c8n, long long total) {
     const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
@@ -212,7 +230,7 @@ avgpool2_backward_kernel(DView dy, DView add, DView dx, int c8n, long long total
     const int n = static_cast<int>(r / c8n);
     Vec8 o;
     if ((z >> 1) < dy.z && (y >> 1) < dy.y && (x >> 1) < dy.x) {
-        o = ldv(dy, vox_index(dy, n, cc, z >> 1, y >> 1, x >> 1));
+        o = ldv<T>(dy, vox_index(dy, n, cc, z >> 1, y >> 1, x >> 1));
 #pragma unroll
         for (int j = 0; j < 8; ++j) o.v[j] = o.v[j] / 8.0f;
     } else {
@@ -220,11 +238,11 @@ avgpool2_backward_kernel(DView dy, DView add, DView dx, int c8n, long long total
         for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
     }
     if (add.data != nullptr) {
-        const Vec8 q = ldv(add, vox_index(add, n, cc, z, y, x));
+        const Vec8 q = ldv<T>(add, vox_index(add, n, cc, z, y, x));
 #pragma unroll
         for (int j = 0; j < 8; ++j) o.v[j] += q.v[j];
     }
-    store_vec8<float>(dx.data, vox_index(dx, n, cc, z, y, x), o);
+    store_vec8<T>(dx.data, vox_index(dx, n, cc, z, y, x), o);
 }
 
 // Same interpolation coefficients as upsample_trilinear2_kernel (hbm_kernels.cu): align_corners = True
@@ -264,6 +282,7 @@ __device__ __forceinline__ int adjoint_taps(int i, int in_size, int out_size, in
 }
 
 // adjoint of nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True): dx(i) = sum_o W(o, i) dy(o), as a gather
+template <typename T>
 __global__ void __launch_bounds__(kTrThreads)
 upsample_trilinear2_backward_kernel(DView dy, DView dx, int c8n, long long total) {
     const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
@@ -288,13 +307,13 @@ upsample_trilinear2_backward_kernel(DView dy, DView dx, int c8n, long long total
         for (int b = 0; b < ny; ++b) {
             const float wzy = wz[a] * wy[b];
             for (int c = 0; c < nx; ++c) {
-                const Vec8 v = ldv(dy, vox_index(dy, n, cc, oz[a], oy[b], ox[c]));
+                const Vec8 v = ldv<T>(dy, vox_index(dy, n, cc, oz[a], oy[b], ox[c]));
                 const float ww = wzy * wx[c];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(ww, v.v[j], acc.v[j]);
             }
         }
-    store_vec8<float>(dx.data, vox_index(dx, n, cc, z, y, x), acc);
+    store_vec8<T>(dx.data, vox_index(dx, n, cc, z, y, x), acc);
 }
 
 // ------------------------------------------------------------------------------------------- wgrad
@@ -311,7 +330,7 @@ struct WgradGeom {
     float inv_px;
 };
 
-template <int K, int H>
+template <typename T, int K, int H>
 __global__ void __launch_bounds__(K * K * 32 * H, (K == 3 && H == 1) ? 2 : 1)
 wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial) {
     // H groups of K*K tap-warps: group h takes every H-th trip over the plane and writes its own partial slice
@@ -337,8 +356,7 @@ wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial)
         const int n = r / g.pz, z = r - n * g.pz;
         const int bz = g.stride * z + tz - g.pad;
         if (bz < 0 || bz >= B.z) continue;                       // block-uniform
-        const float4* arow = reinterpret_cast<const float4*>(A.data) + 2 * vox_index(A, n, ca, z, 0, 0);
-        const float4* bplane = reinterpret_cast<const float4*>(B.data) + 2 * vox_index(B, n, cb, bz, 0, 0);
+        const long long arow = vox_index(A, n, ca, z, 0, 0), bplane = vox_index(B, n, cb, bz, 0, 0);
         int py[U], px[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -354,13 +372,8 @@ wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial)
                 const int by = g.stride * py[u] + ty - g.pad, bx = g.stride * px[u] + tx - g.pad;
                 const bool ok = p < plane && by >= 0 && by < B.y && bx >= 0 && bx < B.x;
                 if (ok) {
-                    const float4* ap = arow + 2 * p;
-                    const float4* bp = bplane + 2 * (by * B.x + bx);
-                    const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
-                    a[u].v[0] = a0.x; a[u].v[1] = a0.y; a[u].v[2] = a0.z; a[u].v[3] = a0.w;
-                    a[u].v[4] = a1.x; a[u].v[5] = a1.y; a[u].v[6] = a1.z; a[u].v[7] = a1.w;
-                    b[u].v[0] = b0.x; b[u].v[1] = b0.y; b[u].v[2] = b0.z; b[u].v[3] = b0.w;
-                    b[u].v[4] = b1.x; b[u].v[5] = b1.y; b[u].v[6] = b1.z; b[u].v[7] = b1.w;
+                    a[u] = ldv<T>(A, arow + p);
+                    b[u] = ldv<T>(B, bplane + by * B.x + bx);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) a[u].v[i] = b[u].v[i] = 0.f;
@@ -395,6 +408,138 @@ wgrad_partial_kernel(DView A, DView B, WgradGeom g, float* __restrict__ partial)
     }
 }
 
+// ------------------------------------------------------------------------------------------- wgrad on the tensor cores
+// bf16 operands (mixed-precision training): the same sum as wgrad_partial_kernel as warp-level MMAs
+// (mma.sync.m16n8k16, bf16 x bf16 -> fp32).  Per tap it is a GEMM  G_tap[a][b] = sum_pos A[a](pos) * B[b](s*pos + tap - pad)
+// with K = positions.  A block owns one tz, a group of <= 48 A channels x <= 40 B channels and a contiguous range of
+// (n, z, y) rows; one warp per in-plane tap holds the whole 48 x 40 fp32 accumulator of its tap (60 registers).  Per
+// row the block stages the A row and the K halo rows of B in shared memory as [chunk][position] 16-byte vectors --
+// exactly the 8 x 8 b16 tiles ldmatrix reads -- and .trans hands every lane the (channel, 2 positions) pairs the
+// fragments want, so no transposed copy of the activations is ever made.  Structural zeros (halo, channel padding,
+// positions past the row end) are zero vectors in shared memory.
+constexpr int kMmaA = 48, kMmaB = 40;      // channels per block: 3 m16 tiles x 5 n8 tiles
+constexpr int kMmaMaxX = 256;
+
+struct WgradMmaGeom {
+    int stride, pad;
+    int pz, py, px;     // A (position) grid
+    int xp;             // px rounded up to 16
+    int bw;             // B positions staged per halo row: stride * (xp - 1) + K
+    int a_groups, b_groups;
+    int a_chunks, b_chunks;   // total chunks of A / B
+    int rows;           // n * pz * py
+};
+
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned (&r)[4], const void* smem_row) {
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(smem_row));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int K>
+__global__ void __launch_bounds__(K * K * 32)
+wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) {
+    extern __shared__ uint4 wg_smem[];
+    uint4* sA = wg_smem;                         // [6 chunks][xp]
+    uint4* sB = wg_smem + 6 * g.xp;              // [K rows][6 chunk slots][bw]  (5 used; slot 5 = zeros for the x4 loads)
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int ty = warp / K, tx = warp % K, tz = blockIdx.z;
+    const int ag = blockIdx.y / g.b_groups, bg = blockIdx.y % g.b_groups;
+    const int ca0 = ag * 6, cb0 = bg * 5;
+    float acc[3][5][4];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int n = 0; n < 5; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
+    const int per = (g.rows + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * per, r1 = min(r0 + per, g.rows);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* Adata = reinterpret_cast<const uint4*>(A.data);
+    const uint4* Bdata = reinterpret_cast<const uint4*>(B.data);
+    const int mat = lane >> 3, jrow = lane & 7;
+    for (int r = r0; r < r1; ++r) {
+        const int y = r % g.py;
+        const int nz = r / g.py;
+        const int z = nz % g.pz, n = nz / g.pz;
+        const int bz = g.stride * z + tz - g.pad;
+        if (bz < 0 || bz >= B.z) continue;                       // block-uniform
+        __syncthreads();
+        for (int i = threadIdx.x; i < 6 * g.xp; i += blockDim.x) {
+            const int c = i / g.xp, x = i - c * g.xp;
+            uint4 v = zero;
+            if (x < g.px && ca0 + c < g.a_chunks) v = __ldg(Adata + vox_index(A, n, ca0 + c, z, y, x));
+            sA[i] = v;
+        }
+        for (int i = threadIdx.x; i < K * 6 * g.bw; i += blockDim.x) {
+            const int pos = i % g.bw;
+            const int rc = i / g.bw;
+            const int c = rc % 6, row = rc / 6;
+            const int by = g.stride * y + row - g.pad, bx = pos - g.pad;
+            uint4 v = zero;
+            if (c < 5 && cb0 + c < g.b_chunks && by >= 0 && by < B.y && bx >= 0 && bx < B.x)
+                v = __ldg(Bdata + vox_index(B, n, cb0 + c, bz, by, bx));
+            sB[i] = v;
+        }
+        __syncthreads();
+        const uint4* brow = sB + static_cast<long long>(ty) * 6 * g.bw;
+        for (int ks = 0; ks < g.xp; ks += 16) {
+            unsigned af[3][4], bf[3][4];
+            // matrices of one x4 load: (chunk 2m, pos 0-7), (chunk 2m+1, pos 0-7), (chunk 2m, pos 8-15), (chunk 2m+1, pos 8-15)
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+                ldmatrix_x4_trans(af[m], sA + (2 * m + (mat & 1)) * g.xp + ks + (mat >> 1) * 8 + jrow);
+            // B: (chunk 2q, pos 0-7), (chunk 2q, pos 8-15), (chunk 2q+1, pos 0-7), (chunk 2q+1, pos 8-15)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                ldmatrix_x4_trans(bf[q], brow + (2 * q + (mat >> 1)) * g.bw + g.stride * (ks + (mat & 1) * 8 + jrow) + tx);
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int nn = 0; nn < 5; ++nn) mma_bf16_16816(acc[m][nn], af[m], bf[nn >> 1][(nn & 1) * 2], bf[nn >> 1][(nn & 1) * 2 + 1]);
+        }
+    }
+    // accumulator fragment: c0,c1 = (row g, cols 2t, 2t+1); c2,c3 = (row g + 8, same cols)
+    const int tap = (tz * K + ty) * K + tx;
+    float* dst = partial + ((static_cast<long long>(blockIdx.x) * (K * K * K) + tap) * gridDim.y + blockIdx.y) * (kMmaA * kMmaB);
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int nn = 0; nn < 5; ++nn) {
+            const int a = m * 16 + gq, b = nn * 8 + 2 * tq;
+            dst[a * kMmaB + b] = acc[m][nn][0];
+            dst[a * kMmaB + b + 1] = acc[m][nn][1];
+            dst[(a + 8) * kMmaB + b] = acc[m][nn][2];
+            dst[(a + 8) * kMmaB + b + 1] = acc[m][nn][3];
+        }
+}
+
+// grad[tap][a][b] (rows a_pad, b_pad) = sum over slices of the per-block 48 x 40 tiles
+__global__ void wgrad_mma_finish_kernel(const float* __restrict__ partial, int slices, int taps, int a_groups, int b_groups,
+                                        int a_pad, int b_pad, float* __restrict__ grad, long long total) {
+    const long long t = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int b = static_cast<int>(t % b_pad);
+    long long r = t / b_pad;
+    const int a = static_cast<int>(r % a_pad);
+    const int tap = static_cast<int>(r / a_pad);
+    const int ag = a / kMmaA, bg = b / kMmaB;
+    const int groups = a_groups * b_groups;
+    const int e = (a - ag * kMmaA) * kMmaB + (b - bg * kMmaB);
+    float s = 0.f;
+    for (int sl = 0; sl < slices; ++sl)
+        s += partial[((static_cast<long long>(sl) * taps + tap) * groups + ag * b_groups + bg) * (kMmaA * kMmaB) + e];
+    grad[t] = s;
+}
+
 // G[tap][ca * 8 + i][cb * 8 + j] = sum over slices, in slice order
 __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int slices, int taps, int pairs, int cb8n,
                                     float* __restrict__ grad, long long total) {
@@ -411,11 +556,8 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int slice
     grad[(static_cast<long long>(tap) * ca8n * 8 + ca * 8 + e / 8) * (cb8n * 8) + cb * 8 + e % 8] = s;
 }
 
-static int check_f32_view(const b200seg_view& v, const char* name) {
-    int rc = validate_view(v, name);
-    if (rc) return rc;
-    B200SEG_CHECK_ARG(v.dtype == B200SEG_F32, "%s: the training kernels take fp32 views", name);
-    return B200SEG_OK;
+static int check_f32_view(const b200seg_view& v, const char* name) {     // fp32 or bf16 (name kept from round 2a)
+    return validate_view(v, name);
 }
 
 static bool same_extent(const b200seg_view& a, const b200seg_view& b) {
@@ -445,7 +587,8 @@ extern "C" int b200seg_channel_moments(b200seg_view x, void* scratch, float* mea
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DView dx = make_dview(x);
     ReduceParams p{};
-    chan_reduce_partial_kernel<0><<<dim3(nblk, c8n), kTrThreads, 0, s>>>(dx, dx, p, static_cast<double*>(scratch), nblk);
+    TRAIN_DISPATCH(x.dtype, (chan_reduce_partial_kernel<T, 0><<<dim3(nblk, c8n), kTrThreads, 0, s>>>(
+                                dx, dx, p, static_cast<double*>(scratch), nblk)));
     const double count = 1.0 * x.n * x.z * x.y * x.x;
     chan_reduce_finish_kernel<<<(c8n * 8 + 127) / 128, 128, 0, s>>>(static_cast<const double*>(scratch), nblk, c8n * 8, count,
                                                                    1, mean, var);
@@ -469,8 +612,10 @@ extern "C" int b200seg_affine_act(b200seg_view src, const float* scale, const fl
     const int c8n = (src.c + 7) / 8;
     const long long total = 1LL * src.n * c8n * src.z * src.y * src.x;
     const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
-    affine_act_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(make_dview(src), scale, shift, slope, dr,
-                                                                                   make_dview(dst), c8n, total);
+    B200SEG_CHECK_ARG(src.dtype == dst.dtype && (residual.data == nullptr || residual.dtype == src.dtype),
+                      "affine_act: views must share one dtype");
+    TRAIN_DISPATCH(src.dtype, (affine_act_kernel<T><<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                  make_dview(src), scale, shift, slope, dr, make_dview(dst), c8n, total)));
     return check_launch("affine_act");
 }
 
@@ -489,14 +634,17 @@ extern "C" int b200seg_bn_backward(b200seg_view dy, b200seg_view z, const float*
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ReduceParams p{scale, shift, slope, mean, rstd};
     DView ddy = make_dview(dy), dzv = make_dview(z);
-    chan_reduce_partial_kernel<1><<<dim3(nblk, c8n), kTrThreads, 0, s>>>(ddy, dzv, p, static_cast<double*>(scratch), nblk);
+    B200SEG_CHECK_ARG(dy.dtype == z.dtype && dy.dtype == dz.dtype, "bn_backward: views must share one dtype");
+    TRAIN_DISPATCH(dy.dtype, (chan_reduce_partial_kernel<T, 1><<<dim3(nblk, c8n), kTrThreads, 0, s>>>(
+                                 ddy, dzv, p, static_cast<double*>(scratch), nblk)));
     chan_reduce_finish_kernel<<<(c8n * 8 + 127) / 128, 128, 0, s>>>(static_cast<const double*>(scratch), nblk, c8n * 8, 1.0, 0,
                                                                    sum_g, sum_gx);
     const double count = 1.0 * dy.n * dy.z * dy.y * dy.x;
     const long long total = 1LL * dy.n * c8n * dy.z * dy.y * dy.x;
     const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
-    bn_backward_apply_kernel<<<blocks, kTrThreads, 0, s>>>(ddy, dzv, p, sum_g, sum_gx, static_cast<float>(1.0 / count),
-                                                           has_norm, make_dview(dz), c8n, total);
+    TRAIN_DISPATCH(dy.dtype, (bn_backward_apply_kernel<T><<<blocks, kTrThreads, 0, s>>>(
+                                 ddy, dzv, p, sum_g, sum_gx, static_cast<float>(1.0 / count), has_norm, make_dview(dz), c8n,
+                                 total)));
     return check_launch("bn_backward");
 }
 
@@ -507,17 +655,70 @@ extern "C" int b200seg_softmax_backward(const float* probs, const float* dprobs,
     B200SEG_CHECK_ARG(probs && dprobs && n == dst.n && c == dst.c, "softmax_backward: bad arguments");
     const long long vox = 1LL * dst.z * dst.y * dst.x, total = vox * n;
     const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
-    softmax_backward_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(probs, dprobs, c, vox, softmax,
-                                                                                         make_dview(dst), total);
+    TRAIN_DISPATCH(dst.dtype, (softmax_backward_kernel<T><<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                  probs, dprobs, c, vox, softmax, make_dview(dst), total)));
     return check_launch("softmax_backward");
 }
 
+static int mma_slices(int groups, int ksize) {
+    int slices = (3 * 148 + groups * ksize - 1) / (groups * ksize);
+    return slices < 1 ? 1 : slices;
+}
+
 extern "C" int64_t b200seg_wgrad_scratch_floats(int32_t a_channels, int32_t b_channels, int32_t ksize) {
-    // at most 1024 slices are ever used
+    // the larger of the two kernels' needs (CUDA-core partials / tensor-core 48 x 40 tiles)
     const int64_t pairs = static_cast<int64_t>((a_channels + 7) / 8) * ((b_channels + 7) / 8);
     int64_t slices = (6 * 148 + pairs * ksize - 1) / (pairs * ksize);
     if (slices < 1) slices = 1;
-    return slices * ksize * ksize * ksize * pairs * 64;
+    const int64_t simt = slices * ksize * ksize * ksize * pairs * 64;
+    const int groups = ((a_channels + kMmaA - 1) / kMmaA) * ((b_channels + kMmaB - 1) / kMmaB);
+    const int64_t mma = static_cast<int64_t>(mma_slices(groups, ksize)) * ksize * ksize * ksize * groups * kMmaA * kMmaB;
+    return simt > mma ? simt : mma;
+}
+
+static int launch_wgrad_mma(const b200seg_view& a, const b200seg_view& b, int ksize, int stride, int pad, float* scratch,
+                            float* grad, cudaStream_t s) {
+    WgradMmaGeom g;
+    g.stride = stride;
+    g.pad = pad;
+    g.pz = a.z;
+    g.py = a.y;
+    g.px = a.x;
+    g.xp = (a.x + 15) / 16 * 16;
+    g.bw = stride * (g.xp - 1) + ksize;
+    g.a_chunks = (a.c + 7) / 8;
+    g.b_chunks = (b.c + 7) / 8;
+    g.a_groups = (g.a_chunks + 5) / 6;
+    g.b_groups = (g.b_chunks + 4) / 5;
+    g.rows = a.n * a.z * a.y;
+    const int groups = g.a_groups * g.b_groups;
+    int slices = mma_slices(groups, ksize);
+    if (slices > g.rows) slices = g.rows;
+    const size_t smem = (6 * static_cast<size_t>(g.xp) + static_cast<size_t>(ksize) * 6 * g.bw) * sizeof(uint4);
+    dim3 grid(slices, groups, ksize);
+    if (ksize == 3) {
+        static bool configured = false;
+        if (!configured) {
+            B200SEG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
+        wgrad_mma_kernel<3><<<grid, 9 * 32, smem, s>>>(make_dview(a), make_dview(b), g, scratch);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            B200SEG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
+        wgrad_mma_kernel<4><<<grid, 16 * 32, smem, s>>>(make_dview(a), make_dview(b), g, scratch);
+    }
+    int rc = check_launch("wgrad (mma partial)");
+    if (rc) return rc;
+    const int taps = ksize * ksize * ksize;
+    const int a_pad = g.a_chunks * 8, b_pad = g.b_chunks * 8;
+    const long long total = 1LL * taps * a_pad * b_pad;
+    wgrad_mma_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(scratch, slices, taps, g.a_groups,
+                                                                                       g.b_groups, a_pad, b_pad, grad, total);
+    return check_launch("wgrad (mma finish)");
 }
 
 extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int32_t stride, int32_t pad, float* scratch,
@@ -528,6 +729,9 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
     if (rc) return rc;
     B200SEG_CHECK_ARG((ksize == 3 || ksize == 4) && stride >= 1 && stride <= 2 && pad >= 0 && scratch && grad && a.n == b.n,
                       "wgrad: bad arguments");
+    static const bool no_mma = getenv("B200SEG_WGRAD_SIMT") != nullptr;      // A/B switch
+    if (a.dtype == B200SEG_BF16 && b.dtype == B200SEG_BF16 && a.x <= kMmaMaxX && !no_mma)
+        return launch_wgrad_mma(a, b, ksize, stride, pad, scratch, grad, static_cast<cudaStream_t>(stream));
     const int ca8n = (a.c + 7) / 8, cb8n = (b.c + 7) / 8, pairs = ca8n * cb8n;
     WgradGeom g;
     g.stride = stride;
@@ -547,10 +751,11 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     dim3 grid(static_cast<unsigned>(slices), pairs, ksize);
     const int halves = 1;      // (two tap-warp groups per block measured slower for K = 3: 14.0 vs 15.5 TFLOP/s)
+    B200SEG_CHECK_ARG(a.dtype == b.dtype, "wgrad: operands must share one dtype");
     if (ksize == 3)
-        wgrad_partial_kernel<3, 1><<<grid, 9 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
+        TRAIN_DISPATCH(a.dtype, (wgrad_partial_kernel<T, 3, 1><<<grid, 9 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch)));
     else
-        wgrad_partial_kernel<4, 1><<<grid, 16 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch);
+        TRAIN_DISPATCH(a.dtype, (wgrad_partial_kernel<T, 4, 1><<<grid, 16 * 32, 0, s>>>(make_dview(a), make_dview(b), g, scratch)));
     rc = check_launch("wgrad (partial)");
     if (rc) return rc;
     const int taps = ksize * ksize * ksize;
@@ -577,8 +782,10 @@ extern "C" int b200seg_avgpool2_backward(b200seg_view dy, b200seg_view add, b200
     const int c8n = (dx.c + 7) / 8;
     const long long total = 1LL * dx.n * c8n * dx.z * dx.y * dx.x;
     const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
-    avgpool2_backward_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(make_dview(dy), dadd, make_dview(dx),
-                                                                                          c8n, total);
+    B200SEG_CHECK_ARG(dy.dtype == dx.dtype && (add.data == nullptr || add.dtype == dx.dtype),
+                      "avgpool2_backward: views must share one dtype");
+    TRAIN_DISPATCH(dx.dtype, (avgpool2_backward_kernel<T><<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                 make_dview(dy), dadd, make_dview(dx), c8n, total)));
     return check_launch("avgpool2_backward");
 }
 
@@ -592,7 +799,8 @@ extern "C" int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_vie
     const int c8n = (dx.c + 7) / 8;
     const long long total = 1LL * dx.n * c8n * dx.z * dx.y * dx.x;
     const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
-    upsample_trilinear2_backward_kernel<<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(make_dview(dy),
-                                                                                                     make_dview(dx), c8n, total);
+    B200SEG_CHECK_ARG(dy.dtype == dx.dtype, "upsample_trilinear2_backward: views must share one dtype");
+    TRAIN_DISPATCH(dx.dtype, (upsample_trilinear2_backward_kernel<T><<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                 make_dview(dy), make_dview(dx), c8n, total)));
     return check_launch("upsample_trilinear2_backward");
 }

@@ -592,6 +592,35 @@ def block_tz(mode: int, j: int, zpar: int) -> int:
 def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) -> torch.Tensor:
     """bf16 operand image for b200seg_conv3d_tc: [pass][image][step][k-half][row][8] with
     row = (plane block j, cout) followed by 16 zero rows; ``phys`` from physical_weight()."""
+    return pack_tc_image(mode, phys, cin_chunks, cout).to(torch.bfloat16).contiguous()
+
+
+_TC_GATHER = {}
+
+
+def tc_gather_index(mode: int, cin_chunks: int, cout: int) -> torch.Tensor:
+    """int64 tensor shaped like the operand image: for every element the flat index into ``phys`` (k, k, k,
+    cin_chunks * 8, round_up(cout, 8)) it is copied from, -1 where the image holds a structural zero.  The packing is
+    a pure gather, so running it once on an index-valued ``phys`` yields the map; the training step, which re-packs
+    every weight after every optimizer step, then packs on the device with one ``take`` (models/_train.py)."""
+    key = (mode, cin_chunks, cout)
+    hit = _TC_GATHER.get(key)
+    if hit is None:
+        k = 3 if mode in (K3, K3T) else 4
+        shape = (k, k, k, cin_chunks * 8, c8(cout) * 8)
+        count = 1
+        for d in shape:
+            count *= d
+        if count >= 1 << 24:
+            raise UnsupportedModule("weight too large for the fp32-exact gather-index trick")
+        marks = torch.arange(1, count + 1, dtype=torch.float32).reshape(shape)
+        hit = pack_tc_image(mode, marks, cin_chunks, cout).to(torch.int64) - 1
+        _TC_GATHER[key] = hit
+    return hit
+
+
+def pack_tc_image(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) -> torch.Tensor:
+    """The operand image of pack_tc_weight in fp32 (before the bf16 rounding)."""
     g = tc_geometry(mode, cin_chunks, cout)
     cpad, nb = g["cpad"], g["nb"]
     img = torch.zeros((g["n_pass"], g["n_bimg"], g["steps_full"], 2, nb, 8), dtype=torch.float32)
@@ -608,7 +637,7 @@ def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) ->
                         for dx in range(3):
                             r0 = j * cpad + (dy * 3 + dx) * cout
                             img[0, 0, grp, half, r0:r0 + cout, :] = phys[2 - j, dy, dx, chunk * 8:(chunk + 1) * 8, :cout].t()
-        return img.to(torch.bfloat16).contiguous()
+        return img
     for ps in range(g["n_pass"]):
         for bi in range(g["n_bimg"]):
             grp = bi % g["groups"]
@@ -631,4 +660,4 @@ def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) ->
                         # (8 cin, Cpad) -> rows = cout, 8 contiguous input channels
                         img[ps, bi, st, half, j * cpad:(j + 1) * cpad, :] = \
                             phys[tz, ty, tx, chunk * 8:(chunk + 1) * 8, :].t()
-    return img.to(torch.bfloat16).contiguous()
+    return img

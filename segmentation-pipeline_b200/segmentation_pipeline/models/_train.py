@@ -26,7 +26,12 @@ with ``Block3d`` blocks (``nn.Conv3d`` / ``WSConv3d`` 3x3x3 convolutions, ``Batc
 ``LeakyReLU`` / no activation, optional residual, ``dropout_p == 0``), ``AvgPool3d(2)`` or ``BlurConv3d`` down- and
 trilinear ``Upsample(2)`` or ``BlurConvTranspose3d`` up-sampling (the class defaults, ``modular_unet.py:38-41``, and the
 msseg2 configuration, ``research/msseg2/msseg2.py:84-93``), 3x3x3 ``out_conv``, ``Softmax(dim=1)`` or
-``Identity`` hypothesis, channel counts that are multiples of 8 wherever tensors are concatenated.  fp32 only."""
+``Identity`` hypothesis, channel counts that are multiples of 8 wherever tensors are concatenated.
+
+Precision follows ``set_precision`` / autocast like the inference path: 'fp32' (default for fp32 modules) is the
+CUDA-core path above; 'bf16' is mixed precision -- forward convolutions and data gradients run on the tcgen05 engine
+(``b200seg_conv3d_tc``, all three geometries) with bf16 activations / activation gradients, while batch statistics,
+weight gradients (fp32 accumulation over bf16 operands), parameters and the optimizer stay fp32."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -207,26 +212,88 @@ def _vec(values: Optional[torch.Tensor], channels: int, fill: float, device) -> 
     return out
 
 
-class _Runner:
-    """State of one training step: buffers kept by the forward for the backward."""
+_TC_INDEX = {}      # (mode, cin_chunks, cout, device) -> (clamped gather index, fp32 mask) on the device
 
-    def __init__(self, spec, device):
+
+def _tc_index(mode, cin_chunks, cout, device):
+    from . import _plan
+    key = (mode, cin_chunks, cout, str(device))
+    hit = _TC_INDEX.get(key)
+    if hit is None:
+        idx = _plan.tc_gather_index(mode, cin_chunks, cout)
+        hit = (idx.clamp(min=0).to(device), (idx >= 0).to(torch.float32).to(device))
+        _TC_INDEX[key] = hit
+    return hit
+
+
+def _sub_view(lib, v, channels, chunk_off):
+    return lib.View(v.data, v.dtype, v.n, channels, v.c8_total, v.c8_off + chunk_off, v.z, v.y, v.x)
+
+
+class _Runner:
+    """State of one training step: buffers kept by the forward for the backward.  ``precision``: 'fp32' (CUDA-core
+    convolutions, fp32 activations) or 'bf16' (mixed precision: tensor-core convolutions for forward and dgrad, bf16
+    activations and activation gradients; statistics, weight gradients, parameters and the optimizer stay fp32)."""
+
+    def __init__(self, spec, device, precision="fp32"):
         self.spec = spec
         self.device = device
+        self.precision = precision
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.lib = _lib()
         self.saved = {}
 
     # -------------------------------------------------------------------------- primitives
     def buffer(self, n, channels, ext):
-        return self.lib.Blocked(n, _pad8(channels) // 8, ext[0], ext[1], ext[2], torch.float32, self.device)
+        return self.lib.Blocked(n, _pad8(channels) // 8, ext[0], ext[1], ext[2], self.dtype, self.device)
 
-    def conv(self, src, weight_packed, cout, dst, bias=None, residual=None, ksize=3, stride=1, pad=1, transposed=False):
+    def conv(self, src, weight_packed, cout, dst, bias=None, residual=None, ksize=3, stride=1, pad=1, transposed=False,
+             out_ncdhw=None, softmax=False):
+        """``weight_packed``: fp32 [k^3][round_up(cin, 8)][round_up(cout, 8)] (``_pack``)."""
         lib = self.lib
+        if self.precision == "bf16":
+            return self._conv_tc(src, weight_packed, cout, dst, bias, residual, ksize, stride, transposed, out_ncdhw,
+                                 softmax)
         one = _vec(None, cout, 1.0, self.device)
         shift = _vec(bias, cout, 0.0, self.device)
-        epi = lib.make_epilogue(one, shift, one, dst, residual=lib.NULL_VIEW if residual is None else residual,
-                                slope01=1)
+        if out_ncdhw is not None:
+            epi = lib.make_epilogue(one, shift, one, out_ncdhw=out_ncdhw, softmax=softmax, slope01=1)
+        else:
+            epi = lib.make_epilogue(one, shift, one, dst, residual=lib.NULL_VIEW if residual is None else residual,
+                                    slope01=1)
         lib.conv3d_direct(src, weight_packed, cout, ksize, stride, pad, transposed, epi)
+
+    def _conv_tc(self, src, phys, cout, dst, bias, residual, ksize, stride, transposed, out_ncdhw, softmax):
+        """The same convolution on the tensor-core engine: the fp32 ``phys`` weight is gathered into the engine's bf16
+        operand image on the device (the weights change every step, so the host-side packer of the inference plan is
+        replaced by one ``take`` through a cached index map), wide outputs are cut into launches of <= 80 channels."""
+        from . import _plan
+        lib = self.lib
+        mode = _plan.K3 if ksize == 3 else (_plan.UP if transposed else _plan.DOWN)
+        cin_chunks = phys.shape[1] // 8
+        out_ext = (src.z, src.y, src.x) if mode == _plan.K3 else \
+            ((src.z * 2, src.y * 2, src.x * 2) if mode == _plan.UP else (src.z // 2, src.y // 2, src.x // 2))
+        limit = 120 if max(out_ext) <= 12 else 80
+        if out_ncdhw is not None:
+            limit = 16
+            if cout <= _plan.K3T_MAX_COUT and cin_chunks <= 12:
+                mode = _plan.K3T
+        for lo in range(0, cout, limit):
+            hi = min(lo + limit, cout)
+            width = _pad8(hi - lo)
+            piece = phys[:, :, lo:lo + width].contiguous().reshape(-1)
+            idx, mask = _tc_index(mode, cin_chunks, hi - lo, self.device)
+            image = (piece[idx] * mask).to(torch.bfloat16).contiguous()
+            one = _vec(None, hi - lo, 1.0, self.device)
+            shift = _vec(None if bias is None else bias[lo:hi], hi - lo, 0.0, self.device)
+            if out_ncdhw is not None:
+                epi = lib.make_epilogue(one, shift, one, out_ncdhw=out_ncdhw, softmax=softmax, slope01=1)
+            else:
+                epi = lib.make_epilogue(one, shift, one, _sub_view(lib, dst, hi - lo, lo // 8),
+                                        residual=lib.NULL_VIEW if residual is None
+                                        else _sub_view(lib, residual, hi - lo, lo // 8),
+                                        slope01=2 if bias is None else 1)
+            lib.conv3d_tc(mode, src, image, hi - lo, epi)
 
     # -------------------------------------------------------------------------- forward
     def block_forward(self, key, bspec, params, src_view, n, ext, dst_buf, dst_off):
@@ -345,10 +412,8 @@ class _Runner:
         probs = torch.empty((n, o["cout"], *ext), dtype=torch.float32, device=self.device)
         w = params[o["w"]].detach()
         bias = None if o["b"] is None else params[o["b"]].detach()
-        one = _vec(None, o["cout"], 1.0, self.device)
-        epi = lib.make_epilogue(one, _vec(bias, o["cout"], 0.0, self.device), one, out_ncdhw=probs,
-                                softmax=spec["softmax"], slope01=1)
-        lib.conv3d_direct(cur, _pack(w.permute(2, 3, 4, 1, 0)), o["cout"], 3, 1, 1, False, epi)
+        self.conv(cur, _pack(w.permute(2, 3, 4, 1, 0)), o["cout"], None, bias=bias, out_ncdhw=probs,
+                  softmax=spec["softmax"])
         self.saved["out_in"] = cur
         self.saved["probs"] = probs
         self.saved["n"], self.saved["ext"], self.saved["exts"] = n, ext, exts
@@ -502,7 +567,8 @@ def forward_train(model, x: torch.Tensor) -> torch.Tensor:
     first = params[0]
     if first.device != x.device or first.dtype != torch.float32:
         raise RuntimeError(f"training: parameters must be fp32 on {x.device}")
-    runner = _Runner(spec, x.device)
+    from . import _engine
+    runner = _Runner(spec, x.device, _engine._resolve_precision(model, x))
     if not torch.is_grad_enabled() or not any(p.requires_grad for p in params):
         with runner.lib.on_device(x):
             probs = runner.forward(x, [p.detach() for p in params])

@@ -15,9 +15,9 @@ def _kernels_vs_torch_inputs(seed, n=2, c=12, ext=(6, 10, 9)):
     return torch.randn(n, c, *ext, generator=g)
 
 
-def _blocked(lib, t):
+def _blocked(lib, t, dtype=torch.float32):
     n, c = t.shape[:2]
-    buf = lib.Blocked(n, (c + 7) // 8, *t.shape[2:], torch.float32, t.device)
+    buf = lib.Blocked(n, (c + 7) // 8, *t.shape[2:], dtype, t.device)
     lib.pack_ncdhw(t.contiguous(), buf.view(c))
     return buf
 
@@ -134,6 +134,41 @@ def test_wgrad_and_dgrad_match_autograd(kind, cin, cout, ext):
     assert float((_unblocked(lib, dx, cin).cpu().double() - x.grad).abs().max()) <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("kind", ["k3", "down", "up"])
+@pytest.mark.parametrize("cin,cout,ext", [(2, 16, (8, 8, 8)), (16, 24, (4, 6, 10)), (40, 40, (12, 12, 12)),
+                                           (80, 40, (6, 20, 36)), (120, 56, (4, 4, 4))])
+def test_tensor_core_wgrad_bf16(kind, cin, cout, ext):
+    """b200seg_wgrad on bf16 views = the mma.sync kernel: bf16-exact inputs, fp32 accumulation -> equal to float64
+    autograd up to fp32 summation error; several channel groups (> 48 / > 40 channels), rows that are not multiples
+    of 16, all three geometries."""
+    import b200seg as lib
+    g = torch.Generator().manual_seed(cin * 100 + cout + 1)
+    n = 2
+    x = torch.randn(n, cin, *ext, generator=g).bfloat16().double().requires_grad_(True)
+    if kind == "k3":
+        w = torch.zeros(cout, cin, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv3d(x, w, padding=1)
+    elif kind == "down":
+        w = torch.zeros(cout, cin, 4, 4, 4, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv3d(x, w, stride=2, padding=1)
+    else:
+        w = torch.zeros(cin, cout, 4, 4, 4, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv_transpose3d(x, w, stride=2, padding=1)
+    dy = torch.randn(y.shape, generator=g).bfloat16().double()
+    y.backward(dy)
+    dev = torch.device("cuda")
+    xb = _blocked(lib, x.detach().float().cuda(), torch.bfloat16)
+    dyb = _blocked(lib, dy.float().cuda(), torch.bfloat16)
+    if kind == "k3":
+        gw = lib.wgrad(dyb.view(cout), xb.view(cin), 3, 1, 1, dev)[:, :cout, :cin].permute(1, 2, 0).reshape(cout, cin, 3, 3, 3)
+    elif kind == "down":
+        gw = lib.wgrad(dyb.view(cout), xb.view(cin), 4, 2, 1, dev)[:, :cout, :cin].permute(1, 2, 0).reshape(cout, cin, 4, 4, 4)
+    else:
+        gw = lib.wgrad(xb.view(cin), dyb.view(cout), 4, 2, 1, dev)[:, :cin, :cout].permute(1, 2, 0).reshape(cin, cout, 4, 4, 4)
+    scale = float(w.grad.abs().max())
+    assert float((gw.cpu().double() - w.grad).abs().max()) <= 2e-5 * scale
+
+
 def _msseg_like(filters, depth, residual=True, act=None):
     from segmentation_pipeline import models as M
     block_params = {"residual": residual}
@@ -206,6 +241,72 @@ def test_training_step_matches_cpu_autograd(filters, depth, residual, act):
     ref_opt.step()
     for (name, p), want in zip(model.named_parameters(), ref_params):
         assert torch.allclose(p.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7), name
+
+
+@pytest.mark.parametrize("filters,depth,residual,blur", [([8, 16], 2, True, True), ([16, 16, 24], 3, True, True),
+                                                        ([8, 16, 24], 3, False, False)])
+def test_mixed_precision_training_step_on_the_tensor_cores(filters, depth, residual, blur):
+    """set_precision('bf16'): forward convolutions and data gradients on the tcgen05 engine, bf16 activations; fp32
+    statistics / weight gradients / parameters.  Against fp32 autograd over the CPU oracle: probabilities within the
+    bf16 tolerance of the inference path (2e-2), loss within 1 %.  Gradients: rounding the stored activations to bf16
+    flips ReLU masks and moves a random-init network's gradients by 5-20 % of their norm -- the CPU oracle shows the
+    same when only its FORWARD activations are rounded (``emulate_bf16``) -- so the bound per parameter is: no further
+    from fp32 than 1.5 x that emulation + 3 % (the bf16 activation gradients of the backward pass)."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    from segmentation_pipeline.models import set_precision
+    torch.manual_seed(5)
+    model = _msseg_like(filters, depth, residual) if blur else M.ModularUNet(2, 2, filters, depth)
+    g = torch.Generator().manual_seed(6)
+    for p in model.parameters():
+        if p.dim() == 1:
+            p.data.add_(0.1 * torch.randn(p.shape, generator=g))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.randn(3, 2, 32, 32, 32, generator=g)
+    labels = (torch.rand(3, 32, 32, 32, generator=g) < 0.3).long()
+    target = torch.nn.functional.one_hot(labels, 2).movedim(-1, 1).float()
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "kernel" not in k)
+              for k, v in sd0.items()}
+    cfg = {"depth": depth, "filters": filters, "down": "blur" if blur else "avgpool", "up": "blur" if blur else "trilinear",
+           "block": {"residual": residual, "bn_training": True}}
+    emu_sd = {k: (v if v.requires_grad else v.clone()) for k, v in ref_sd.items()}    # own running statistics
+    with unet.emulate_bf16():
+        emu_probs = unet.modular_unet_forward(emu_sd, x, cfg)
+    unet.hybrid_logistic_dice_loss(emu_probs, target, logistic_class_weights=[1, 100])["loss"].backward()
+    emulated = {k: v.grad.clone() for k, v in ref_sd.items() if v.grad is not None}
+    for v in ref_sd.values():
+        v.grad = None
+    ref_probs = unet.modular_unet_forward(ref_sd, x, cfg)
+    ref_loss = unet.hybrid_logistic_dice_loss(ref_probs, target, logistic_class_weights=[1, 100])["loss"]
+    ref_loss.backward()
+    model.cuda().train()
+    set_precision("bf16")
+    try:
+        import b200seg
+        launches = b200seg.launches()
+        probs = model(x.cuda())
+        loss = HybridLogisticDiceLoss(logistic_class_weights=[1, 100])(probs, target.cuda())["loss"]
+        loss.backward()
+    finally:
+        set_precision("auto")
+    assert b200seg.launches() > launches
+    assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 2e-2
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        want = ref_sd[name].grad
+        if want is None:
+            assert p.grad is None, name
+            continue
+        err = float((p.grad.cpu() - want).norm()) / (float(want.norm()) + 1e-12)
+        explained = float((emulated[name] - want).norm()) / (float(want.norm()) + 1e-12)
+        assert err <= 1.5 * explained + 3e-2, (name, err, explained)
+        if err > worst[1]:
+            worst = (name, err, explained)
+    print("worst relative gradient error (bf16 mixed precision; CPU forward emulation):", worst)
+    for name, buf in model.named_buffers():
+        if "running" in name:
+            assert torch.allclose(buf.cpu(), ref_sd[name], rtol=2e-2, atol=2e-3), name
 
 
 def test_default_modular_unet_training_step_matches_cpu_autograd():

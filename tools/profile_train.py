@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Times one trainer iteration (segmentation_trainer.py:162-180) of the msseg2 network on the device:
-model.train() forward, HybridLogisticDiceLoss, backward, SGD step.  Usage: profile_train.py [batch] [patch] [steps]."""
+model.train() forward, HybridLogisticDiceLoss, backward, SGD step.
+Usage: profile_train.py [batch] [patch] [steps] [fp32|bf16]."""
 import os
 import sys
 import time
@@ -18,6 +19,8 @@ def main():
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     patch = int(sys.argv[2]) if len(sys.argv) > 2 else 96
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    from segmentation_pipeline.models import set_precision
+    set_precision(sys.argv[4] if len(sys.argv) > 4 else "fp32")
     model = bench.build_model().cuda().train()
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.95)
     criterion = HybridLogisticDiceLoss(logistic_class_weights=[1, 100])
