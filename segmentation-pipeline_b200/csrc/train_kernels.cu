@@ -443,7 +443,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a
 }
 
 template <int K>
-__global__ void __launch_bounds__(K * K * 32)
+__global__ void __launch_bounds__(K * K * 32, K == 3 ? 2 : 1)
 wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) {
     extern __shared__ uint4 wg_smem[];
     uint4* sA = wg_smem;                         // [6 chunks][xp]
@@ -465,31 +465,49 @@ wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) 
     const uint4* Adata = reinterpret_cast<const uint4*>(A.data);
     const uint4* Bdata = reinterpret_cast<const uint4*>(B.data);
     const int mat = lane >> 3, jrow = lane & 7;
+    const int nwarps = K * K;
+    // Everything that is structurally zero (halo columns, positions past the row end, missing chunks, the sixth B slot)
+    // is written once; per row only the data sections [0, px) of A and [pad, pad + B.x) of the NEW halo rows of B are
+    // copied, one contiguous global line per warp trip (first version: per-vector index arithmetic in the staging loop
+    // cost twice the instructions of the MMA loop).  The K halo rows live in a ring: row by sits in slot (by + pad) % K,
+    // so stepping y by one loads `stride` new rows instead of K.
+    for (int i = threadIdx.x; i < 6 * g.xp + K * 6 * g.bw; i += blockDim.x) wg_smem[i] = zero;
+    const int na = min(6, g.a_chunks - ca0), nb = min(5, g.b_chunks - cb0);
+    int key = -1, staged_hi = 0;                                  // (n, z) of the rows in the ring; highest staged by
     for (int r = r0; r < r1; ++r) {
         const int y = r % g.py;
         const int nz = r / g.py;
         const int z = nz % g.pz, n = nz / g.pz;
         const int bz = g.stride * z + tz - g.pad;
         if (bz < 0 || bz >= B.z) continue;                       // block-uniform
-        __syncthreads();
-        for (int i = threadIdx.x; i < 6 * g.xp; i += blockDim.x) {
-            const int c = i / g.xp, x = i - c * g.xp;
-            uint4 v = zero;
-            if (x < g.px && ca0 + c < g.a_chunks) v = __ldg(Adata + vox_index(A, n, ca0 + c, z, y, x));
-            sA[i] = v;
+        const int lo = g.stride * y - g.pad, hi = lo + K - 1;
+        int first_new = lo;
+        if (key == nz && staged_hi >= lo) first_new = staged_hi + 1;
+        key = nz;
+        staged_hi = hi;
+        const int new_rows = hi - first_new + 1;
+        __syncthreads();                                          // every warp is done with the previous row
+        const int lines = na + new_rows * nb;
+        for (int line = warp; line < lines; line += nwarps) {
+            if (line < na) {
+                const uint4* src = Adata + vox_index(A, n, ca0 + line, z, y, 0);
+                uint4* dst = sA + line * g.xp;
+                for (int x = lane; x < g.px; x += 32) dst[x] = __ldg(src + x);
+            } else {
+                const int q = line - na;
+                const int rr = q / nb, c = q - rr * nb;
+                const int by = first_new + rr;
+                uint4* dst = sB + (((by + g.pad) % K) * 6 + c) * g.bw + g.pad;
+                if (by >= 0 && by < B.y) {
+                    const uint4* src = Bdata + vox_index(B, n, cb0 + c, bz, by, 0);
+                    for (int x = lane; x < B.x; x += 32) dst[x] = __ldg(src + x);
+                } else {
+                    for (int x = lane; x < B.x; x += 32) dst[x] = zero;
+                }
+            }
         }
-        for (int i = threadIdx.x; i < K * 6 * g.bw; i += blockDim.x) {
-            const int pos = i % g.bw;
-            const int rc = i / g.bw;
-            const int c = rc % 6, row = rc / 6;
-            const int by = g.stride * y + row - g.pad, bx = pos - g.pad;
-            uint4 v = zero;
-            if (c < 5 && cb0 + c < g.b_chunks && by >= 0 && by < B.y && bx >= 0 && bx < B.x)
-                v = __ldg(Bdata + vox_index(B, n, cb0 + c, bz, by, bx));
-            sB[i] = v;
-        }
         __syncthreads();
-        const uint4* brow = sB + static_cast<long long>(ty) * 6 * g.bw;
+        const uint4* brow = sB + static_cast<long long>((g.stride * y + ty) % K) * 6 * g.bw;
         for (int ks = 0; ks < g.xp; ks += 16) {
             unsigned af[3][4], bf[3][4];
             // matrices of one x4 load: (chunk 2m, pos 0-7), (chunk 2m+1, pos 0-7), (chunk 2m, pos 8-15), (chunk 2m+1, pos 8-15)

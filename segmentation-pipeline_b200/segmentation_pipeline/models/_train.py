@@ -200,15 +200,29 @@ def build_spec(model):
 def _pack(t: torch.Tensor) -> torch.Tensor:
     """(k, k, k, in, out) -> fp32 [k^3][round_up(in, 8)][round_up(out, 8)] for b200seg_conv3d_direct."""
     k, cin, cout = t.shape[0], t.shape[3], t.shape[4]
+    if cin % 8 == 0 and cout % 8 == 0:
+        return t.reshape(k ** 3, cin, cout).to(torch.float32).contiguous()
     out = torch.zeros((k ** 3, _pad8(cin), _pad8(cout)), dtype=torch.float32, device=t.device)
     out[:, :cin, :cout] = t.reshape(k ** 3, cin, cout)
     return out
 
 
+_CONST_VEC = {}
+
+
 def _vec(values: Optional[torch.Tensor], channels: int, fill: float, device) -> torch.Tensor:
+    """fp32 vector of length round_up(channels, 8): ``values`` padded with ``fill`` (constant vectors are cached: a
+    training step asks for a few hundred of them)."""
+    if values is None:
+        key = (_pad8(channels), float(fill), str(device))
+        hit = _CONST_VEC.get(key)
+        if hit is None:
+            hit = _CONST_VEC[key] = torch.full((_pad8(channels),), fill, dtype=torch.float32, device=device)
+        return hit
+    if channels == _pad8(channels):
+        return values.to(torch.float32).contiguous()
     out = torch.full((_pad8(channels),), fill, dtype=torch.float32, device=device)
-    if values is not None:
-        out[:channels] = values
+    out[:channels] = values
     return out
 
 

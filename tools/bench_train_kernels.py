@@ -27,12 +27,13 @@ def timed(fn, reps=3):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     e = int(sys.argv[2]) if len(sys.argv) > 2 else 96
+    dtype = torch.bfloat16 if (len(sys.argv) > 3 and sys.argv[3] == "bf16") else torch.float32
     dev = torch.device("cuda")
     lib.load_library()
-    runner = _train._Runner({}, dev)
+    runner = _train._Runner({}, dev, "bf16" if dtype == torch.bfloat16 else "fp32")
 
     def buf(c, ext):
-        b = lib.Blocked(n, (c + 7) // 8, ext, ext, ext, torch.float32, dev)
+        b = lib.Blocked(n, (c + 7) // 8, ext, ext, ext, dtype, dev)
         b.tensor.normal_()
         return b
 
@@ -55,7 +56,7 @@ def main():
     print(f"wgrad up   40->40 @{e}^3 x{n}: {ms:8.2f} ms  {2 * vox / 8 * 64 * 1600 / ms / 1e9:7.1f} TFLOP/s")
     z, dy, dzb = buf(40, e), buf(40, e), buf(40, e)
     vec = lambda v: torch.full((40,), v, device=dev)
-    bytes_t = vox * 40 * 4
+    bytes_t = vox * 40 * (2 if dtype == torch.bfloat16 else 4)
     ms = timed(lambda: lib.bn_backward(dy.view(40), z.view(40), vec(1.0), vec(0.0), vec(0.0), vec(0.0), vec(1.0), True,
                                        dzb.view(40), 40, dev))
     print(f"bn_backward 40ch: {ms:8.2f} ms  {5 * bytes_t / ms / 1e6:7.1f} GB/s (2 reads + 2 reads + 1 write)")
