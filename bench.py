@@ -575,13 +575,29 @@ TRAIN_WORKLOAD = ("config5: one trainer iteration (segmentation_trainer.py:162-1
                   "DistributedDataParallel gradient all-reduce over NCCL")
 
 
+class _StdoutToStderr:
+    """fd-level redirect: NCCL writes its version banner to fd 1 when DistributedDataParallel creates its communicator;
+    the bench contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_train_section(world: int, rank: int, local: int, device, steps: int = 3, warmup: int = 1) -> dict:
     """BASELINE config 5 in both precisions of the training step: 'fp32' (the reference's arithmetic: CUDA-core
     convolutions) and 'bf16' (mixed precision: forward and dgrad on the tcgen05 engine, fp32 statistics / wgrad /
     parameters)."""
     out = {"workload": TRAIN_WORKLOAD}
-    for precision in ("fp32", "bf16"):
-        out[precision] = _run_train(world, rank, local, device, precision, steps, warmup)
+    with _StdoutToStderr():
+        for precision in ("fp32", "bf16"):
+            out[precision] = _run_train(world, rank, local, device, precision, steps, warmup)
     return out
 
 
