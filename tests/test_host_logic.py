@@ -162,3 +162,46 @@ def test_c_abi_exports_every_declared_symbol():
         g = _plan.tc_geometry(mode, chunks, cout)
         assert lib.b200seg_conv3d_tc_wbytes(mode, chunks, cout) == g["n_pass"] * g["n_bimg"] * g["bimg_elems"] * 2
     assert lib.b200seg_conv3d_tc_wbytes(_plan.K3T, 5, 5) == -1       # K3T serves at most 4 output channels
+
+
+def test_training_spec_of_the_msseg2_network_and_refusals():
+    """Host side of the training step (models/_train.py): the layer list and the flat parameter list autograd sees;
+    the effective (blurred / standardised) weights are differentiable expressions of the module's parameters; module
+    configurations outside the lowered space raise instead of falling back."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.models import _train
+    model = M.ModularUNet(2, 2, [40, 40, 80, 80, 120, 120], 6, block_params={"residual": True},
+                          downsample_class=M.BlurConv3d, downsample_params={"kernel_size": 3, "stride": 2, "padding": 1},
+                          upsample_class=M.BlurConvTranspose3d,
+                          upsample_params={"kernel_size": 3, "stride": 2, "padding": 1, "output_padding": 0})
+    spec, params = _train.build_spec(model)
+    assert spec["depth"] == 6 and len(spec["down"]) == 6 and len(spec["up"]) == 5
+    assert [d["cout"] for d in spec["downs"]] == [40, 40, 80, 80, 120] and spec["ups"][0]["cin"] == 40
+    assert spec["up"][4]["cin"] == 240 and spec["out"]["cout"] == 2 and spec["softmax"]
+    # every parameter the reference's forward uses is reachable from the flat list (blur-conv biases are not: never applied)
+    loss = sum((p.float() ** 2).sum() for p in params)
+    loss.backward()
+    unused = [n for n, p in model.named_parameters() if p.grad is None]
+    assert sorted(unused) == sorted([f"downsampling.{i}.bias" for i in range(5)] + [f"upsampling.{i}.bias" for i in range(5)])
+    blurred = params[spec["downs"][0]["w"]]
+    assert blurred.shape == (40, 40, 4, 4, 4) and blurred.requires_grad and not blurred.is_leaf
+    with pytest.raises(NotImplementedError):
+        _train.build_spec(M.NestedResUNet(1, 2, 8))
+    with pytest.raises(NotImplementedError):
+        _train.build_spec(M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.5}))
+    with pytest.raises(NotImplementedError):
+        _train.build_spec(M.ModularUNet(1, 2, [12, 12], 2))          # concatenated widths must be multiples of 8
+    default = _train.build_spec(M.ModularUNet(1, 2, [8, 16], 2))[0]
+    assert default["downs"][0]["w"] is None and default["ups"][0]["w"] is None       # AvgPool3d / trilinear Upsample
+
+
+def test_tc_gather_index_reproduces_the_host_packer():
+    """The training step packs tensor-core operand images on the device through a cached gather index."""
+    from segmentation_pipeline.models import _plan
+    for mode, k, cin_chunks, cout in ((_plan.K3, 3, 5, 40), (_plan.K3, 3, 1, 80), (_plan.DOWN, 4, 10, 80),
+                                      (_plan.UP, 4, 15, 120), (_plan.K3T, 3, 5, 2)):
+        phys = torch.randn(k, k, k, cin_chunks * 8, _plan.c8(cout) * 8)
+        want = _plan.pack_tc_weight(mode, phys, cin_chunks, cout)
+        idx = _plan.tc_gather_index(mode, cin_chunks, cout)
+        got = torch.where(idx >= 0, phys.reshape(-1)[idx.clamp(min=0)], torch.zeros(())).to(torch.bfloat16)
+        assert got.shape == want.shape and bool((got == want).all())
