@@ -92,7 +92,8 @@ def test_softmax_backward(softmax):
 
 
 @pytest.mark.parametrize("kind", ["k3", "down", "up"])
-@pytest.mark.parametrize("cin,cout,ext", [(2, 16, (8, 8, 8)), (16, 24, (4, 6, 10)), (40, 40, (12, 12, 12))])
+@pytest.mark.parametrize("cin,cout,ext", [(2, 16, (8, 8, 8)), (16, 24, (4, 6, 10)), (40, 40, (12, 12, 12)),
+                                           (8, 16, (32, 32, 32)), (16, 8, (16, 16, 16)), (16, 16, (20, 36, 68))])
 def test_wgrad_and_dgrad_match_autograd(kind, cin, cout, ext):
     """Weight and data gradients of the three convolution geometries vs torch.autograd (float64 on the CPU)."""
     import b200seg as lib
