@@ -442,7 +442,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int K>
+// MT / NT: m16 / n8 tiles actually computed (3 x 5 in general; 1 when the A / B group holds at most 2 / 1 chunks -- the
+// first layer's 2-channel input and the 2-class logits would otherwise spend 2/3 resp. 4/5 of their MMAs on zeros)
+template <int K, int MT, int NT>
 __global__ void __launch_bounds__(K * K * 32, K == 3 ? 2 : 1)
 wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) {
     extern __shared__ uint4 wg_smem[];
@@ -452,11 +454,11 @@ wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) 
     const int ty = warp / K, tx = warp % K, tz = blockIdx.z;
     const int ag = blockIdx.y / g.b_groups, bg = blockIdx.y % g.b_groups;
     const int ca0 = ag * 6, cb0 = bg * 5;
-    float acc[3][5][4];
+    float acc[MT][NT][4];
 #pragma unroll
-    for (int m = 0; m < 3; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int n = 0; n < 5; ++n)
+        for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
     const int per = (g.rows + gridDim.x - 1) / gridDim.x;
@@ -509,19 +511,19 @@ wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) 
         __syncthreads();
         const uint4* brow = sB + static_cast<long long>((g.stride * y + ty) % K) * 6 * g.bw;
         for (int ks = 0; ks < g.xp; ks += 16) {
-            unsigned af[3][4], bf[3][4];
+            unsigned af[MT][4], bf[(NT + 1) / 2][4];
             // matrices of one x4 load: (chunk 2m, pos 0-7), (chunk 2m+1, pos 0-7), (chunk 2m, pos 8-15), (chunk 2m+1, pos 8-15)
 #pragma unroll
-            for (int m = 0; m < 3; ++m)
+            for (int m = 0; m < MT; ++m)
                 ldmatrix_x4_trans(af[m], sA + (2 * m + (mat & 1)) * g.xp + ks + (mat >> 1) * 8 + jrow);
             // B: (chunk 2q, pos 0-7), (chunk 2q, pos 8-15), (chunk 2q+1, pos 0-7), (chunk 2q+1, pos 8-15)
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
+            for (int q = 0; q < (NT + 1) / 2; ++q)
                 ldmatrix_x4_trans(bf[q], brow + (2 * q + (mat >> 1)) * g.bw + g.stride * (ks + (mat & 1) * 8 + jrow) + tx);
 #pragma unroll
-            for (int m = 0; m < 3; ++m)
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
-                for (int nn = 0; nn < 5; ++nn) mma_bf16_16816(acc[m][nn], af[m], bf[nn >> 1][(nn & 1) * 2], bf[nn >> 1][(nn & 1) * 2 + 1]);
+                for (int nn = 0; nn < NT; ++nn) mma_bf16_16816(acc[m][nn], af[m], bf[nn >> 1][(nn & 1) * 2], bf[nn >> 1][(nn & 1) * 2 + 1]);
         }
     }
     // accumulator fragment: c0,c1 = (row g, cols 2t, 2t+1); c2,c3 = (row g + 8, same cols)
@@ -533,10 +535,11 @@ wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) 
 #pragma unroll
         for (int nn = 0; nn < 5; ++nn) {
             const int a = m * 16 + gq, b = nn * 8 + 2 * tq;
-            dst[a * kMmaB + b] = acc[m][nn][0];
-            dst[a * kMmaB + b + 1] = acc[m][nn][1];
-            dst[(a + 8) * kMmaB + b] = acc[m][nn][2];
-            dst[(a + 8) * kMmaB + b + 1] = acc[m][nn][3];
+            const bool live = m < MT && nn < NT;
+            dst[a * kMmaB + b] = live ? acc[m < MT ? m : 0][nn < NT ? nn : 0][0] : 0.f;
+            dst[a * kMmaB + b + 1] = live ? acc[m < MT ? m : 0][nn < NT ? nn : 0][1] : 0.f;
+            dst[(a + 8) * kMmaB + b] = live ? acc[m < MT ? m : 0][nn < NT ? nn : 0][2] : 0.f;
+            dst[(a + 8) * kMmaB + b + 1] = live ? acc[m < MT ? m : 0][nn < NT ? nn : 0][3] : 0.f;
         }
 }
 
@@ -714,21 +717,27 @@ static int launch_wgrad_mma(const b200seg_view& a, const b200seg_view& b, int ks
     if (slices > g.rows) slices = g.rows;
     const size_t smem = (6 * static_cast<size_t>(g.xp) + static_cast<size_t>(ksize) * 6 * g.bw) * sizeof(uint4);
     dim3 grid(slices, groups, ksize);
+    const bool one_m = g.a_chunks <= 2, one_n = g.b_chunks <= 1;      // a single group then, too
+#define B200SEG_WGRAD_MMA(KK, MT, NT)                                                                                   \
+    do {                                                                                                               \
+        static bool configured = false;                                                                                \
+        if (!configured) {                                                                                             \
+            B200SEG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<KK, MT, NT>,                                       \
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));         \
+            configured = true;                                                                                         \
+        }                                                                                                              \
+        wgrad_mma_kernel<KK, MT, NT><<<grid, KK * KK * 32, smem, s>>>(make_dview(a), make_dview(b), g, scratch);        \
+    } while (0)
     if (ksize == 3) {
-        static bool configured = false;
-        if (!configured) {
-            B200SEG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = true;
-        }
-        wgrad_mma_kernel<3><<<grid, 9 * 32, smem, s>>>(make_dview(a), make_dview(b), g, scratch);
+        if (one_m) B200SEG_WGRAD_MMA(3, 1, 5);
+        else if (one_n) B200SEG_WGRAD_MMA(3, 3, 1);
+        else B200SEG_WGRAD_MMA(3, 3, 5);
     } else {
-        static bool configured = false;
-        if (!configured) {
-            B200SEG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = true;
-        }
-        wgrad_mma_kernel<4><<<grid, 16 * 32, smem, s>>>(make_dview(a), make_dview(b), g, scratch);
+        if (one_m) B200SEG_WGRAD_MMA(4, 1, 5);
+        else if (one_n) B200SEG_WGRAD_MMA(4, 3, 1);
+        else B200SEG_WGRAD_MMA(4, 3, 5);
     }
+#undef B200SEG_WGRAD_MMA
     int rc = check_launch("wgrad (mma partial)");
     if (rc) return rc;
     const int taps = ksize * ksize * ksize;
