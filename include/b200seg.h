@@ -290,8 +290,11 @@ int b200seg_hybrid_loss_backward(const float* prediction, const float* target, c
  *                        B = dy, k 4, stride 2, pad 1.  scratch: wgrad_scratch_floats() floats.
  *   avgpool2_backward / upsample_trilinear2_backward   adjoints of nn.AvgPool3d(2) (dx = dy(v/2)/8 + add) and of
  *                        nn.Upsample(scale_factor=2, 'trilinear', align_corners=True) (modular_unet.py:38-41), the
- *                        latter as a deterministic gather with the forward kernel's coefficients */
+ *                        latter as a deterministic gather with the forward kernel's coefficients
+ *   channel_scale        dst = src * mask[n][c] (mask: fp32 [N][round_up(C, 8)]): nn.Dropout3d forward / backward with the
+ *                        mask the host drew (components.py:70-71, nested_residual_unet.py:44-45) */
 int64_t b200seg_train_scratch_bytes(int32_t channels);
+int b200seg_channel_scale(b200seg_view src, const float* mask, b200seg_view dst, void* stream);
 int b200seg_avgpool2_backward(b200seg_view dy, b200seg_view add, b200seg_view dx, void* stream);
 int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_view dx, void* stream);
 int b200seg_channel_moments(b200seg_view x, void* scratch, float* mean, float* var, void* stream);

@@ -206,16 +206,23 @@ def modular_unet_forward(sd: SD, x: torch.Tensor, cfg: dict) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------- NestedResUNet
-def _nested_block(x, sd: SD, name: str, residual: bool):
-    """NestedResUNet.Block.forward, models/nested_residual_unet.py:30-47."""
+def _nested_block(x, sd: SD, name: str, residual: bool, cfg: Optional[dict] = None):
+    """NestedResUNet.Block.forward, models/nested_residual_unet.py:30-47.  ``cfg['bn_training']``: batch-statistic
+    BatchNorm (``model.train()``); ``cfg['dropout_masks'][name]``: the (N, C) multiplier nn.Dropout3d drew for this
+    block (0 or 1 / (1 - p) per sample and channel), applied after the residual add (:44-45)."""
+    cfg = cfg or {}
+    bn = batch_norm_train if cfg.get("bn_training", False) else batch_norm_eval
     x_in = x
     x = F.conv3d(_q(x), _q(sd[f"{name}.conv1.weight"]), None, padding=1)
-    x = _q(F.relu(batch_norm_eval(x, sd, f"{name}.bn1.")))
+    x = _q(F.relu(bn(x, sd, f"{name}.bn1.")))
     x = F.conv3d(x, _q(sd[f"{name}.conv2.weight"]), None, padding=1)
-    x = F.relu(batch_norm_eval(x, sd, f"{name}.bn2."))
+    x = F.relu(bn(x, sd, f"{name}.bn2."))
     if residual:
         r = F.conv3d(_q(x_in), _q(sd[f"{name}.res_conv.weight"]), sd[f"{name}.res_conv.bias"], padding=1)
-        return _q(_q(r) + x)
+        x = _q(r) + x
+    mask = (cfg.get("dropout_masks") or {}).get(name)
+    if mask is not None:
+        x = x * mask.reshape(*mask.shape, 1, 1, 1)
     return _q(x)
 
 
@@ -225,16 +232,16 @@ def nested_res_unet_forward(sd: SD, x: torch.Tensor, cfg: Optional[dict] = None)
     cfg = cfg or {}
     down = lambda t: _q(F.avg_pool3d(t, 2, 2, count_include_pad=False))
     up = lambda t: _q(F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=True))
-    x0_0 = _nested_block(x, sd, "conv0_0", True)
-    x1_0 = _nested_block(down(x0_0), sd, "conv1_0", False)
-    x0_1 = _nested_block(torch.cat((x0_0, up(x1_0)), 1), sd, "conv0_1", True)
-    x2_0 = _nested_block(down(x1_0), sd, "conv2_0", False)
-    x1_1 = _nested_block(torch.cat((x1_0, up(x2_0), down(x0_1)), 1), sd, "conv1_1", False)
-    x0_2 = _nested_block(torch.cat((x0_1, up(x1_1)), 1), sd, "conv0_2", True)
-    x3_0 = _nested_block(down(x2_0), sd, "conv3_0", False)
-    x2_1 = _nested_block(torch.cat((x2_0, up(x3_0), down(x1_1)), 1), sd, "conv2_1", False)
-    x1_2 = _nested_block(torch.cat((x1_1, up(x2_1), down(x0_2)), 1), sd, "conv1_2", False)
-    x0_3 = _nested_block(torch.cat((x0_2, up(x1_2)), 1), sd, "conv0_3", True)
+    x0_0 = _nested_block(x, sd, "conv0_0", True, cfg)
+    x1_0 = _nested_block(down(x0_0), sd, "conv1_0", False, cfg)
+    x0_1 = _nested_block(torch.cat((x0_0, up(x1_0)), 1), sd, "conv0_1", True, cfg)
+    x2_0 = _nested_block(down(x1_0), sd, "conv2_0", False, cfg)
+    x1_1 = _nested_block(torch.cat((x1_0, up(x2_0), down(x0_1)), 1), sd, "conv1_1", False, cfg)
+    x0_2 = _nested_block(torch.cat((x0_1, up(x1_1)), 1), sd, "conv0_2", True, cfg)
+    x3_0 = _nested_block(down(x2_0), sd, "conv3_0", False, cfg)
+    x2_1 = _nested_block(torch.cat((x2_0, up(x3_0), down(x1_1)), 1), sd, "conv2_1", False, cfg)
+    x1_2 = _nested_block(torch.cat((x1_1, up(x2_1), down(x0_2)), 1), sd, "conv1_2", False, cfg)
+    x0_3 = _nested_block(torch.cat((x0_2, up(x1_2)), 1), sd, "conv0_3", True, cfg)
     if cfg.get("return_features", False):
         return x0_3                 # input of out_conv (tests fit a linear read-out on it)
     x_out = F.conv3d(_q(x0_3), _q(sd["out_conv.weight"]), sd["out_conv.bias"], padding=1)

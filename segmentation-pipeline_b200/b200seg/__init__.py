@@ -84,6 +84,7 @@ _SIGNATURES = {
     "b200seg_softmax_backward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, View, c_void_p]),
     "b200seg_wgrad_scratch_floats": (c_int64, [c_int32, c_int32, c_int32]),
     "b200seg_wgrad": (c_int32, [View, View, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200seg_channel_scale": (c_int32, [View, c_void_p, View, c_void_p]),
     "b200seg_avgpool2_backward": (c_int32, [View, View, View, c_void_p]),
     "b200seg_upsample_trilinear2_backward": (c_int32, [View, View, c_void_p]),
     "b200seg_window_patches": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
@@ -666,3 +667,11 @@ def avgpool2_backward(dy: View, dx: View, add: View = NULL_VIEW) -> None:
 def upsample_trilinear2_backward(dy: View, dx: View) -> None:
     _LAUNCHES[0] += 1
     _check(load_library().b200seg_upsample_trilinear2_backward(dy, dx, _stream()), "upsample_trilinear2_backward")
+
+
+def channel_scale(src: View, mask: torch.Tensor, dst: View) -> None:
+    """dst = src * mask[n][c]; mask fp32 (N, round_up(C, 8)) on the device (Dropout3d)."""
+    _require_cuda(mask)
+    assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.dim() == 2
+    _LAUNCHES[0] += 1
+    _check(load_library().b200seg_channel_scale(src, _ptr(mask), dst, _stream()), "channel_scale")

@@ -155,6 +155,22 @@ affine_act_kernel(DView src, const float* __restrict__ scale, const float* __res
     store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, a);
 }
 
+// nn.Dropout3d (forward and backward are the same map): dst = src * mask[n][c], mask = 0 or 1 / (1 - p) per (sample, channel)
+template <typename T>
+__global__ void __launch_bounds__(kTrThreads)
+channel_scale_kernel(DView src, const float* __restrict__ mask, int mask_stride, DView dst, int c8n, long long total) {
+    const long long t = blockIdx.x * 1LL * kTrThreads + threadIdx.x;
+    if (t >= total) return;
+    const long long v = t % src.chunk_stride;
+    const long long r = t / src.chunk_stride;
+    const int cc = static_cast<int>(r % c8n);
+    const long long n = r / c8n;
+    Vec8 a = ldv<T>(src, n * src.sample_stride + (src.c8_off + cc) * src.chunk_stride + v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] *= __ldg(mask + n * mask_stride + cc * 8 + j);
+    store_vec8<T>(dst.data, n * dst.sample_stride + (dst.c8_off + cc) * dst.chunk_stride + v, a);
+}
+
 // dz = has_norm ? scale * (g - c1 - xhat * c2) : g,   g = dy * act'(scale * z + shift); c1 = sum g / M, c2 = sum g xhat / M
 template <typename T>
 __global__ void __launch_bounds__(kTrThreads)
@@ -830,4 +846,18 @@ extern "C" int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_vie
     TRAIN_DISPATCH(dx.dtype, (upsample_trilinear2_backward_kernel<T><<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
                                  make_dview(dy), make_dview(dx), c8n, total)));
     return check_launch("upsample_trilinear2_backward");
+}
+
+extern "C" int b200seg_channel_scale(b200seg_view src, const float* mask, b200seg_view dst, void* stream) {
+    int rc = check_f32_view(src, "channel_scale src");
+    if (rc) return rc;
+    rc = check_f32_view(dst, "channel_scale dst");
+    if (rc) return rc;
+    B200SEG_CHECK_ARG(mask && same_extent(src, dst) && src.dtype == dst.dtype, "channel_scale: bad arguments");
+    const int c8n = (src.c + 7) / 8;
+    const long long total = 1LL * src.n * c8n * src.z * src.y * src.x;
+    const unsigned blocks = static_cast<unsigned>((total + kTrThreads - 1) / kTrThreads);
+    TRAIN_DISPATCH(src.dtype, (channel_scale_kernel<T><<<blocks, kTrThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                  make_dview(src), mask, c8n * 8, make_dview(dst), c8n, total)));
+    return check_launch("channel_scale");
 }

@@ -21,9 +21,10 @@ derivatives by itself; everything that touches activations is a libb200seg kerne
             (flipped taps for 3x3x3; the strided conv's adjoint is the transposed geometry and vice versa), the
             two branches of a residual block / a skip connection summed through the convolution's residual epilogue.
 
-Supported module space (anything else raises ``NotImplementedError`` -- never a silent ATen fallback): ``ModularUNet``
-with ``Block3d`` blocks (``nn.Conv3d`` / ``WSConv3d`` 3x3x3 convolutions, ``BatchNorm3d`` or no norm, ``ReLU`` /
-``LeakyReLU`` / no activation, optional residual, ``dropout_p == 0``), ``AvgPool3d(2)`` or ``BlurConv3d`` down- and
+Supported module space (anything else raises ``NotImplementedError`` -- never a silent ATen fallback):
+``NestedResUNet`` (``nested_residual_unet.py:49-106``, run as a small tape because its skip tensors have several
+consumers) and ``ModularUNet`` with ``Block3d`` blocks (``nn.Conv3d`` / ``WSConv3d`` 3x3x3 convolutions, ``BatchNorm3d`` or
+no norm, ``ReLU`` / ``LeakyReLU`` / no activation, optional residual, ``Dropout3d``), ``AvgPool3d(2)`` or ``BlurConv3d`` down- and
 trilinear ``Upsample(2)`` or ``BlurConvTranspose3d`` up-sampling (the class defaults, ``modular_unet.py:38-41``, and the
 msseg2 configuration, ``research/msseg2/msseg2.py:84-93``), 3x3x3 ``out_conv``, ``Softmax(dim=1)`` or
 ``Identity`` hypothesis, channel counts that are multiples of 8 wherever tensors are concatenated.
@@ -108,8 +109,6 @@ def _block_spec(block, params):
     from .components import Block3d
     if not isinstance(block, Block3d):
         raise Unsupported(f"training: block class {type(block).__name__} is not lowered")
-    if block.dropout is not None:
-        raise Unsupported("training: Dropout3d is not lowered (dropout_p must be 0)")
     convs = []
     names = list(block.layers._modules.keys())
     index = 0
@@ -134,17 +133,64 @@ def _block_spec(block, params):
     if block.residual:
         wi, bi = _effective_conv_weight(block.res_conv, params)
         res = {"w": wi, "b": bi}
-    return {"convs": convs, "res": res, "cin": convs[0]["cin"], "cout": convs[-1]["cout"]}
+    return {"convs": convs, "res": res, "cin": convs[0]["cin"], "cout": convs[-1]["cout"],
+            "dropout_p": 0.0 if block.dropout is None else float(block.dropout.p)}
+
+
+def _nested_block_spec(block, params):
+    """NestedResUNet.Block (nested_residual_unet.py:7-47): conv1-bn1-relu, conv2-bn2-relu, optional res_conv, dropout."""
+    convs = []
+    for conv, norm in ((block.conv1, block.bn1), (block.conv2, block.bn2)):
+        wi, bi = _effective_conv_weight(conv, params)
+        params.append(norm.weight)
+        params.append(norm.bias)
+        convs.append({"w": wi, "b": bi, "cin": conv.in_channels, "cout": conv.out_channels, "slope": 0.0,
+                      "norm": {"g": len(params) - 2, "b": len(params) - 1, "module": norm}})
+    res = None
+    if block.residual:
+        wi, bi = _effective_conv_weight(block.res_conv, params)
+        res = {"w": wi, "b": bi}
+    return {"convs": convs, "res": res, "cin": convs[0]["cin"], "cout": convs[-1]["cout"],
+            "dropout_p": 0.0 if block.dropout is None else float(block.dropout.p)}
+
+
+NESTED_BLOCKS = ("conv0_0", "conv1_0", "conv0_1", "conv2_0", "conv1_1", "conv0_2", "conv3_0", "conv2_1", "conv1_2", "conv0_3")
+
+
+def build_nested_spec(model):
+    """-> (spec, params) of a NestedResUNet (nested_residual_unet.py:49-106)."""
+    params: List[torch.Tensor] = []
+    spec = {"kind": "nested", "blocks": {}}
+    for name in NESTED_BLOCKS:
+        spec["blocks"][name] = _nested_block_spec(getattr(model, name), params)
+    filters = spec["blocks"]["conv0_0"]["cout"]
+    if filters % 8:
+        raise Unsupported("training: NestedResUNet filters must be a multiple of 8 (channel concatenation)")
+    wi, bi = _effective_conv_weight(model.out_conv, params)
+    spec["out"] = {"w": wi, "b": bi, "cin": model.out_conv.in_channels, "cout": model.out_conv.out_channels}
+    hyp = model.hypothesis
+    if isinstance(hyp, nn.Softmax) and hyp.dim == 1:
+        spec["softmax"] = True
+    elif isinstance(hyp, nn.Identity):
+        spec["softmax"] = False
+    else:
+        raise Unsupported(f"training: hypothesis {type(hyp).__name__} is not lowered (Softmax(dim=1) / Identity are)")
+    if spec["out"]["cout"] > 16:
+        raise Unsupported("training: more than 16 output channels are not lowered")
+    return spec, params
 
 
 def build_spec(model):
     """-> (spec, params): the layer list of a ModularUNet and the flat list of effective parameter tensors."""
     from .components import BlurConv3d, BlurConvTranspose3d
     from .modular_unet import ModularUNet
+    from .nested_residual_unet import NestedResUNet
+    if isinstance(model, NestedResUNet):
+        return build_nested_spec(model)
     if not isinstance(model, ModularUNet):
-        raise Unsupported(f"training: {type(model).__name__} is not lowered (ModularUNet is)")
+        raise Unsupported(f"training: {type(model).__name__} is not lowered (ModularUNet and NestedResUNet are)")
     params: List[torch.Tensor] = []
-    spec = {"depth": model.depth, "down": [], "downs": [], "up": [], "ups": []}
+    spec = {"kind": "modular", "depth": model.depth, "down": [], "downs": [], "up": [], "ups": []}
     for block in model.down_blocks:
         spec["down"].append(_block_spec(block, params))
     for i, down in enumerate(model.downsampling):
@@ -224,6 +270,24 @@ def _vec(values: Optional[torch.Tensor], channels: int, fill: float, device) -> 
     out = torch.full((_pad8(channels),), fill, dtype=torch.float32, device=device)
     out[:channels] = values
     return out
+
+
+MASK_OVERRIDE = None     # tests: callable (block key, n, channels, p) -> (n, channels) multiplier or None
+
+
+class _Val:
+    """A tensor of the training tape: a chunk range of a blocked buffer plus its gradient (another _Val) once known."""
+    __slots__ = ("buf", "channels", "off", "grad")
+
+    def __init__(self, buf, channels, off=0):
+        self.buf, self.channels, self.off, self.grad = buf, channels, off, None
+
+    def view(self):
+        return self.buf.view(self.channels, self.off)
+
+    @property
+    def ext(self):
+        return (self.buf.z, self.buf.y, self.buf.x)
 
 
 _TC_INDEX = {}      # (mode, cin_chunks, cout, device) -> (clamped gather index, fp32 mask) on the device
@@ -356,9 +420,24 @@ class _Runner:
             state["convs"].append({"in": cur, "z": z, "scale": scale, "shift": shift, "slope": slope, "mean": mean,
                                    "rstd": rstd})
             cur = a_view
+        if bspec.get("dropout_p", 0.0) > 0.0:
+            # nn.Dropout3d after the residual add (components.py:70-71): one Bernoulli draw per (sample, channel)
+            mask = self.dropout_mask(key, n, cout, bspec["dropout_p"])
+            lib.channel_scale(cur, mask, cur)
+            state["mask"] = mask
         state["ext"], state["n"] = ext, n
         self.saved[key] = state
         return cur
+
+    def dropout_mask(self, key, n, channels, p):
+        if MASK_OVERRIDE is not None:
+            forced = MASK_OVERRIDE(key, n, channels, p)
+            if forced is not None:
+                out = torch.zeros((n, _pad8(channels)), dtype=torch.float32, device=self.device)
+                out[:, :channels] = forced.to(self.device, torch.float32)
+                return out
+        keep = (torch.rand((n, _pad8(channels)), device=self.device) >= p).to(torch.float32)
+        return (keep / (1.0 - p)).contiguous()
 
     @staticmethod
     def _update_running(bn, mean, var, count):
@@ -372,6 +451,8 @@ class _Runner:
             bn.running_var.mul_(1 - momentum).add_(unbiased.to(bn.running_var.dtype), alpha=momentum)
 
     def forward(self, x, params):
+        if self.spec.get("kind") == "nested":
+            return self.nested_forward(x, params)
         lib, spec = self.lib, self.spec
         n, cin = x.shape[0], x.shape[1]
         ext = tuple(x.shape[2:])
@@ -451,6 +532,10 @@ class _Runner:
         n, ext = st["n"], st["ext"]
         count = n * ext[0] * ext[1] * ext[2]
         cin, cout = bspec["cin"], bspec["cout"]
+        if "mask" in st:
+            masked = self.buffer(n, cout, ext)
+            lib.channel_scale(dout_view, st["mask"], masked.view(cout))
+            dout_view = masked.view(cout)
         dcur = dout_view
         dsrc = self.buffer(n, cin, ext) if need_dsrc else None
         for j in reversed(range(len(bspec["convs"]))):
@@ -489,7 +574,137 @@ class _Runner:
                 dsrc = total
         return dsrc
 
+    # -------------------------------------------------------------------------- NestedResUNet: a small tape
+    def accumulate(self, val, g):
+        """val.grad += g (g: _Val).  The first contribution is aliased, later ones are added into a fresh buffer."""
+        if val.grad is None:
+            val.grad = g
+            return
+        n = val.buf.n
+        total = self.buffer(n, val.channels, val.ext)
+        one, zero = _vec(None, val.channels, 1.0, self.device), _vec(None, val.channels, 0.0, self.device)
+        self.lib.affine_act(g.view(), one, zero, one, total.view(val.channels), residual=val.grad.view())
+        val.grad = _Val(total, val.channels)
+
+    def nested_forward(self, x, params):
+        """NestedResUNet.forward (nested_residual_unet.py:88-106) op by op; every op appends its backward to the tape."""
+        lib, spec = self.lib, self.spec
+        n, cin = x.shape[0], x.shape[1]
+        ext = tuple(x.shape[2:])
+        if any(e % 8 for e in ext):
+            raise RuntimeError(f"training: spatial extent {ext} must be divisible by 8")
+        if cin != spec["blocks"]["conv0_0"]["cin"]:
+            raise RuntimeError(f"expected {spec['blocks']['conv0_0']['cin']} input channels, got {cin}")
+        exts = [tuple(e >> lvl for e in ext) for lvl in range(4)]
+        tape = []
+        xin = self.buffer(n, cin, ext)
+        lib.pack_ncdhw(x.detach().to(torch.float32).contiguous(), xin.view(cin))
+        v_in = _Val(xin, cin)
+
+        def block(name, src, level, is_input=False):
+            b = spec["blocks"][name]
+            if src.channels != b["cin"]:
+                raise RuntimeError(f"{name}: expected {b['cin']} channels, got {src.channels}")
+            out = self.buffer(n, b["cout"], exts[level])
+            self.block_forward(name, b, params, src.view(), n, exts[level], out, 0)
+            o = _Val(out, b["cout"])
+
+            def bwd(grads):
+                if o.grad is None:
+                    return
+                dsrc = self.block_backward(name, b, params, o.grad.view(), grads, need_dsrc=not is_input)
+                if dsrc is not None:
+                    self.accumulate(src, _Val(dsrc, b["cin"]))
+            tape.append(bwd)
+            return o
+
+        def down(src, level):          # nn.AvgPool3d(2), level -> level + 1
+            c = src.channels
+            out = self.buffer(n, c, exts[level + 1])
+            lib.avgpool2(src.view(), out.view(c))
+            o = _Val(out, c)
+
+            def bwd(grads):
+                dx = self.buffer(n, c, exts[level])
+                lib.avgpool2_backward(o.grad.view(), dx.view(c), add=lib.NULL_VIEW if src.grad is None else src.grad.view())
+                src.grad = _Val(dx, c)
+            tape.append(bwd)
+            return o
+
+        def up(src, level):            # trilinear Upsample(2), level -> level - 1
+            c = src.channels
+            out = self.buffer(n, c, exts[level - 1])
+            lib.upsample_trilinear2(src.view(), out.view(c))
+            o = _Val(out, c)
+
+            def bwd(grads):
+                dx = self.buffer(n, c, exts[level])
+                lib.upsample_trilinear2_backward(o.grad.view(), dx.view(c))
+                self.accumulate(src, _Val(dx, c))
+            tape.append(bwd)
+            return o
+
+        def cat(parts, level):         # torch.cat(..., 1): copies into one buffer (skip tensors have several consumers)
+            total = sum(p.channels for p in parts)
+            buf = self.buffer(n, total, exts[level])
+            off = 0
+            for p in parts:
+                lib.copy_view(p.view(), buf.view(p.channels, off // 8))
+                off += p.channels
+            o = _Val(buf, total)
+
+            def bwd(grads):
+                off = 0
+                for p in parts:
+                    self.accumulate(p, _Val(o.grad.buf, p.channels, o.grad.off + off // 8))
+                    off += p.channels
+            tape.append(bwd)
+            return o
+
+        x0_0 = block("conv0_0", v_in, 0, is_input=True)
+        x1_0 = block("conv1_0", down(x0_0, 0), 1)
+        x0_1 = block("conv0_1", cat([x0_0, up(x1_0, 1)], 0), 0)
+        x2_0 = block("conv2_0", down(x1_0, 1), 2)
+        x1_1 = block("conv1_1", cat([x1_0, up(x2_0, 2), down(x0_1, 0)], 1), 1)
+        x0_2 = block("conv0_2", cat([x0_1, up(x1_1, 1)], 0), 0)
+        x3_0 = block("conv3_0", down(x2_0, 2), 3)
+        x2_1 = block("conv2_1", cat([x2_0, up(x3_0, 3), down(x1_1, 1)], 2), 2)
+        x1_2 = block("conv1_2", cat([x1_1, up(x2_1, 2), down(x0_2, 0)], 1), 1)
+        x0_3 = block("conv0_3", cat([x0_2, up(x1_2, 1)], 0), 0)
+        o = spec["out"]
+        probs = torch.empty((n, o["cout"], *ext), dtype=torch.float32, device=self.device)
+        w = params[o["w"]].detach()
+        bias = None if o["b"] is None else params[o["b"]].detach()
+        self.conv(x0_3.view(), _pack(w.permute(2, 3, 4, 1, 0)), o["cout"], None, bias=bias, out_ncdhw=probs,
+                  softmax=spec["softmax"])
+        self.saved["tape"], self.saved["head_in"], self.saved["probs"] = tape, x0_3, probs
+        self.saved["n"], self.saved["ext"] = n, ext
+        return probs
+
+    def nested_backward(self, dprobs, params):
+        lib, spec = self.lib, self.spec
+        n, ext = self.saved["n"], self.saved["ext"]
+        grads = [None] * len(params)
+        o = spec["out"]
+        head_in = self.saved.pop("head_in")
+        dlogits = self.buffer(n, o["cout"], ext)
+        lib.softmax_backward(self.saved.pop("probs"), dprobs.detach().to(torch.float32).contiguous(), spec["softmax"],
+                             dlogits.view(o["cout"]))
+        grads[o["w"]] = self._wgrad_conv(dlogits.view(o["cout"]), head_in.view(), o["cout"], o["cin"])
+        if o["b"] is not None:
+            grads[o["b"]] = self._chan_sum(dlogits.view(o["cout"]), o["cout"], n * ext[0] * ext[1] * ext[2])
+        w = params[o["w"]].detach()
+        dhead = self.buffer(n, o["cin"], ext)
+        self.conv(dlogits.view(o["cout"]), _pack(w.flip(2, 3, 4).permute(2, 3, 4, 0, 1)), o["cin"], dhead.view(o["cin"]))
+        self.accumulate(head_in, _Val(dhead, o["cin"]))
+        for bwd in reversed(self.saved.pop("tape")):
+            bwd(grads)
+        self.saved.clear()
+        return grads
+
     def backward(self, dprobs, params):
+        if self.spec.get("kind") == "nested":
+            return self.nested_backward(dprobs, params)
         lib, spec = self.lib, self.spec
         n, ext, exts = self.saved["n"], self.saved["ext"], self.saved["exts"]
         depth = spec["depth"]

@@ -211,12 +211,12 @@ def test_unsupported_and_training_mode_raise():
     with pytest.raises(RuntimeError):
         model.eval()(x)           # CPU tensor
     # training mode: ModularUNet is lowered (tests/test_gpu_train.py); what is not raises instead of falling back
-    nested = M.NestedResUNet(1, 2, 8).cuda().train()
+    inorm = M.ModularUNet(1, 2, [8, 8], 2, block_params={"normalization_class": nn.InstanceNorm3d}).cuda().train()
     with pytest.raises(NotImplementedError):
-        nested(torch.zeros(1, 1, 16, 16, 16).cuda())
-    dropout = M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.1}).cuda().train()
+        inorm(torch.zeros(1, 1, 8, 8, 8).cuda())
+    tanh = M.ModularUNet(1, 2, [8, 8], 2, block_params={"activation_class": nn.Tanh, "activation_params": {}}).cuda().train()
     with pytest.raises(NotImplementedError):
-        dropout(torch.zeros(1, 1, 8, 8, 8).cuda())
+        tanh(torch.zeros(1, 1, 8, 8, 8).cuda())
 
 
 def test_components_forward():

@@ -359,8 +359,86 @@ def test_pool_and_upsample_adjoints_match_autograd():
     assert float((_unblocked(lib, dbig, 12).cpu().double() - (big.grad + add)).abs().max()) <= 1e-6
 
 
+@pytest.mark.parametrize("dropout_p", [0.0, 0.3])
+def test_nested_res_unet_training_step_matches_cpu_autograd(dropout_p, monkeypatch):
+    """NestedResUNet (the dmri_hippo / qsm network; research/dmri_hippo/configs/*.py train it with dropout) through one
+    training step: dense skip connections (tensors with several consumers), AvgPool / trilinear adjoints, Dropout3d.
+    The Dropout3d draws are injected on both sides (the CPU oracle cannot share the device RNG stream)."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    from segmentation_pipeline.models import _train
+    torch.manual_seed(12)
+    model = M.NestedResUNet(3, 2, 8, dropout_p=dropout_p)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(13)
+    n = 2
+    x = torch.randn(n, 3, 16, 24, 8, generator=g)
+    target = torch.nn.functional.one_hot(torch.randint(0, 2, (n, 16, 24, 8), generator=g), 2).movedim(-1, 1).float()
+    masks = {}
+    if dropout_p:
+        for name in _train.NESTED_BLOCKS:
+            masks[name] = (torch.rand(n, 8, generator=g) >= dropout_p).float() / (1 - dropout_p)
+        monkeypatch.setattr(_train, "MASK_OVERRIDE", lambda key, nn_, c, p: masks[key])
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    ref_probs = unet.nested_res_unet_forward(ref_sd, x, {"bn_training": True, "dropout_masks": masks})
+    ref_loss = unet.hybrid_logistic_dice_loss(ref_probs, target)["loss"]
+    ref_loss.backward()
+    model.cuda().train()
+    probs = model(x.cuda())
+    loss = HybridLogisticDiceLoss()(probs, target.cuda())["loss"]
+    loss.backward()
+    assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-5
+    checked = 0
+    for name, p in model.named_parameters():
+        want = ref_sd[name].grad
+        scale = float(want.abs().max()) + 1e-12
+        assert float((p.grad.cpu() - want).abs().max()) <= 2e-4 * scale + 1e-9, name
+        checked += 1
+    assert checked == 70
+    for name, buf in model.named_buffers():
+        if "running" in name:
+            assert torch.allclose(buf.cpu(), ref_sd[name], rtol=1e-5, atol=1e-6), name
+
+
+def test_nested_res_unet_mixed_precision_and_real_dropout():
+    """bf16 tensor-core path of the tape, and Dropout3d with the device RNG: channels are dropped per (sample, channel),
+    survivors are scaled by 1 / (1 - p), gradients are finite."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    from segmentation_pipeline.models import set_precision
+    torch.manual_seed(3)
+    model = M.NestedResUNet(3, 2, 16, dropout_p=0.5).cuda().train()
+    x = torch.randn(2, 3, 32, 32, 16).cuda()
+    target = torch.nn.functional.one_hot(torch.randint(0, 2, (2, 32, 32, 16)), 2).movedim(-1, 1).float().cuda()
+    for precision in ("fp32", "bf16"):
+        set_precision(precision)
+        try:
+            model.zero_grad()
+            loss = HybridLogisticDiceLoss()(model(x), target)["loss"]
+            loss.backward()
+        finally:
+            set_precision("auto")
+        assert torch.isfinite(loss.detach())
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+        assert float(model.conv0_0.conv1.weight.grad.abs().max()) > 0
+
+
+def test_modular_unet_dropout_training_step(monkeypatch):
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.models import _train
+    torch.manual_seed(4)
+    model = M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.25}).cuda().train()
+    seen = []
+    monkeypatch.setattr(_train, "MASK_OVERRIDE", lambda key, n, c, p: seen.append((key, n, c, p)))
+    probs = model(torch.randn(2, 1, 16, 16, 16).cuda())
+    probs.sum().backward()
+    assert [k for k, *_ in seen] == [("down", 0), ("down", 1), ("up", 0)] and all(p == 0.25 for *_, p in seen)
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
 def test_training_mode_unsupported_configuration_raises():
     from segmentation_pipeline import models as M
-    model = M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.2}).cuda().train()    # Dropout3d: not lowered
+    model = M.ModularUNet(1, 2, [8, 8], 2, block_params={"normalization_class": torch.nn.InstanceNorm3d}).cuda().train()
     with pytest.raises(NotImplementedError):
         model(torch.randn(1, 1, 8, 8, 8).cuda())

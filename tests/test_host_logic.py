@@ -185,10 +185,14 @@ def test_training_spec_of_the_msseg2_network_and_refusals():
     assert sorted(unused) == sorted([f"downsampling.{i}.bias" for i in range(5)] + [f"upsampling.{i}.bias" for i in range(5)])
     blurred = params[spec["downs"][0]["w"]]
     assert blurred.shape == (40, 40, 4, 4, 4) and blurred.requires_grad and not blurred.is_leaf
+    nested, nested_params = _train.build_spec(M.NestedResUNet(3, 2, 16, dropout_p=0.2))
+    assert nested["kind"] == "nested" and nested["blocks"]["conv1_1"]["cin"] == 48 and len(nested_params) == 70
+    assert nested["blocks"]["conv0_3"]["dropout_p"] == 0.2 and nested["blocks"]["conv0_1"]["res"] is not None
+    assert _train.build_spec(M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.5}))[0]["down"][0]["dropout_p"] == 0.5
     with pytest.raises(NotImplementedError):
-        _train.build_spec(M.NestedResUNet(1, 2, 8))
+        _train.build_spec(M.NestedResUNet(1, 2, 12))                  # filters must be a multiple of 8
     with pytest.raises(NotImplementedError):
-        _train.build_spec(M.ModularUNet(1, 2, [8, 8], 2, block_params={"dropout_p": 0.5}))
+        _train.build_spec(M.ModularUNet(1, 2, [8, 8], 2, block_params={"normalization_class": torch.nn.InstanceNorm3d}))
     with pytest.raises(NotImplementedError):
         _train.build_spec(M.ModularUNet(1, 2, [12, 12], 2))          # concatenated widths must be multiples of 8
     default = _train.build_spec(M.ModularUNet(1, 2, [8, 16], 2))[0]
