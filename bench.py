@@ -590,7 +590,7 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
-def run_train_section(world: int, rank: int, local: int, device, steps: int = 3, warmup: int = 1) -> dict:
+def run_train_section(world: int, rank: int, local: int, device, steps: int = 4, warmup: int = 3) -> dict:
     """BASELINE config 5 in both precisions of the training step: 'fp32' (the reference's arithmetic: CUDA-core
     convolutions) and 'bf16' (mixed precision: forward and dgrad on the tcgen05 engine, fp32 statistics / wgrad /
     parameters)."""
@@ -633,15 +633,16 @@ def _run_train(world: int, rank: int, local: int, device, precision: str, steps:
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    marks[0].record()
+    for i in range(steps):
         step()
-    e1.record()
+        marks[i + 1].record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+    step_ms = [a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:])]
+    ms = torch.tensor([marks[0].elapsed_time(marks[-1]) / steps], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
@@ -649,7 +650,7 @@ def _run_train(world: int, rank: int, local: int, device, precision: str, steps:
     patches = world * TRAIN_BATCH
     return {"n_gpus": world, "dtype": "f32" if precision == "fp32" else "bf16 activations / fp32 accumulation, statistics and weights",
             "scaling": "weak", "steps": steps, "warmup": warmup,
-            "ms_per_step": ms, "patches_per_s": patches / (ms * 1e-3),
+            "ms_per_step": ms, "step_ms_rank0": step_ms, "patches_per_s": patches / (ms * 1e-3),
             "value": patches * PATCH ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxel/s (patch voxels trained)",
             "tflops": 3 * FLOP_PER_PATCH * patches / (ms * 1e-3) / 1e12,
             "tflops_basis": "3 x the forward FLOPs (forward + dgrad + wgrad)",
