@@ -460,12 +460,22 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a
 
 // MT / NT: m16 / n8 tiles actually computed (3 x 5 in general; 1 when the A / B group holds at most 2 / 1 chunks -- the
 // first layer's 2-channel input and the 2-class logits would otherwise spend 2/3 resp. 4/5 of their MMAs on zeros)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(addr), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 template <int K, int MT, int NT>
 __global__ void __launch_bounds__(K * K * 32, K == 3 ? 2 : 1)
 wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) {
+    constexpr int S = K == 3 ? 1 : 2;            // the two geometries: 3^3 stride 1, 4^3 stride 2
+    constexpr int RING = K + S;                  // halo rows of row y AND the S new rows of row y + 1
     extern __shared__ uint4 wg_smem[];
-    uint4* sA = wg_smem;                         // [6 chunks][xp]
-    uint4* sB = wg_smem + 6 * g.xp;              // [K rows][6 chunk slots][bw]  (5 used; slot 5 = zeros for the x4 loads)
+    uint4* sA = wg_smem;                         // [2 buffers][6 chunks][xp]
+    uint4* sB = wg_smem + 12 * g.xp;             // [RING rows][6 chunk slots][bw]  (5 used; slot 5 = zeros for the x4 loads)
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int ty = warp / K, tx = warp % K, tz = blockIdx.z;
     const int ag = blockIdx.y / g.b_groups, bg = blockIdx.y % g.b_groups;
@@ -487,59 +497,72 @@ wgrad_mma_kernel(DView A, DView B, WgradMmaGeom g, float* __restrict__ partial) 
     // Everything that is structurally zero (halo columns, positions past the row end, missing chunks, the sixth B slot)
     // is written once; per row only the data sections [0, px) of A and [pad, pad + B.x) of the NEW halo rows of B are
     // copied, one contiguous global line per warp trip (first version: per-vector index arithmetic in the staging loop
-    // cost twice the instructions of the MMA loop).  The K halo rows live in a ring: row by sits in slot (by + pad) % K,
-    // so stepping y by one loads `stride` new rows instead of K.
-    for (int i = threadIdx.x; i < 6 * g.xp + K * 6 * g.bw; i += blockDim.x) wg_smem[i] = zero;
+    // cost twice the instructions of the MMA loop).  The halo rows live in a ring of K + S slots (row by in slot
+    // (by + pad) % RING) and the A row is double-buffered, so the copies of row y + 1 (cp.async) run under the MMAs of
+    // row y and there is ONE barrier per row (second version: two barriers and synchronous copies -- ncu: tensor pipe
+    // 41 % active, 4.2 barrier + 2.4 scoreboard stall cycles per issue).
+    for (int i = threadIdx.x; i < 12 * g.xp + RING * 6 * g.bw; i += blockDim.x) wg_smem[i] = zero;
     const int na = min(6, g.a_chunks - ca0), nb = min(5, g.b_chunks - cb0);
-    int key = -1, staged_hi = 0;                                  // (n, z) of the rows in the ring; highest staged by
-    for (int r = r0; r < r1; ++r) {
-        const int y = r % g.py;
-        const int nz = r / g.py;
-        const int z = nz % g.pz, n = nz / g.pz;
-        const int bz = g.stride * z + tz - g.pad;
-        if (bz < 0 || bz >= B.z) continue;                       // block-uniform
-        const int lo = g.stride * y - g.pad, hi = lo + K - 1;
-        int first_new = lo;
-        if (key == nz && staged_hi >= lo) first_new = staged_hi + 1;
-        key = nz;
-        staged_hi = hi;
-        const int new_rows = hi - first_new + 1;
-        __syncthreads();                                          // every warp is done with the previous row
-        const int lines = na + new_rows * nb;
+
+    // copies of one row: the A row into buffer ab, the halo rows [first, last] of B into their ring slots
+    auto issue = [&](int n, int z, int y, int bz, int ab, int first, int last) {
+        const int lines = na + (last - first + 1) * nb;
         for (int line = warp; line < lines; line += nwarps) {
             if (line < na) {
                 const uint4* src = Adata + vox_index(A, n, ca0 + line, z, y, 0);
-                uint4* dst = sA + line * g.xp;
-                for (int x = lane; x < g.px; x += 32) dst[x] = __ldg(src + x);
+                uint4* dst = sA + (ab * 6 + line) * g.xp;
+                for (int x = lane; x < g.px; x += 32) cp_async16(dst + x, src + x);
             } else {
                 const int q = line - na;
                 const int rr = q / nb, c = q - rr * nb;
-                const int by = first_new + rr;
-                uint4* dst = sB + (((by + g.pad) % K) * 6 + c) * g.bw + g.pad;
+                const int by = first + rr;
+                uint4* dst = sB + (((by + g.pad) % RING) * 6 + c) * g.bw + g.pad;
                 if (by >= 0 && by < B.y) {
                     const uint4* src = Bdata + vox_index(B, n, cb0 + c, bz, by, 0);
-                    for (int x = lane; x < B.x; x += 32) dst[x] = __ldg(src + x);
+                    for (int x = lane; x < B.x; x += 32) cp_async16(dst + x, src + x);
                 } else {
                     for (int x = lane; x < B.x; x += 32) dst[x] = zero;
                 }
             }
         }
+    };
+
+    int r = r0;
+    while (r < r1) {
+        const int nz = r / g.py, yb = r - nz * g.py;
+        const int yend = min(g.py, yb + (r1 - r));                // rows [yb, yend) of plane nz belong to this block
+        const int z = nz % g.pz, n = nz / g.pz;
+        const int bz = S * z + tz - g.pad;
+        r += yend - yb;
+        if (bz < 0 || bz >= B.z) continue;                        // block-uniform
+        __syncthreads();                                           // every warp is done with the previous plane
+        issue(n, z, yb, bz, 0, S * yb - g.pad, S * yb - g.pad + K - 1);
+        cp_async_wait_all();
         __syncthreads();
-        const uint4* brow = sB + static_cast<long long>((g.stride * y + ty) % K) * 6 * g.bw;
-        for (int ks = 0; ks < g.xp; ks += 16) {
-            unsigned af[MT][4], bf[(NT + 1) / 2][4];
-            // matrices of one x4 load: (chunk 2m, pos 0-7), (chunk 2m+1, pos 0-7), (chunk 2m, pos 8-15), (chunk 2m+1, pos 8-15)
+        for (int y = yb; y < yend; ++y) {
+            const int ab = (y - yb) & 1;
+            const int hi = S * y - g.pad + K - 1;
+            if (y + 1 < yend) issue(n, z, y + 1, bz, ab ^ 1, hi + 1, hi + S);
+            const uint4* arow = sA + ab * 6 * g.xp;
+            const uint4* brow = sB + static_cast<long long>((S * y + ty) % RING) * 6 * g.bw;
+            for (int ks = 0; ks < g.xp; ks += 16) {
+                unsigned af[MT][4], bf[(NT + 1) / 2][4];
+                // matrices of one x4 load: (chunk 2m, pos 0-7), (chunk 2m+1, pos 0-7), (chunk 2m, pos 8-15), (chunk 2m+1, pos 8-15)
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-                ldmatrix_x4_trans(af[m], sA + (2 * m + (mat & 1)) * g.xp + ks + (mat >> 1) * 8 + jrow);
-            // B: (chunk 2q, pos 0-7), (chunk 2q, pos 8-15), (chunk 2q+1, pos 0-7), (chunk 2q+1, pos 8-15)
+                for (int m = 0; m < MT; ++m)
+                    ldmatrix_x4_trans(af[m], arow + (2 * m + (mat & 1)) * g.xp + ks + (mat >> 1) * 8 + jrow);
+                // B: (chunk 2q, pos 0-7), (chunk 2q, pos 8-15), (chunk 2q+1, pos 0-7), (chunk 2q+1, pos 8-15)
 #pragma unroll
-            for (int q = 0; q < (NT + 1) / 2; ++q)
-                ldmatrix_x4_trans(bf[q], brow + (2 * q + (mat >> 1)) * g.bw + g.stride * (ks + (mat & 1) * 8 + jrow) + tx);
+                for (int q = 0; q < (NT + 1) / 2; ++q)
+                    ldmatrix_x4_trans(bf[q], brow + (2 * q + (mat >> 1)) * g.bw + S * (ks + (mat & 1) * 8 + jrow) + tx);
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
+                for (int m = 0; m < MT; ++m)
 #pragma unroll
-                for (int nn = 0; nn < NT; ++nn) mma_bf16_16816(acc[m][nn], af[m], bf[nn >> 1][(nn & 1) * 2], bf[nn >> 1][(nn & 1) * 2 + 1]);
+                    for (int nn = 0; nn < NT; ++nn)
+                        mma_bf16_16816(acc[m][nn], af[m], bf[nn >> 1][(nn & 1) * 2], bf[nn >> 1][(nn & 1) * 2 + 1]);
+            }
+            cp_async_wait_all();
+            __syncthreads();
         }
     }
     // accumulator fragment: c0,c1 = (row g, cols 2t, 2t+1); c2,c3 = (row g + 8, same cols)
@@ -731,7 +754,8 @@ static int launch_wgrad_mma(const b200seg_view& a, const b200seg_view& b, int ks
     const int groups = g.a_groups * g.b_groups;
     int slices = mma_slices(groups, ksize);
     if (slices > g.rows) slices = g.rows;
-    const size_t smem = (6 * static_cast<size_t>(g.xp) + static_cast<size_t>(ksize) * 6 * g.bw) * sizeof(uint4);
+    const int ring = ksize + stride;
+    const size_t smem = (12 * static_cast<size_t>(g.xp) + static_cast<size_t>(ring) * 6 * g.bw) * sizeof(uint4);
     dim3 grid(slices, groups, ksize);
     const bool one_m = g.a_chunks <= 2, one_n = g.b_chunks <= 1;      // a single group then, too
 #define B200SEG_WGRAD_MMA(KK, MT, NT)                                                                                   \
@@ -773,7 +797,8 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
     B200SEG_CHECK_ARG((ksize == 3 || ksize == 4) && stride >= 1 && stride <= 2 && pad >= 0 && scratch && grad && a.n == b.n,
                       "wgrad: bad arguments");
     static const bool no_mma = getenv("B200SEG_WGRAD_SIMT") != nullptr;      // A/B switch
-    if (a.dtype == B200SEG_BF16 && b.dtype == B200SEG_BF16 && a.x <= kMmaMaxX && !no_mma)
+    if (a.dtype == B200SEG_BF16 && b.dtype == B200SEG_BF16 && a.x <= kMmaMaxX && !no_mma &&
+        stride == (ksize == 3 ? 1 : 2))
         return launch_wgrad_mma(a, b, ksize, stride, pad, scratch, grad, static_cast<cudaStream_t>(stream));
     const int ca8n = (a.c + 7) / 8, cb8n = (b.c + 7) / 8, pairs = ca8n * cb8n;
     WgradGeom g;
