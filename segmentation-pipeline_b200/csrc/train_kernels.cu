@@ -616,7 +616,7 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int slice
     grad[(static_cast<long long>(tap) * ca8n * 8 + ca * 8 + e / 8) * (cb8n * 8) + cb * 8 + e % 8] = s;
 }
 
-static int check_f32_view(const b200seg_view& v, const char* name) {     // fp32 or bf16 (name kept from round 2a)
+static int check_view(const b200seg_view& v, const char* name) {     // fp32 or bf16
     return validate_view(v, name);
 }
 
@@ -640,7 +640,7 @@ extern "C" int64_t b200seg_train_scratch_bytes(int32_t channels) {
 }
 
 extern "C" int b200seg_channel_moments(b200seg_view x, void* scratch, float* mean, float* var, void* stream) {
-    int rc = check_f32_view(x, "channel_moments x");
+    int rc = check_view(x, "channel_moments x");
     if (rc) return rc;
     B200SEG_CHECK_ARG(scratch && mean && var, "channel_moments: null argument");
     const int c8n = (x.c + 7) / 8, nblk = reduce_blocks(x);
@@ -657,14 +657,14 @@ extern "C" int b200seg_channel_moments(b200seg_view x, void* scratch, float* mea
 
 extern "C" int b200seg_affine_act(b200seg_view src, const float* scale, const float* shift, const float* slope,
                                   b200seg_view residual, b200seg_view dst, void* stream) {
-    int rc = check_f32_view(src, "affine_act src");
+    int rc = check_view(src, "affine_act src");
     if (rc) return rc;
-    rc = check_f32_view(dst, "affine_act dst");
+    rc = check_view(dst, "affine_act dst");
     if (rc) return rc;
     B200SEG_CHECK_ARG(scale && shift && slope && same_extent(src, dst), "affine_act: bad arguments");
     DView dr = null_dview();
     if (residual.data != nullptr) {
-        rc = check_f32_view(residual, "affine_act residual");
+        rc = check_view(residual, "affine_act residual");
         if (rc) return rc;
         B200SEG_CHECK_ARG(same_extent(src, residual), "affine_act: residual extent differs");
         dr = make_dview(residual);
@@ -682,11 +682,11 @@ extern "C" int b200seg_affine_act(b200seg_view src, const float* scale, const fl
 extern "C" int b200seg_bn_backward(b200seg_view dy, b200seg_view z, const float* scale, const float* shift,
                                    const float* slope, const float* mean, const float* rstd, int32_t has_norm,
                                    void* scratch, float* sum_g, float* sum_gx, b200seg_view dz, void* stream) {
-    int rc = check_f32_view(dy, "bn_backward dy");
+    int rc = check_view(dy, "bn_backward dy");
     if (rc) return rc;
-    rc = check_f32_view(z, "bn_backward z");
+    rc = check_view(z, "bn_backward z");
     if (rc) return rc;
-    rc = check_f32_view(dz, "bn_backward dz");
+    rc = check_view(dz, "bn_backward dz");
     if (rc) return rc;
     B200SEG_CHECK_ARG(scale && shift && slope && mean && rstd && scratch && sum_g && sum_gx, "bn_backward: null argument");
     B200SEG_CHECK_ARG(same_extent(dy, z) && same_extent(dy, dz), "bn_backward: extents differ");
@@ -710,7 +710,7 @@ extern "C" int b200seg_bn_backward(b200seg_view dy, b200seg_view z, const float*
 
 extern "C" int b200seg_softmax_backward(const float* probs, const float* dprobs, int32_t n, int32_t c, int32_t softmax,
                                         b200seg_view dst, void* stream) {
-    int rc = check_f32_view(dst, "softmax_backward dst");
+    int rc = check_view(dst, "softmax_backward dst");
     if (rc) return rc;
     B200SEG_CHECK_ARG(probs && dprobs && n == dst.n && c == dst.c, "softmax_backward: bad arguments");
     const long long vox = 1LL * dst.z * dst.y * dst.x, total = vox * n;
@@ -790,9 +790,9 @@ static int launch_wgrad_mma(const b200seg_view& a, const b200seg_view& b, int ks
 
 extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int32_t stride, int32_t pad, float* scratch,
                              float* grad, void* stream) {
-    int rc = check_f32_view(a, "wgrad a");
+    int rc = check_view(a, "wgrad a");
     if (rc) return rc;
-    rc = check_f32_view(b, "wgrad b");
+    rc = check_view(b, "wgrad b");
     if (rc) return rc;
     B200SEG_CHECK_ARG((ksize == 3 || ksize == 4) && stride >= 1 && stride <= 2 && pad >= 0 && scratch && grad && a.n == b.n,
                       "wgrad: bad arguments");
@@ -834,15 +834,15 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
 }
 
 extern "C" int b200seg_avgpool2_backward(b200seg_view dy, b200seg_view add, b200seg_view dx, void* stream) {
-    int rc = check_f32_view(dy, "avgpool2_backward dy");
+    int rc = check_view(dy, "avgpool2_backward dy");
     if (rc) return rc;
-    rc = check_f32_view(dx, "avgpool2_backward dx");
+    rc = check_view(dx, "avgpool2_backward dx");
     if (rc) return rc;
     B200SEG_CHECK_ARG(dy.n == dx.n && (dy.c + 7) / 8 == (dx.c + 7) / 8 && dy.z == dx.z / 2 && dy.y == dx.y / 2 && dy.x == dx.x / 2,
                       "avgpool2_backward: dy must be the pooled extent of dx");
     DView dadd = null_dview();
     if (add.data != nullptr) {
-        rc = check_f32_view(add, "avgpool2_backward add");
+        rc = check_view(add, "avgpool2_backward add");
         if (rc) return rc;
         B200SEG_CHECK_ARG(same_extent(add, dx), "avgpool2_backward: add extent differs");
         dadd = make_dview(add);
@@ -858,9 +858,9 @@ extern "C" int b200seg_avgpool2_backward(b200seg_view dy, b200seg_view add, b200
 }
 
 extern "C" int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_view dx, void* stream) {
-    int rc = check_f32_view(dy, "upsample_trilinear2_backward dy");
+    int rc = check_view(dy, "upsample_trilinear2_backward dy");
     if (rc) return rc;
-    rc = check_f32_view(dx, "upsample_trilinear2_backward dx");
+    rc = check_view(dx, "upsample_trilinear2_backward dx");
     if (rc) return rc;
     B200SEG_CHECK_ARG(dy.n == dx.n && (dy.c + 7) / 8 == (dx.c + 7) / 8 && dy.z == 2 * dx.z && dy.y == 2 * dx.y && dy.x == 2 * dx.x,
                       "upsample_trilinear2_backward: dy must be twice the extent of dx");
@@ -874,9 +874,9 @@ extern "C" int b200seg_upsample_trilinear2_backward(b200seg_view dy, b200seg_vie
 }
 
 extern "C" int b200seg_channel_scale(b200seg_view src, const float* mask, b200seg_view dst, void* stream) {
-    int rc = check_f32_view(src, "channel_scale src");
+    int rc = check_view(src, "channel_scale src");
     if (rc) return rc;
-    rc = check_f32_view(dst, "channel_scale dst");
+    rc = check_view(dst, "channel_scale dst");
     if (rc) return rc;
     B200SEG_CHECK_ARG(mask && same_extent(src, dst) && src.dtype == dst.dtype, "channel_scale: bad arguments");
     const int c8n = (src.c + 7) / 8;
