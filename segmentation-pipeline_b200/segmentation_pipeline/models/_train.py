@@ -703,6 +703,9 @@ class _Runner:
         return grads
 
     def backward(self, dprobs, params):
+        if not self.saved:
+            raise RuntimeError("the activations of this training step were released by its first backward pass "
+                               "(backward through the b200 network twice / retain_graph is not supported)")
         if self.spec.get("kind") == "nested":
             return self.nested_backward(dprobs, params)
         lib, spec = self.lib, self.spec
