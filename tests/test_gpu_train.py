@@ -310,6 +310,50 @@ def test_mixed_precision_training_step_on_the_tensor_cores(filters, depth, resid
             assert torch.allclose(buf.cpu(), ref_sd[name], rtol=2e-2, atol=2e-3), name
 
 
+def test_weight_standardised_network_training_step():
+    """WSConv3d blocks and weight-standardised blur convolutions: the standardisation (components.py:81-88, :113-116)
+    is a tensor expression outside the device function, so autograd chains it -- checked against the oracle."""
+    from segmentation_pipeline import models as M
+    from segmentation_pipeline.criterions.hybrid_logistic_dice_loss import HybridLogisticDiceLoss
+    torch.manual_seed(21)
+    filters, depth = [8, 16], 2
+    model = M.ModularUNet(2, 2, filters, depth,
+                          block_params={"conv_class": M.WSConv3d, "conv_params": {"kernel_size": 3, "padding": 1},
+                                        "residual": True, "residual_params": {"kernel_size": 3, "padding": 1}},
+                          downsample_class=M.BlurConv3d,
+                          downsample_params={"kernel_size": 3, "stride": 2, "padding": 1, "weight_standardization": True},
+                          upsample_class=M.BlurConvTranspose3d,
+                          upsample_params={"kernel_size": 3, "stride": 2, "padding": 1, "output_padding": 0,
+                                           "weight_standardization": True},
+                          hypothesis_class=torch.nn.Identity, hypothesis_params={})
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(2, 2, 16, 16, 16, generator=g)
+    # unit-variance weights make the logits large (a softmax would saturate): compare the logits themselves, relatively,
+    # under a fixed linear functional
+    weights = torch.randn(2, 2, 16, 16, 16, generator=g)
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "kernel" not in k)
+              for k, v in sd0.items()}
+    cfg = {"depth": depth, "filters": filters, "down": "blur", "up": "blur", "down_ws": True, "up_ws": True,
+           "hypothesis": "identity", "block": {"residual": True, "bn_training": True, "conv": "ws"}}
+    ref_probs = unet.modular_unet_forward(ref_sd, x, cfg)
+    (ref_probs * weights).sum().backward()
+    model.cuda().train()
+    probs = model(x.cuda())
+    (probs * weights.cuda()).sum().backward()
+    assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5 * float(ref_probs.detach().abs().max())
+    checked = 0
+    for name, p in model.named_parameters():
+        want = ref_sd[name].grad
+        if want is None:                      # biases the reference never applies (WSConv3d, blur convolutions)
+            assert p.grad is None, name
+            continue
+        scale = float(want.abs().max()) + 1e-12
+        assert float((p.grad.cpu() - want).abs().max()) <= 5e-4 * scale + 1e-8, name
+        checked += 1
+    assert checked >= 10
+
+
 def test_default_modular_unet_training_step_matches_cpu_autograd():
     """The class defaults (AvgPool3d(2) down, trilinear Upsample(2, align_corners=True) up, no residual) -- the
     BASELINE config-1 network -- through one training step."""
