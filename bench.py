@@ -744,7 +744,7 @@ def run_gpu_arm(args) -> None:
     # ---- patch_batch_size = 1, the reference inference script's setting (research/msseg2/competition/ms-inference.py:32):
     #      144 single-patch forwards per volume; the plan of one patch is replayed as a CUDA graph
     batch1 = None
-    if rank == 0:
+    if rank == 0 and not args.main_only:
         from segmentation_pipeline import prediction as _pred
         p1 = PatchPredict(patch_batch_size=1, patch_size=PATCH, patch_overlap=OVERLAP, padding_mode=PADDING)
         batch1 = {"patch_batch_size": 1}
@@ -771,9 +771,9 @@ def run_gpu_arm(args) -> None:
                          "forward, its plan replayed 144 times as a CUDA graph")
     # ---- z-slab mode: one config-3 volume over all ranks (strong scaling; the collective path)
     set_precision("bf16")
-    slab = run_slab_section(world, rank, device) if (world > 1 or args.slab) else None
-    cohort4 = run_cohort_section(world, rank, device)
-    train5 = run_train_section(world, rank, local, device)
+    slab = run_slab_section(world, rank, device) if ((world > 1 or args.slab) and not args.main_only) else None
+    cohort4 = None if args.main_only else run_cohort_section(world, rank, device)
+    train5 = None if args.main_only else run_train_section(world, rank, local, device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -815,11 +815,11 @@ def run_gpu_arm(args) -> None:
         line["slab"] = slab
     line["cohort_config4"] = cohort4
     line["train_config5"] = train5
-    if world == 1:
+    if world == 1 and not args.main_only:
         line["config1"] = run_config1_section(device)
         set_precision("bf16")
     line["patch_batch_1"] = batch1
-    if world == 1:
+    if world == 1 and not args.main_only:
         threads = os.cpu_count() or 1
         ref = CpuReference(threads)
         ref.run_patch(SAMPLE_PATCHES[0])                                  # warm-up
@@ -845,6 +845,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slab", action="store_true", help="also run the config-3 z-slab section at N = 1")
+    ap.add_argument("--main-only", action="store_true",
+                    help="profiling aid: only the headline workload (config 2), none of the extra sections")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
