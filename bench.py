@@ -329,6 +329,56 @@ def gpu_incumbent(ref: "CpuReference", device, n_batch: int = 8) -> dict:
             "out_dtype": str(y.dtype)}
 
 
+def gpu_incumbent_train(ref: "CpuReference", device, steps: int = 3) -> dict:
+    """The 'existing' GPU TRAINING step next to ``train_config5``: the same network, batch and loss as plain ATen / cuDNN
+    autograd (oracle/unet.py's functional forward with batch-statistic BatchNorm on CUDA tensors, torch.autocast(bfloat16),
+    channels_last_3d input), SGD on the same parameters.  Baseline leg (rank 0, N = 1 only)."""
+    try:
+        sd = {k: v.to(device).clone() for k, v in ref.sd.items()}
+        params = [v.requires_grad_(True) for k, v in sd.items()
+                  if v.is_floating_point() and "running" not in k and "kernel" not in k]
+        opt = torch.optim.SGD(params, lr=1e-3, momentum=0.95)
+        g = torch.Generator().manual_seed(100)
+        x = torch.randn(TRAIN_BATCH, 2, PATCH, PATCH, PATCH, generator=g).to(device)
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        labels = (torch.rand(TRAIN_BATCH, PATCH, PATCH, PATCH, generator=g) < 0.05).long()
+        y = torch.nn.functional.one_hot(labels, 2).movedim(-1, 1).float().to(device)
+        cfg = dict(ORACLE_CFG, block=dict(ORACLE_CFG["block"], bn_training=True))
+        class_weights = torch.tensor([1.0, 100.0], device=device)
+
+        def torch_hybrid_loss(p, t, w, eps=1e-8):
+            """criterions/hybrid_logistic_dice_loss.py:13-43 as tensor expressions on the device."""
+            dims = (2, 3, 4)
+            dice = 2 * (p * t).sum(dims) / ((t * t).sum(dims) + (p * p).sum(dims) + eps)
+            logistic = (t * torch.log((p + eps) / (1 + eps))).mean(dims) * w[None]
+            return 0.5 * (-logistic).mean() + 0.5 * (1 - dice).mean()
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                probs = ref.unet.modular_unet_forward(sd, x, cfg)
+            loss = torch_hybrid_loss(probs.float(), y, class_weights)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    return {"ms_per_step": ms, "patches_per_s": TRAIN_BATCH / (ms * 1e-3),
+            "tflops": 3 * FLOP_PER_PATCH * TRAIN_BATCH / (ms * 1e-3) / 1e12,
+            "what": f"ATen/cuDNN autograd of the functional network, autocast bf16 + channels_last_3d, batch {TRAIN_BATCH} x "
+                    f"(2, {PATCH}^3), torch loss, SGD; {steps} timed steps after 2 warm-up steps"}
+
+
 def label_check(ref: "CpuReference", model, device) -> dict:
     """Unfiltered argmax agreement of the CUDA bf16 path with the CPU fp32 oracle on the sample patches the baseline
     leg just ran (same weights incl. the fitted head), plus the oracle's top-2 margin histogram of the disagreeing
@@ -833,6 +883,7 @@ def run_gpu_arm(args) -> None:
                                           f"divide/crop/argmax of the padded volume ({t_fin:.2f} s)"}
         line["label_check"] = label_check(ref, model, device)
         line["gpu_incumbent"] = gpu_incumbent(ref, device)
+        line["gpu_incumbent_train"] = gpu_incumbent_train(ref, device)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
