@@ -481,6 +481,59 @@ def test_modular_unet_dropout_training_step(monkeypatch):
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
 
 
+@pytest.mark.parametrize("momentum", [0.1, None])
+def test_train_then_eval_uses_the_updated_weights_and_running_statistics(momentum):
+    """segmentation_trainer.py:162-180 then :196-242: after ``optimizer.step()`` and ``model.eval()`` the inference plan
+    must be rebuilt from the new weights AND the running statistics the training forward just updated (momentum, or the
+    cumulative average of ``momentum=None``) -- compared with the oracle in eval mode on the oracle's own post-step state."""
+    from segmentation_pipeline import models as M
+    torch.manual_seed(31)
+    filters, depth = [8, 16], 2
+    model = M.ModularUNet(1, 2, filters, depth, block_params={"normalization_params": {"momentum": momentum}})
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 16, 16, 16, generator=g)
+    weights = torch.randn(2, 2, 16, 16, 16, generator=g)
+    model.cuda()
+    with torch.no_grad():
+        before = model.eval()(x.cuda()).cpu()                  # builds and caches the inference plan
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    model.train()
+    (model(x.cuda()) * weights.cuda()).sum().backward()
+    opt.step()
+    model.eval()
+    with torch.no_grad():
+        after = model(x.cuda()).cpu()
+    # oracle: the same step, then eval
+    ref_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    cfg = {"depth": depth, "filters": filters, "down": "avgpool", "up": "trilinear", "block": {"bn_training": True}}
+    if momentum is None:        # F.batch_norm(momentum=None) is not the module's cumulative average: first batch -> factor 1
+        for k in ref_sd:
+            if "running_mean" in k:
+                ref_sd[k].zero_()
+            if "running_var" in k:
+                ref_sd[k].zero_()
+    import torch.nn.functional as F  # noqa: F401
+    orig = unet.batch_norm_train
+    try:
+        if momentum is None:
+            unet.batch_norm_train = lambda t, sd, prefix, eps=unet.BN_EPS, momentum=1.0: orig(t, sd, prefix, eps, 1.0)
+        (unet.modular_unet_forward(ref_sd, x, cfg) * weights).sum().backward()
+    finally:
+        unet.batch_norm_train = orig
+    with torch.no_grad():
+        for v in ref_sd.values():
+            if v.grad is not None:
+                v -= 0.05 * v.grad
+        want = unet.modular_unet_forward({k: v.detach() for k, v in ref_sd.items()}, x,
+                                         {"depth": depth, "filters": filters, "down": "avgpool", "up": "trilinear", "block": {}})
+    assert float((after - before).abs().max()) > 1e-3                       # the plan was rebuilt
+    assert float((after - want).abs().max()) <= 2e-5
+    for name, buf in model.named_buffers():
+        if "running" in name:
+            assert torch.allclose(buf.cpu(), ref_sd[name], rtol=1e-5, atol=1e-6), name
+
+
 def test_training_mode_unsupported_configuration_raises():
     from segmentation_pipeline import models as M
     model = M.ModularUNet(1, 2, [8, 8], 2, block_params={"normalization_class": torch.nn.InstanceNorm3d}).cuda().train()
