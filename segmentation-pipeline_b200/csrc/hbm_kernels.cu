@@ -569,7 +569,9 @@ overlap_crop_kernel(float* __restrict__ out, int C, int PW, int PH, int PD, cons
 }
 
 // =========================================================================================== finalize (+ argmax)
-// Block = 64 k-vectors x 4 rows; grid = (k blocks, row blocks, planes): no per-thread 64-bit div / mod.  The channel
+// Block = 256 consecutive (row j, k-vector) pairs of one plane i; grid = (pair blocks, planes): one 32-bit division per
+// thread, no 64-bit div / mod, and no idle lanes when D / VEC is not a multiple of 64 (config 2: 48 vectors per row --
+// the earlier 64 x 4 tiling left a quarter of every block idle).  The channel
 // loop loads up to 4 channels' vectors before touching them, so every thread keeps 4 x 16 bytes in flight (round 1
 // loaded, divided and compared one channel at a time and sat at 22 % of the copy bandwidth with 2 channels).
 template <int VEC>
@@ -577,11 +579,12 @@ __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ out, int C, int PW, int PH, int PD, const int* __restrict__ cw,
                 const int* __restrict__ ch, const int* __restrict__ cd, int b0, int b1, int b2, int W, int H, int D,
                 float* __restrict__ probs, long long* __restrict__ lab64, uint8_t* __restrict__ lab8) {
-    const int kv = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const int i = blockIdx.z;
-    const int k = kv * VEC;
-    if (k >= D || j >= H) return;
+    const int kvs = (D + VEC - 1) / VEC;                       // k-vectors per row
+    const int pair = blockIdx.x * kThreads + threadIdx.x;
+    const int j = pair / kvs;
+    const int i = blockIdx.y;
+    const int k = (pair - j * kvs) * VEC;
+    if (j >= H) return;
     const long long pvox = 1LL * PW * PH * PD;
     const long long vox = 1LL * W * H * D;
     const long long src = (static_cast<long long>(i + b0) * PH + (j + b1)) * PD + (k + b2);
@@ -1131,13 +1134,13 @@ int b200seg_finalize_region(const float* out, int32_t c, int32_t pw, int32_t ph,
     bool vec = (D % 4 == 0) && (pd % 4 == 0) && (border[2] % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                (probs == nullptr || (reinterpret_cast<uintptr_t>(probs) & 15) == 0) &&
                (labels_u8 == nullptr || (reinterpret_cast<uintptr_t>(labels_u8) & 3) == 0);
-    B200SEG_CHECK_ARG(W <= 65535 && (H + 3) / 4 <= 65535, "finalize: extent (%d, %d) exceeds the launch grid", W, H);
+    B200SEG_CHECK_ARG(W <= 65535, "finalize: extent %d exceeds the launch grid", W);
     if (vec) {
-        dim3 grid(static_cast<unsigned>((D / 4 + 63) / 64), static_cast<unsigned>((H + 3) / 4), static_cast<unsigned>(W));
+        dim3 grid(static_cast<unsigned>((1LL * H * (D / 4) + kThreads - 1) / kThreads), static_cast<unsigned>(W));
         finalize_kernel<4><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1], border[2], W, H, D,
                                                     probs, reinterpret_cast<long long*>(labels_i64), labels_u8);
     } else {
-        dim3 grid(static_cast<unsigned>((D + 63) / 64), static_cast<unsigned>((H + 3) / 4), static_cast<unsigned>(W));
+        dim3 grid(static_cast<unsigned>((1LL * H * D + kThreads - 1) / kThreads), static_cast<unsigned>(W));
         finalize_kernel<1><<<grid, kThreads, 0, s>>>(out, c, pw, ph, pd, cw, ch, cd, border[0], border[1], border[2], W, H, D,
                                                     probs, reinterpret_cast<long long*>(labels_i64), labels_u8);
     }
