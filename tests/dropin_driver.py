@@ -7,9 +7,11 @@
   * the dataset is the reference's ``SubjectFolder`` over a temporary folder tree, fed by a synthetic in-memory
     ``SubjectLoader``; the transform pipeline is ``CustomRemapLabels`` (a label swap) + ``CustomOneHot`` -- so that
     ``add_evaluation_labels`` has a real history to invert (reference prediction.py:155-170);
-  * the TRAINING step (segmentation_trainer.py:162-180) is driven with a stub train predictor / criterion / optimizer
-    -- training kernels are SURVEY.md section 8 f3, not built -- the VALIDATION branch (:196-242) is the real thing:
-    ``PatchPredict.predict`` -> ``add_evaluation_labels`` -> ``SegmentationEvaluator`` through the scheduled evaluation.
+  * on the GPU the TRAINING step (segmentation_trainer.py:162-180) is the real thing too: ``StandardPredict(['X', 'y'])``
+    over the b200 model in training mode, the b200 criterion, backward through the device autograd function, the
+    reference's SGD step (on a CPU-only box a stub train predictor / criterion / optimizer stand in, the device path
+    refuses CPU tensors); then the VALIDATION branch (:196-242): ``PatchPredict.predict`` -> ``add_evaluation_labels`` ->
+    ``SegmentationEvaluator`` through the scheduled evaluation.
 
 Prints one JSON line: which files served the key modules, and either the evaluation results (+ the oracle comparison)
 or the error raised on the way (on a box without a GPU the predictor must refuse, loudly)."""
