@@ -15,34 +15,36 @@ from .evaluator import Evaluator
 from .labeled_tensor import LabeledTensor
 
 
+def _instance_detected(overlaps, own_volume, other_volumes, min_recall, contribution_threshold, min_precision) -> bool:
+    """One row of the detection test: ``overlaps[j]`` = voxels this instance shares with instance j + 1 of the other
+    map, ``own_volume`` its voxel count, ``other_volumes[j]`` the voxel count of that other instance."""
+    covered = overlaps.sum()
+    if covered / own_volume < min_recall:
+        return False                                    # the instance is barely touched by the other map
+    reached = 0.0
+    for j in torch.argsort(overlaps, descending=True):  # largest contributor first
+        if overlaps[j] / other_volumes[j] < min_precision:
+            return False                                # a main contributor mostly lies outside this instance
+        reached += overlaps[j] / covered
+        if reached >= contribution_threshold:
+            return True
+    return False                                        # unreachable for covered > 0; the reference appends nothing here
+
+
 def msseg_detection_test(overlap_histogram, min_recall=0.1, contribution_threshold=0.65, min_precision=0.3):
     """Detection test of "Objective Evaluation of Multiple Sclerosis Lesion Segmentation using a Data Management and
     Processing Infrastructure" (MSSEG 2016 / MSSEG-2 2021), reference instance_segmentation_evaluator.py:10-72.
 
     ``overlap_histogram``: (N + 1, M + 1), element [i, j] = voxels shared by target component i and predicted component
     j (0 = background).  Returns a boolean tensor of length N: target instance i is detected when it is covered by at
-    least ``min_recall`` and the predicted instances that make up the first ``contribution_threshold`` of its overlap
-    each have precision >= ``min_precision``."""
-    n = overlap_histogram.shape[0] - 1
-    target_volume = overlap_histogram.sum(dim=1)
-    prediction_volume = overlap_histogram.sum(dim=0)
-    detected = []
-    for i in range(1, n + 1):
-        target_tp = overlap_histogram[i, 1:].sum()
-        if target_tp / target_volume[i] < min_recall:
-            detected.append(False)
-            continue
-        order = torch.argsort(overlap_histogram[i, 1:], descending=True) + 1
-        contribution_total = 0.0
-        for j in order:
-            if overlap_histogram[i, j] / prediction_volume[j] < min_precision:
-                detected.append(False)
-                break
-            contribution_total += overlap_histogram[i, j] / target_tp
-            if contribution_total >= contribution_threshold:
-                detected.append(True)
-                break
-    return torch.tensor(detected)
+    least ``min_recall`` (alpha of the paper) and the predicted instances that make up the first
+    ``contribution_threshold`` (gamma) of its overlap each have precision >= ``min_precision`` (1 - beta)."""
+    row_volume = overlap_histogram.sum(dim=1)
+    column_volume = overlap_histogram.sum(dim=0)
+    flags = [_instance_detected(overlap_histogram[i, 1:], row_volume[i], column_volume[1:], min_recall,
+                                contribution_threshold, min_precision)
+             for i in range(1, overlap_histogram.shape[0])]
+    return torch.tensor(flags)
 
 
 def instance_overlap(pred_labels: torch.Tensor, target_labels: torch.Tensor, connectivity: int = 2):
@@ -86,45 +88,34 @@ class InstanceSegmentationEvaluator(Evaluator):
         self.detection_test = detection_test
         self.detection_test_params = {} if detection_test_params is None else detection_test_params
 
+    def _subject_stats(self, subject) -> Dict[str, Any]:
+        """All statistics of one subject from its (N + 1) x (M + 1) overlap table (reference :131-160)."""
+        images = [subject[self.prediction_label_map_name], subject[self.target_label_map_name]]
+        pred_data, targ_data = (im.data if hasattr(im, "data") else im["data"] for im in images)
+        table, n_target, n_pred = instance_overlap(pred_data, targ_data, self.connectivity)
+        hits_target = self.detection_test(table, **self.detection_test_params).sum()
+        hits_pred = self.detection_test(table.T, **self.detection_test_params).sum()
+        det_recall, det_precision = hits_target / n_target, hits_pred / n_pred
+        # voxel-level counts: foreground = any component
+        tp, fp, tn, fn = table[1:, 1:].sum(), table[0, 1:].sum(), table[0, 0].sum(), table[1:, 0].sum()
+        return {
+            'target_components': n_target, 'predicted_components': n_pred,
+            'target_detections': hits_target, 'predicted_detections': hits_pred,
+            'detection_recall': det_recall, 'detection_precision': det_precision,
+            'detection_f1': 2 * (det_recall * det_precision) / (det_recall + det_precision),
+            'target_volume': tp + fn, 'prediction_volume': tp + fp,
+            'TP': tp, 'FP': fp, 'TN': tn, 'FN': fn,
+            'dice': 2 * tp / (2 * tp + fp + fn), 'jaccard': tp / (tp + fp + fn),
+            'precision': tp / (tp + fp), 'recall': tp / (tp + fn),
+        }
+
     def __call__(self, subjects):
-        subject_names = [subject['name'] for subject in subjects]
-        subject_stats = LabeledTensor(dim_names=['subject', 'stat'],
-                                      dim_keys=[subject_names, self.stats_to_output])
+        table = LabeledTensor(dim_names=['subject', 'stat'],
+                              dim_keys=[[subject['name'] for subject in subjects], self.stats_to_output])
         for subject in subjects:
-            pred = subject[self.prediction_label_map_name]
-            targ = subject[self.target_label_map_name]
-            pred_data = pred["data"] if not hasattr(pred, "data") else pred.data
-            targ_data = targ["data"] if not hasattr(targ, "data") else targ.data
-            overlap_histogram, N, M = instance_overlap(pred_data, targ_data, self.connectivity)
-            target_detected = self.detection_test(overlap_histogram, **self.detection_test_params)
-            prediction_detected = self.detection_test(overlap_histogram.T, **self.detection_test_params)
-            detection_recall = target_detected.sum() / N
-            detection_precision = prediction_detected.sum() / M
-            detection_f1 = 2 * (detection_recall * detection_precision) / (detection_recall + detection_precision)
-            TP = overlap_histogram[1:, 1:].sum()
-            FP = overlap_histogram[0, 1:].sum()
-            TN = overlap_histogram[0, 0].sum()
-            FN = overlap_histogram[1:, 0].sum()
-            stats = {
-                'target_components': N,
-                'predicted_components': M,
-                'target_detections': target_detected.sum(),
-                'predicted_detections': prediction_detected.sum(),
-                'detection_recall': detection_recall,
-                'detection_precision': detection_precision,
-                'detection_f1': detection_f1,
-                'target_volume': TP + FN,
-                'prediction_volume': TP + FP,
-                'TP': TP, 'FP': FP, 'TN': TN, 'FN': FN,
-                'dice': 2 * TP / (2 * TP + FP + FN),
-                'jaccard': TP / (TP + FP + FN),
-                'precision': TP / (TP + FP),
-                'recall': TP / (TP + FN),
-            }
-            for stat_name in self.stats_to_output:
-                value = stats[stat_name]
-                if isinstance(value, torch.Tensor):
-                    value = value.item()
-                subject_stats[subject['name'], stat_name] = value
-        summary_stats = subject_stats.compute_summary_stats(self.summary_stats_to_output)
-        return {'subject_stats': subject_stats.to_dataframe(), 'summary_stats': summary_stats}
+            stats = self._subject_stats(subject)
+            for key in self.stats_to_output:
+                value = stats[key]
+                table[subject['name'], key] = value.item() if isinstance(value, torch.Tensor) else value
+        return {'subject_stats': table.to_dataframe(),
+                'summary_stats': table.compute_summary_stats(self.summary_stats_to_output)}
