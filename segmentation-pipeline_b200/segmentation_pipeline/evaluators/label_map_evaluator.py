@@ -28,36 +28,39 @@ class LabelMapEvaluator(Evaluator):
         self.stats_to_output = stats_to_output
         self.summary_stats_to_output = summary_stats_to_output
 
-        curve_stats = ['error', 'absolute_error', 'squared_error', 'percent_diff']
-        if any(stat in curve_stats for stat in self.stats_to_output):
-            if curve_params is None:
-                raise ValueError("curve_params must be provided")
-            if curve_attribute is None:
-                raise ValueError("curve_attribute must be provided")
+        needs_curve = {'error', 'absolute_error', 'squared_error', 'percent_diff'} & set(self.stats_to_output)
+        for argument, value in (("curve_params", curve_params), ("curve_attribute", curve_attribute)):
+            if needs_curve and value is None:
+                raise ValueError(f"{argument} must be provided")
+        self.poly_func = None
         if curve_params is not None and curve_attribute is not None:
-            self.poly_func = {label: np.poly1d(param) for label, param in curve_params.items()}
-        else:
-            self.poly_func = None
+            self.poly_func = {name: np.poly1d(coefficients) for name, coefficients in curve_params.items()}
+
+    def _label_stats(self, subject, label_name, voxels: int) -> Dict[str, torch.Tensor]:
+        """Volume of one label and, when a growth curve was given, its deviation from the curve at the subject's
+        ``curve_attribute`` (reference :83-99)."""
+        volume = torch.tensor(voxels)                          # int64, like label.sum() in the reference
+        out = {'volume': volume}
+        if self.poly_func is not None:
+            expected = self.poly_func[label_name](subject[self.curve_attribute])
+            delta = volume - expected
+            out['error'], out['absolute_error'], out['squared_error'] = delta, abs(delta), delta ** 2
+            out['percent_diff'] = (delta / expected) * 100
+        return out
 
     def __call__(self, subjects):
         label_values = subjects[0][self.label_map_name]['label_values']
-        label_names = list(label_values.keys())
-        subject_names = [subject['name'] for subject in subjects]
-        subject_stats = LabeledTensor(dim_names=['subject', 'label', 'stat'],
-                                      dim_keys=[subject_names, label_names, self.stats_to_output])
+        names = list(label_values.keys())
+        table = LabeledTensor(dim_names=['subject', 'label', 'stat'],
+                              dim_keys=[[subject['name'] for subject in subjects], names, self.stats_to_output])
         for subject in subjects:
             image = subject[self.label_map_name]
-            data = image["data"] if not hasattr(image, "data") else image.data
+            data = image.data if hasattr(image, "data") else image["data"]
+            # one device histogram pass: a map against itself puts every label's volume on the diagonal (its "TP")
             counts = confusion_counts(data, data, label_values)
-            for label_name in label_names:
-                volume = torch.tensor(counts[label_name][0])   # TP of a map against itself = its volume (int64)
-                stats = {'volume': volume}
-                if self.poly_func is not None:
-                    predicted = self.poly_func[label_name](subject[self.curve_attribute])
-                    error = volume - predicted
-                    stats.update({'error': error, 'absolute_error': abs(error), 'squared_error': error ** 2,
-                                  'percent_diff': (error / predicted) * 100})
-                for stat_name in self.stats_to_output:
-                    subject_stats[subject['name'], label_name, stat_name] = stats[stat_name].item()
-        summary_stats = subject_stats.compute_summary_stats(self.summary_stats_to_output)
-        return {'subject_stats': subject_stats.to_dataframe(), 'summary_stats': summary_stats}
+            for label_name in names:
+                stats = self._label_stats(subject, label_name, counts[label_name][0])
+                for key in self.stats_to_output:
+                    table[subject['name'], label_name, key] = stats[key].item()
+        return {'subject_stats': table.to_dataframe(),
+                'summary_stats': table.compute_summary_stats(self.summary_stats_to_output)}
