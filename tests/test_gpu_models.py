@@ -443,3 +443,37 @@ def test_slab_mode_single_rank_equals_patch_predict():
     finally:
         set_precision("auto")
     assert torch.equal(labels, labels2) and torch.equal(probs, probs2)
+
+
+def test_label_map_evaluator_growth_curve_statistics():
+    """LabelMapEvaluator with ``curve_params`` / ``curve_attribute`` (reference label_map_evaluator.py:83-99): volume
+    error against a per-label polynomial of a subject attribute; missing arguments raise like the reference."""
+    from segmentation_pipeline import _tio
+    from segmentation_pipeline.evaluators import LabelMapEvaluator
+    rng = np.random.default_rng(5)
+    label_values = {"left": 1, "right": 2}
+    curve = {"left": np.array([2.0, 100.0]), "right": np.array([0.5, -3.0, 400.0])}
+    stats = ("volume", "error", "absolute_error", "squared_error", "percent_diff")
+    subjects, maps = [], []
+    for i, age in enumerate((20.0, 63.5)):
+        data = rng.integers(0, 3, size=(1, 16, 12, 10))
+        maps.append(data)
+        subjects.append(_tio.Subject(name=f"s{i}", age=age,
+                                     pred=_tio.LabelMap(tensor=torch.from_numpy(data), label_values=label_values)))
+    res = LabelMapEvaluator("pred", curve_params=curve, curve_attribute="age", stats_to_output=stats)(subjects)
+    frame = res["subject_stats"]
+    row = 0
+    for i, subject in enumerate(subjects):
+        for name, value in label_values.items():
+            volume = torch.tensor(int((maps[i] == value).sum()))
+            expected = np.poly1d(curve[name])(subject["age"])
+            err = volume - expected
+            want = {"volume": volume, "error": err, "absolute_error": abs(err), "squared_error": err ** 2,
+                    "percent_diff": (err / expected) * 100}
+            for st in stats:
+                assert float(frame.iloc[row][st]) == float(want[st].item()), (i, name, st)
+            row += 1
+    with pytest.raises(ValueError):
+        LabelMapEvaluator("pred", stats_to_output=("volume", "error"))
+    with pytest.raises(ValueError):
+        LabelMapEvaluator("pred", curve_params=curve, stats_to_output=("percent_diff",))
