@@ -729,7 +729,10 @@ extern "C" int b200seg_softmax_backward(const float* probs, const float* dprobs,
 }
 
 static int mma_slices(int groups, int ksize) {
-    int slices = (3 * 148 + groups * ksize - 1) / (groups * ksize);
+    // one full wave of resident blocks: 2 per SM for the 9-warp 3^3 kernel, 1 per SM for the 16-warp 4^3 kernel
+    // (the first choice, 3 * 148 blocks, ran the 3^3 kernel as 1.5 waves: the second wave half empty)
+    const int slots = (ksize == 3 ? 2 : 1) * 148;
+    int slices = slots / (groups * ksize);
     return slices < 1 ? 1 : slices;
 }
 
