@@ -728,6 +728,14 @@ extern "C" int b200seg_softmax_backward(const float* probs, const float* dprobs,
     return check_launch("softmax_backward");
 }
 
+static long long simt_slices(long long pairs, int ksize) {
+    // at most three full waves of resident blocks (2 per SM for the 9-warp 3^3 kernel, 1 per SM for the 16-warp 4^3
+    // one); rounding DOWN keeps a nearly empty fourth wave from forming (6 * 148 / (pairs * k), rounded up, did that)
+    const long long slots = (ksize == 3 ? 2 : 1) * 148;
+    const long long slices = 3 * slots / (pairs * ksize);
+    return slices < 1 ? 1 : slices;
+}
+
 static int mma_slices(int groups, int ksize) {
     // one full wave of resident blocks: 2 per SM for the 9-warp 3^3 kernel, 1 per SM for the 16-warp 4^3 kernel
     // (the first choice, 3 * 148 blocks, ran the 3^3 kernel as 1.5 waves: the second wave half empty)
@@ -739,8 +747,7 @@ static int mma_slices(int groups, int ksize) {
 extern "C" int64_t b200seg_wgrad_scratch_floats(int32_t a_channels, int32_t b_channels, int32_t ksize) {
     // the larger of the two kernels' needs (CUDA-core partials / tensor-core 48 x 40 tiles)
     const int64_t pairs = static_cast<int64_t>((a_channels + 7) / 8) * ((b_channels + 7) / 8);
-    int64_t slices = (6 * 148 + pairs * ksize - 1) / (pairs * ksize);
-    if (slices < 1) slices = 1;
+    const int64_t slices = simt_slices(pairs, ksize);
     const int64_t simt = slices * ksize * ksize * ksize * pairs * 64;
     const int groups = ((a_channels + kMmaA - 1) / kMmaA) * ((b_channels + kMmaB - 1) / kMmaB);
     const int64_t mma = static_cast<int64_t>(mma_slices(groups, ksize)) * ksize * ksize * ksize * groups * kMmaA * kMmaB;
@@ -823,8 +830,7 @@ extern "C" int b200seg_wgrad(b200seg_view a, b200seg_view b, int32_t ksize, int3
     g.items = a.n * a.z * g.plane_blocks;
     g.cb8n = cb8n;
     g.inv_px = 1.0f / static_cast<float>(a.x);
-    long long slices = (6 * 148 + 1LL * pairs * ksize - 1) / (1LL * pairs * ksize);
-    if (slices < 1) slices = 1;
+    long long slices = simt_slices(pairs, ksize);
     if (slices > 1LL * a.n * a.z) slices = 1LL * a.n * a.z;      // a block owns whole (n, z) rows
     B200SEG_CHECK_ARG(pairs <= 65535, "wgrad: too many channel chunk pairs");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
