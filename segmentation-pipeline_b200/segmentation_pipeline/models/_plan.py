@@ -591,8 +591,18 @@ def block_tz(mode: int, j: int, zpar: int) -> int:
 
 def pack_tc_weight(mode: int, phys: torch.Tensor, cin_chunks: int, cout: int) -> torch.Tensor:
     """bf16 operand image for b200seg_conv3d_tc: [pass][image][step][k-half][row][8] with
-    row = (plane block j, cout) followed by 16 zero rows; ``phys`` from physical_weight()."""
-    return pack_tc_image(mode, phys, cin_chunks, cout).to(torch.bfloat16).contiguous()
+    row = (plane block j, cout) followed by 16 zero rows; ``phys`` from physical_weight().
+
+    The layout is defined by pack_tc_image(); after the first weight of a geometry the image is produced through the
+    cached gather index instead (one ``take``): re-packing a whole network -- every time the weights changed between two
+    ``eval()`` forwards, e.g. the trainer's periodic validation -- costs milliseconds instead of ~0.5 s of Python loops."""
+    try:
+        idx = tc_gather_index(mode, cin_chunks, cout)
+    except UnsupportedModule:
+        return pack_tc_image(mode, phys, cin_chunks, cout).to(torch.bfloat16).contiguous()
+    flat = phys.reshape(-1)
+    img = torch.where(idx >= 0, flat[idx.clamp(min=0)], torch.zeros((), dtype=flat.dtype))
+    return img.to(torch.bfloat16).contiguous()
 
 
 _TC_GATHER = {}
